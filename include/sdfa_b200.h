@@ -1,0 +1,141 @@
+/* sdfa_b200.h -- C ABI of the B200-native dgrad -> mesh reconstruction path.
+ *
+ * Drop-in boundary for the ONE hot path of chaiyujin/sdfa-2019 that this library replaces:
+ * `deformation.get_mesh` and friends (reference: deformation/cpp/src/pybind.cpp:129-153, which
+ * forward to deformation::TriangleDeformation, deformation/cpp/src/deform_triangle.hpp:12-85).
+ * Plain pointers and sizes only; no torch / pybind / Eigen types.  All compute entry points
+ * run hand-written sm_100a CUDA kernels; there is no CPU fallback -- if no CUDA device is
+ * usable they return SDFA_ERR_CUDA and sdfa_last_error() says why.
+ *
+ * Conventions
+ *   - every function returns an int status (SDFA_OK == 0) unless stated otherwise;
+ *     sdfa_last_error() returns a thread-local, human-readable message for the last failure
+ *     (the reference instead logs and calls exit(1): deformation/cpp/src/log.hpp:32-33)
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
+ *     ordinary host memory; `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - dgrad layout: [N, n_src_tris, 9] row-major, per triangle
+ *     [s00,s01,s02,s11,s12,s22,r01,r02,r12]  (deform_triangle_impl.hpp:232-240;
+ *     speech_anime/model/model.py:246-257)
+ *   - vertex layout: [N, n_verts, 3] float32 row-major (pybind.cpp:108)
+ */
+#ifndef SDFA_B200_H_
+#define SDFA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFA_OK            0
+#define SDFA_ERR_ARG       1   /* bad argument (shape, index out of range, NULL, duplicate constraint) */
+#define SDFA_ERR_FACTOR    2   /* A^T A + reg*I not positive definite (reference: setStaticTarget returns false) */
+#define SDFA_ERR_CUDA      3   /* CUDA runtime failure or no usable device */
+#define SDFA_ERR_STATE     4   /* call order (e.g. decode before sdfa_set_pca) */
+#define SDFA_ERR_UNSUPPORTED 5
+
+typedef struct sdfa_handle sdfa_handle;   /* opaque: one template + factor + device plan */
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces TriangleDeformation::setStaticTarget (deform_triangle_impl.hpp:7-142; marshalled by
+ * SetTarget, pybind.cpp:13-33).  Builds A, A^T A + reg*I, its fp64 Cholesky factor and the device
+ * schedules, uploads them to CUDA device `device`.
+ *   verts      [n_verts,3] float32        tris  [n_tris,3] uint32
+ *   cnsts      [n_cnsts] uint32 or NULL   corr_count [n_tris] uint32 or NULL (deform_triangle_impl.hpp:18-22)
+ * `device` < 0 builds the host-side analysis only (no CUDA call is made; compute entry points then
+ * fail with SDFA_ERR_CUDA) -- used by CPU-only tests of the host logic. */
+int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32_t *tris, int n_tris,
+                const uint32_t *cnsts, int n_cnsts, const uint32_t *corr_count, double reg, int device);
+void sdfa_destroy(sdfa_handle *h);
+
+/* Counts; any out pointer may be NULL.  n_eq = number of equation blocks, n_active = blocks that touch
+ * a free vertex, nnz_l = nonzeros of the Cholesky factor.  (IsSame, pybind.cpp:119-126, compares the
+ * first three.) */
+int sdfa_info(const sdfa_handle *h, int *n_verts, int *n_tris, int *n_cnsts, int *n_free, int *n_eq,
+              int *n_active, long long *nnz_l);
+
+const char *sdfa_last_error(void);
+
+/* ---- constraint positions --------------------------------------------------------------- */
+
+/* Positions of the constrained vertices used by the following reconstruct calls
+ * (`_cnst_verts`, deform_triangle_impl.hpp:272-283, :302-308).  [n_cnsts,3] float32 host, or NULL to
+ * use the template's own positions (the way viewer/frame.py:130-132 calls it).  Recomputes the fp64
+ * base solution on the host. */
+int sdfa_set_constraint_positions(sdfa_handle *h, const float *cnst_verts_host);
+
+/* Correspondence mode of getMeshFromDeformationGradients (deform_triangle_impl.hpp:254-268):
+ * corr_count [n_tris], corr_faces [n_eq] uint32 host arrays; corr_count == NULL switches back to
+ * "block k reads source triangle k".  n_src_tris = triangles per source dgrad row. */
+int sdfa_set_correspondences(sdfa_handle *h, const uint32_t *corr_count, const uint32_t *corr_faces,
+                             int n_src_tris);
+
+/* ---- reconstruction: dgrad -> vertices (getMeshFromDeformationGradients, impl.hpp:215-310) ---- */
+
+/* Batched, device buffers, stream-ordered.  dgrad_dev [n_frames, n_src_tris*9] float32 with row stride
+ * `dgrad_stride` floats (0 = dense); out_dev [n_frames, n_verts, 3] float32. */
+int sdfa_reconstruct_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames,
+                         float *out_dev, void *stream);
+
+/* Batched, HOST buffers (float32 in, float32 out): copies in, runs the kernels, copies out, synchronises. */
+int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host);
+
+/* The legacy single-frame call: float64 dgrad in, float32 vertices out (GetMeshFromGrad,
+ * pybind.cpp:101-117).  cnst_verts / corr_* as in the reference call; NULL = not given. */
+int sdfa_get_mesh_f64(sdfa_handle *h, const double *dgrad_host, long long dgrad_len,
+                      const float *cnst_verts_host, const uint32_t *corr_count, const uint32_t *corr_faces,
+                      long long corr_faces_len, float *out_host);
+
+/* Raw-matrix variant (getMeshFromDeformationMatrix, impl.hpp:382-440; GetMeshFromMat pybind.cpp:60-74):
+ * dmat [n_tris,9] float64 row-major T per triangle. */
+int sdfa_get_mesh_from_dm_f64(sdfa_handle *h, const double *dmat_host, long long dmat_len,
+                              const float *cnst_verts_host, float *out_host);
+
+/* ---- PCA decode (PcaInversion.forward x2 + interleave: output_module.py:115-116, model.py:246-257) ---- */
+
+/* compT_scale [n_tris*6, k_scale], means_scale [n_tris*6], compT_rotat [n_tris*3, k_rotat],
+ * means_rotat [n_tris*3]; float32 host arrays, copied (only active triangles' rows are kept on device). */
+int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_scale, int k_scale,
+                 const float *compT_rotat, const float *means_rotat, int k_rotat);
+
+/* coefficients -> vertices, device buffers: coeff_scale_dev [n_frames,k_scale], coeff_rotat_dev
+ * [n_frames,k_rotat] float32; out_dev [n_frames,n_verts,3]. */
+int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
+                                int n_frames, float *out_dev, void *stream);
+int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host,
+                                 int n_frames, float *out_host);
+
+/* decode only: writes the full reference-layout dgrad [n_frames, n_tris*9] (inactive triangles included)
+ * -- the tensor data_to_anime_feat returns.  Needs the full basis: pass keep_full=1 here. */
+int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
+                          int n_frames, float *dgrad_dev, void *stream);
+
+/* ---- inverse path: meshes -> dgrad (getDeformationGradients, impl.hpp:144-213) ----------- */
+
+/* Stateless like the reference (GetDeformGrad, pybind.cpp:78-99): verts_a/verts_b [n_verts,3] float32,
+ * tris [n_tris,3] uint32 host; out [n_tris*9] float64 host.  as_matrix != 0 returns row-major T
+ * instead (getDeformationMatrix, impl.hpp:313-380).  Runs on CUDA device `device`. */
+int sdfa_get_deform_grad_host(const float *verts_a, const float *verts_b, int n_verts, const uint32_t *tris,
+                              int n_tris, double eps, int as_matrix, int device, double *out_host);
+
+/* ---- measurement / introspection -------------------------------------------------------- */
+
+/* Kernel launches issued by this library since process start (for bench.py's gpu_launches). */
+long long sdfa_launch_count(void);
+
+/* Per-stage device time of the most recent *_dev / *_host reconstruct call when timing is enabled
+ * with sdfa_set_timing(h, 1): ms[0]=decode, ms[1]=assembly, ms[2]=solve, ms[3]=fill.  Enabling
+ * timing adds event records + a synchronise per call. */
+int sdfa_set_timing(sdfa_handle *h, int enable);
+int sdfa_last_timing(const sdfa_handle *h, float ms[4]);
+
+/* Host-side plan introspection for tests (no CUDA needed).  `what` selects a buffer; returns its size in
+ * bytes, copies min(size, cap) bytes into dst when dst != NULL.  See csrc/plan.hpp for the list. */
+long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long long cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFA_B200_H_ */

@@ -1,0 +1,524 @@
+// api.cpp -- the C ABI declared in include/sdfa_b200.h: handle lifetime, uploads, and the host side of
+// every entry point.  Mirrors what deformation/cpp/src/pybind.cpp:13-126 does around the reference solver
+// (argument checks, singleton state) but reports errors through status codes instead of exit(1).
+#include "../../include/sdfa_b200.h"
+#include "device_plan.hpp"
+#include "plan.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace sdfa;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(SDFA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+struct sdfa_handle {
+    HostPlan host;
+    DevicePlan dev;
+    std::vector<void *> allocs;           // every device allocation, freed in destroy
+    std::vector<int32_t> eq_src_host;     // current equation -> source triangle map
+    int n_src_tris = 0;
+    bool has_pca = false, has_full_pca = false;
+    std::vector<int32_t> needed_tris;     // source triangles the active equations read (decode keeps these)
+    // growable scratch
+    float *rhs = nullptr; size_t rhs_cap = 0;          // [frames][n_free][3]
+    float *dgrad_c = nullptr; size_t dgrad_c_cap = 0;  // compact decoded dgrad
+    float *io_in = nullptr; size_t io_in_cap = 0;      // staging for *_host entry points
+    float *io_out = nullptr; size_t io_out_cap = 0;
+    float *io_in2 = nullptr; size_t io_in2_cap = 0;
+    bool timing = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+};
+
+const char *sdfa_last_error(void) { return g_err.c_str(); }
+
+template <typename T>
+static int upload(sdfa_handle *h, const std::vector<T> &v, const T **dst) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    h->allocs.push_back(p);
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = static_cast<const T *>(p);
+    return SDFA_OK;
+}
+template <typename T>
+static int upload_mut(sdfa_handle *h, const std::vector<T> &v, T **dst) {
+    const T *p = nullptr;
+    int rc = upload(h, v, &p);
+    *dst = const_cast<T *>(p);
+    return rc;
+}
+static int grow(float **buf, size_t *cap, size_t floats) {
+    if (*cap >= floats) return SDFA_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    CUDA_TRY(cudaMalloc((void **)buf, floats * sizeof(float)));
+    *cap = floats;
+    return SDFA_OK;
+}
+
+static void default_eq_src(sdfa_handle *h) {
+    // no correspondences given at call time: block i reads source triangle i for i < n_tris, the remaining
+    // blocks stay zero (deform_triangle_impl.hpp:224, :249-253)
+    const HostPlan &p = h->host;
+    h->eq_src_host.assign(p.n_eq, -2);
+    for (int k = 0; k < std::min(p.n_eq, p.n_tris); ++k) h->eq_src_host[k] = k;
+    h->n_src_tris = p.n_tris;
+}
+
+static int upload_eq_src(sdfa_handle *h) {
+    if (h->dev.device < 0) return SDFA_OK;
+    CUDA_TRY(cudaSetDevice(h->dev.device));
+    CUDA_TRY(cudaMemcpy(h->dev.eq_src, h->eq_src_host.data(), h->eq_src_host.size() * 4, cudaMemcpyHostToDevice));
+    // which source triangles are read at all, and the same map into the compact decoded layout
+    const HostPlan &p = h->host;
+    std::vector<int32_t> needed;
+    for (int k : p.active_eq) if (h->eq_src_host[k] >= 0) needed.push_back(h->eq_src_host[k]);
+    std::sort(needed.begin(), needed.end());
+    needed.erase(std::unique(needed.begin(), needed.end()), needed.end());
+    std::vector<int32_t> compact(p.n_eq);
+    for (int k = 0; k < p.n_eq; ++k) {
+        int s = h->eq_src_host[k];
+        if (s >= 0) {
+            auto it = std::lower_bound(needed.begin(), needed.end(), s);
+            compact[k] = (it != needed.end() && *it == s) ? (int32_t)(it - needed.begin()) : -1;
+        } else compact[k] = s;
+    }
+    CUDA_TRY(cudaMemcpy(h->dev.eq_src_compact, compact.data(), compact.size() * 4, cudaMemcpyHostToDevice));
+    if (needed != h->needed_tris) { h->needed_tris = needed; h->has_pca = false; }   // basis rows must be re-packed
+    h->dev.n_needed = (int)needed.size();
+    return SDFA_OK;
+}
+
+static int upload_base(sdfa_handle *h) {
+    if (h->dev.device < 0) return SDFA_OK;
+    const HostPlan &p = h->host;
+    std::vector<float> hi(p.x_base.size()), lo(p.x_base.size());
+    for (size_t i = 0; i < hi.size(); ++i) {
+        hi[i] = (float)p.x_base[i];
+        lo[i] = (float)(p.x_base[i] - (double)hi[i]);
+    }
+    CUDA_TRY(cudaSetDevice(h->dev.device));
+    CUDA_TRY(cudaMemcpy(h->dev.xbase_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->dev.xbase_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+    if (p.n_cnsts > 0)
+        CUDA_TRY(cudaMemcpy(h->dev.cnst_pos, p.cnst_pos.data(), p.cnst_pos.size() * 4, cudaMemcpyHostToDevice));
+    return SDFA_OK;
+}
+
+int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32_t *tris, int n_tris,
+                const uint32_t *cnsts, int n_cnsts, const uint32_t *corr_count, double reg, int device) {
+    if (!out || !verts || !tris || n_verts <= 0 || n_tris <= 0 || n_cnsts < 0 || (n_cnsts > 0 && !cnsts))
+        return fail(SDFA_ERR_ARG, "sdfa_create: bad arguments");
+    *out = nullptr;
+    sdfa_handle *h = new sdfa_handle();
+    HostPlan &p = h->host;
+    p.n_verts = n_verts; p.n_tris = n_tris; p.n_cnsts = n_cnsts; p.reg = reg;
+    p.verts.assign(verts, verts + (size_t)n_verts * 3);
+    p.tris.assign(tris, tris + (size_t)n_tris * 3);
+    if (n_cnsts) p.cnsts.assign(cnsts, cnsts + n_cnsts);
+    if (corr_count) p.corr_count.assign(corr_count, corr_count + n_tris);
+    std::string err;
+    int rc;
+    try {
+        if ((rc = build_system(p, err)) != 0) { delete h; return fail(SDFA_ERR_ARG, "sdfa_create: " + err); }
+        if ((rc = order_and_factor(p, err)) != 0) { delete h; return fail(SDFA_ERR_FACTOR, "sdfa_create: " + err); }
+        compute_base_solution(p, nullptr);
+        build_solve_program(p, /*piece_cap=*/64);
+        build_assembly_plan(p, /*rows_per_block=*/128);
+    } catch (const std::exception &e) {
+        delete h;
+        return fail(SDFA_ERR_UNSUPPORTED, std::string("sdfa_create: ") + e.what());
+    }
+    default_eq_src(h);
+    h->dev.device = device;
+    h->dev.n_verts = n_verts; h->dev.n_tris = n_tris; h->dev.n_cnsts = n_cnsts;
+    h->dev.n_free = p.n_free; h->dev.n_eq = p.n_eq;
+    if (device >= 0) {
+        auto up = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(device));
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+            if (prop.major < 10)
+                return fail(SDFA_ERR_CUDA, "sdfa_create: device is not sm_100-class (kernels are built for sm_100a only)");
+            h->dev.sm_count = prop.multiProcessorCount;
+            if (solve_smem_bytes(p.prog.n_slots) > (size_t)prop.sharedMemPerBlockOptin)
+                return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: solve state (" + std::to_string(p.prog.n_slots) +
+                                                      " rows) does not fit in shared memory");
+            DevicePlan &d = h->dev;
+            const AssemblyPlan &ap = p.asmplan;
+            std::vector<int4> blocks;
+            for (auto &b : ap.blocks) blocks.push_back(make_int4(b.eq_begin, b.eq_end, b.row_begin, b.row_end));
+            int r;
+            if ((r = upload_mut(h, blocks, &d.asm_blocks))) return r;
+            if ((r = upload(h, ap.eq_id, &d.asm_eq_id))) return r;
+            if ((r = upload(h, ap.eq_u, &d.asm_eq_u))) return r;
+            if ((r = upload(h, ap.row_perm, &d.asm_row_perm))) return r;
+            if ((r = upload(h, ap.row_ptr, &d.asm_row_ptr))) return r;
+            if ((r = upload(h, ap.inc, &d.asm_inc))) return r;
+            d.n_asm_blocks = (int)ap.blocks.size();
+            d.asm_max_eq = ap.max_eq_per_block;
+            d.asm_max_rows = ap.max_rows_per_block;
+            std::vector<int32_t> tmp(p.n_eq, 0);
+            if ((r = upload_mut(h, tmp, &d.eq_src))) return r;
+            if ((r = upload_mut(h, tmp, &d.eq_src_compact))) return r;
+            if ((r = upload(h, p.prog.bytes, &d.prog))) return r;
+            if ((r = upload(h, p.prog.stage_off, &d.stage_off))) return r;
+            d.n_stages = (int)p.prog.stage_off.size() - 1;
+            d.n_slots = p.prog.n_slots;
+            std::vector<int32_t> row_vert(p.n_free);
+            for (int i = 0; i < p.n_free; ++i) row_vert[i] = p.free_to_vi[p.perm[i]];
+            if ((r = upload(h, row_vert, &d.row_vert))) return r;
+            std::vector<float> z((size_t)p.n_free * 3, 0.f);
+            if ((r = upload_mut(h, z, &d.xbase_hi))) return r;
+            if ((r = upload_mut(h, z, &d.xbase_lo))) return r;
+            std::vector<int32_t> cv(p.cnsts.begin(), p.cnsts.end());
+            if ((r = upload(h, cv, &d.cnst_vert))) return r;
+            std::vector<float> cz((size_t)p.n_cnsts * 3, 0.f);
+            if ((r = upload_mut(h, cz, &d.cnst_pos))) return r;
+            if ((r = upload_base(h))) return r;
+            if ((r = upload_eq_src(h))) return r;
+            return SDFA_OK;
+        };
+        rc = up();
+        if (rc != SDFA_OK) { std::string keep = g_err; sdfa_destroy(h); g_err = keep; return rc; }
+    }
+    *out = h;
+    return SDFA_OK;
+}
+
+void sdfa_destroy(sdfa_handle *h) {
+    if (!h) return;
+    if (h->dev.device >= 0) {
+        cudaSetDevice(h->dev.device);
+        for (void *p : h->allocs) cudaFree(p);
+        for (float *p : {h->rhs, h->dgrad_c, h->io_in, h->io_out, h->io_in2}) if (p) cudaFree(p);
+        for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    }
+    delete h;
+}
+
+int sdfa_info(const sdfa_handle *h, int *n_verts, int *n_tris, int *n_cnsts, int *n_free, int *n_eq, int *n_active,
+              long long *nnz_l) {
+    if (!h) return fail(SDFA_ERR_ARG, "sdfa_info: NULL handle");
+    const HostPlan &p = h->host;
+    if (n_verts) *n_verts = p.n_verts;
+    if (n_tris) *n_tris = p.n_tris;
+    if (n_cnsts) *n_cnsts = p.n_cnsts;
+    if (n_free) *n_free = p.n_free;
+    if (n_eq) *n_eq = p.n_eq;
+    if (n_active) *n_active = p.n_active;
+    if (nnz_l) *nnz_l = (long long)p.l_rowidx.size();
+    return SDFA_OK;
+}
+
+int sdfa_set_constraint_positions(sdfa_handle *h, const float *cnst_verts_host) {
+    if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    HostPlan &p = h->host;
+    if (p.n_cnsts == 0) return SDFA_OK;
+    // unchanged positions: nothing to redo
+    bool same = true;
+    for (int i = 0; i < p.n_cnsts * 3 && same; ++i) {
+        float want = cnst_verts_host ? cnst_verts_host[i] : p.verts[(size_t)p.cnsts[i / 3] * 3 + i % 3];
+        same = (std::memcmp(&want, &p.cnst_pos[i], 4) == 0);
+    }
+    if (same) return SDFA_OK;
+    compute_base_solution(p, cnst_verts_host);
+    return upload_base(h);
+}
+
+int sdfa_set_correspondences(sdfa_handle *h, const uint32_t *corr_count, const uint32_t *corr_faces, int n_src_tris) {
+    if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    const HostPlan &p = h->host;
+    std::vector<int32_t> prev = h->eq_src_host;
+    if (!corr_count) {
+        default_eq_src(h);
+    } else {
+        if (!corr_faces) return fail(SDFA_ERR_ARG, "sdfa_set_correspondences: corr_faces is NULL");
+        // deform_triangle_impl.hpp:246-269: the block counter fi advances by max(1,count) per target triangle
+        std::vector<int32_t> m;
+        for (int i = 0; i < p.n_tris; ++i) {
+            if (corr_count[i] > 0) {
+                for (uint32_t j = 0; j < corr_count[i]; ++j) {
+                    uint32_t s = corr_faces[m.size()];
+                    if ((int)s >= n_src_tris) return fail(SDFA_ERR_ARG, "sdfa_set_correspondences: source triangle out of range");
+                    m.push_back((int32_t)s);
+                }
+            } else m.push_back(-1);
+        }
+        if ((int)m.size() != p.n_eq)
+            return fail(SDFA_ERR_ARG, "sdfa_set_correspondences: counts do not match the ones given to sdfa_create");
+        h->eq_src_host.swap(m);
+        h->n_src_tris = n_src_tris;
+    }
+    if (prev == h->eq_src_host) return SDFA_OK;
+    return upload_eq_src(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int need_device(sdfa_handle *h) {
+    if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    if (h->dev.device < 0)
+        return fail(SDFA_ERR_CUDA, "handle was created without a CUDA device; this library has no CPU path");
+    CUDA_TRY(cudaSetDevice(h->dev.device));
+    return SDFA_OK;
+}
+
+static int time_mark(sdfa_handle *h, int i, cudaStream_t s) {
+    if (!h->timing) return SDFA_OK;
+    if (!h->ev[i]) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    CUDA_TRY(cudaEventRecord(h->ev[i], s));
+    return SDFA_OK;
+}
+static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
+    if (!h->timing) return SDFA_OK;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int i = 0; i < 4; ++i) h->last_ms[i] = 0.f;
+    if (decoded) CUDA_TRY(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&h->last_ms[3], h->ev[3], h->ev[4]));
+    return SDFA_OK;
+}
+
+static int reconstruct_core(sdfa_handle *h, const float *dgrad_dev, long long stride, const int32_t *eq_src, int mode,
+                            int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
+    int rc;
+    if ((rc = grow(&h->rhs, &h->rhs_cap, (size_t)n_frames * h->dev.n_free * 3))) return rc;
+    if ((rc = time_mark(h, 1, s))) return rc;
+    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, eq_src, n_frames, mode, h->rhs, s));
+    if ((rc = time_mark(h, 2, s))) return rc;
+    CUDA_TRY(launch_solve(h->dev, h->rhs, n_frames, out_dev, s));
+    if ((rc = time_mark(h, 3, s))) return rc;
+    CUDA_TRY(launch_fill_constraints(h->dev, n_frames, out_dev, s));
+    if ((rc = time_mark(h, 4, s))) return rc;
+    return time_finish(h, s, decoded);
+}
+
+int sdfa_reconstruct_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames, float *out_dev,
+                         void *stream) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!dgrad_dev || !out_dev))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_dev: bad arguments");
+    long long stride = dgrad_stride ? dgrad_stride : (long long)h->n_src_tris * 9;
+    return reconstruct_core(h, dgrad_dev, stride, h->dev.eq_src, ASM_DGRAD, n_frames, out_dev, (cudaStream_t)stream, false);
+}
+
+int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (n_frames < 0 || (n_frames > 0 && (!dgrad_host || !out_host))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_host: bad arguments");
+    if (n_frames == 0) return SDFA_OK;
+    const size_t in_f = (size_t)n_frames * h->n_src_tris * 9, out_f = (size_t)n_frames * h->dev.n_verts * 3;
+    if ((rc = grow(&h->io_in, &h->io_in_cap, in_f))) return rc;
+    if ((rc = grow(&h->io_out, &h->io_out_cap, out_f))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->io_in, dgrad_host, in_f * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = reconstruct_core(h, h->io_in, (long long)h->n_src_tris * 9, h->dev.eq_src, ASM_DGRAD, n_frames, h->io_out, 0, false))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, h->io_out, out_f * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return SDFA_OK;
+}
+
+static int single_frame(sdfa_handle *h, const double *in, long long len, int mode, const float *cnst, float *out_host) {
+    int rc;
+    const HostPlan &p = h->host;
+    if (p.n_cnsts > 0 && !cnst)
+        return fail(SDFA_ERR_ARG, "cnst_verts is not given, but " + std::to_string(p.n_cnsts) +
+                                      " constraints (reference asserts: deform_triangle_impl.hpp:274)");
+    if ((rc = sdfa_set_constraint_positions(h, p.n_cnsts > 0 ? cnst : nullptr))) return rc;
+    std::vector<float> f32((size_t)len);
+    for (long long i = 0; i < len; ++i) f32[(size_t)i] = (float)in[i];
+    if ((rc = grow(&h->io_in, &h->io_in_cap, (size_t)len))) return rc;
+    if ((rc = grow(&h->io_out, &h->io_out_cap, (size_t)p.n_verts * 3))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->io_in, f32.data(), (size_t)len * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = reconstruct_core(h, h->io_in, len, h->dev.eq_src, mode, 1, h->io_out, 0, false))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, h->io_out, (size_t)p.n_verts * 12, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return SDFA_OK;
+}
+
+int sdfa_get_mesh_f64(sdfa_handle *h, const double *dgrad_host, long long dgrad_len, const float *cnst_verts_host,
+                      const uint32_t *corr_count, const uint32_t *corr_faces, long long corr_faces_len, float *out_host) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (!dgrad_host || !out_host || dgrad_len <= 0 || dgrad_len % 9) return fail(SDFA_ERR_ARG, "sdfa_get_mesh_f64: bad arguments");
+    const HostPlan &p = h->host;
+    const int n_src = (int)(dgrad_len / 9);
+    if (corr_count) {
+        if (corr_faces_len < p.n_eq) return fail(SDFA_ERR_ARG, "sdfa_get_mesh_f64: corr_faces shorter than the number of equation blocks");
+        if ((rc = sdfa_set_correspondences(h, corr_count, corr_faces, n_src))) return rc;
+    } else {
+        if (n_src < std::min(p.n_tris, p.n_eq)) return fail(SDFA_ERR_ARG, "sdfa_get_mesh_f64: deform_grad shorter than 9*n_tris");
+        if ((rc = sdfa_set_correspondences(h, nullptr, nullptr, n_src))) return rc;
+        h->n_src_tris = n_src;
+    }
+    return single_frame(h, dgrad_host, dgrad_len, ASM_DGRAD, cnst_verts_host, out_host);
+}
+
+int sdfa_get_mesh_from_dm_f64(sdfa_handle *h, const double *dmat_host, long long dmat_len, const float *cnst_verts_host,
+                              float *out_host) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    const HostPlan &p = h->host;
+    if (!dmat_host || !out_host || dmat_len < (long long)p.n_tris * 9) return fail(SDFA_ERR_ARG, "sdfa_get_mesh_from_dm_f64: bad arguments");
+    if ((rc = sdfa_set_correspondences(h, nullptr, nullptr, (int)(dmat_len / 9)))) return rc;
+    return single_frame(h, dmat_host, dmat_len, ASM_MATRIX, cnst_verts_host, out_host);
+}
+
+// ---------------------------------------------------------------------------------------------
+int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_scale, int k_scale,
+                 const float *compT_rotat, const float *means_rotat, int k_rotat) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (!compT_scale || !means_scale || !compT_rotat || !means_rotat || k_scale <= 0 || k_rotat <= 0)
+        return fail(SDFA_ERR_ARG, "sdfa_set_pca: bad arguments");
+    DevicePlan &d = h->dev;
+    const int nt = h->n_src_tris;
+    auto pack = [&](const float *W, const float *m, int per, int K, float **dw, float **dm, bool full) -> int {
+        const std::vector<int32_t> &need = h->needed_tris;
+        size_t ntri = full ? (size_t)nt : need.size();
+        std::vector<float> w(ntri * per * K), mm(ntri * per);
+        for (size_t t = 0; t < ntri; ++t) {
+            size_t src = full ? t : (size_t)need[t];
+            std::memcpy(&w[t * per * K], &W[src * per * K], sizeof(float) * per * K);
+            std::memcpy(&mm[t * per], &m[src * per], sizeof(float) * per);
+        }
+        int r;
+        if ((r = upload_mut(h, w, dw))) return r;
+        return upload_mut(h, mm, dm);
+    };
+    d.k_scale = k_scale; d.k_rotat = k_rotat;
+    if ((rc = pack(compT_scale, means_scale, 6, k_scale, &d.w_scale, &d.m_scale, false))) return rc;
+    if ((rc = pack(compT_rotat, means_rotat, 3, k_rotat, &d.w_rotat, &d.m_rotat, false))) return rc;
+    if ((rc = pack(compT_scale, means_scale, 6, k_scale, &d.wfull_scale, &d.mfull_scale, true))) return rc;
+    if ((rc = pack(compT_rotat, means_rotat, 3, k_rotat, &d.wfull_rotat, &d.mfull_rotat, true))) return rc;
+    h->has_pca = h->has_full_pca = true;
+    return SDFA_OK;
+}
+
+int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
+                                float *out_dev, void *stream) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_reconstruct: call sdfa_set_pca first (and again after changing correspondences)");
+    if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !out_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
+    if (n_frames == 0) return SDFA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long stride = (long long)h->dev.n_needed * 9;
+    if ((rc = grow(&h->dgrad_c, &h->dgrad_c_cap, (size_t)n_frames * stride))) return rc;
+    if ((rc = time_mark(h, 0, s))) return rc;
+    CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, h->dgrad_c, s));
+    return reconstruct_core(h, h->dgrad_c, stride, h->dev.eq_src_compact, ASM_DGRAD, n_frames, out_dev, s, true);
+}
+
+int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host,
+                                 int n_frames, float *out_host) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_reconstruct: call sdfa_set_pca first");
+    if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_host || !coeff_rotat_host || !out_host))) return fail(SDFA_ERR_ARG, "bad arguments");
+    if (n_frames == 0) return SDFA_OK;
+    const size_t ns = (size_t)n_frames * h->dev.k_scale, nr = (size_t)n_frames * h->dev.k_rotat;
+    const size_t out_f = (size_t)n_frames * h->dev.n_verts * 3;
+    if ((rc = grow(&h->io_in, &h->io_in_cap, ns))) return rc;
+    if ((rc = grow(&h->io_in2, &h->io_in2_cap, nr))) return rc;
+    if ((rc = grow(&h->io_out, &h->io_out_cap, out_f))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->io_in, coeff_scale_host, ns * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->io_in2, coeff_rotat_host, nr * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = sdfa_decode_reconstruct_dev(h, h->io_in, h->io_in2, n_frames, h->io_out, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, h->io_out, out_f * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return SDFA_OK;
+}
+
+int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
+                          float *dgrad_dev, void *stream) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (!h->has_full_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_dgrad_dev: call sdfa_set_pca first");
+    if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
+    CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, true, dgrad_dev, (cudaStream_t)stream));
+    return SDFA_OK;
+}
+
+int sdfa_get_deform_grad_host(const float *, const float *, int, const uint32_t *, int, double, int, int, double *) {
+    return fail(SDFA_ERR_UNSUPPORTED, "sdfa_get_deform_grad_host: the inverse path (mesh -> dgrad) is not built yet");
+}
+
+long long sdfa_launch_count(void) { return launch_counter(); }
+
+int sdfa_set_timing(sdfa_handle *h, int enable) {
+    if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    h->timing = enable != 0;
+    return SDFA_OK;
+}
+int sdfa_last_timing(const sdfa_handle *h, float ms[4]) {
+    if (!h || !ms) return fail(SDFA_ERR_ARG, "bad arguments");
+    for (int i = 0; i < 4; ++i) ms[i] = h->last_ms[i];
+    return SDFA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static long long give(const std::vector<T> &v, void *dst, long long cap) {
+    long long bytes = (long long)(v.size() * sizeof(T));
+    if (dst && cap > 0) std::memcpy(dst, v.data(), (size_t)std::min(bytes, cap));
+    return bytes;
+}
+
+long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long long cap) {
+    if (!h || !what) return -1;
+    const HostPlan &p = h->host;
+    const std::string w(what);
+    if (w == "perm") return give(p.perm, dst, cap);
+    if (w == "parent") return give(p.parent, dst, cap);
+    if (w == "free_to_vi") return give(p.free_to_vi, dst, cap);
+    if (w == "l_colptr") return give(p.l_colptr, dst, cap);
+    if (w == "l_rowidx") return give(p.l_rowidx, dst, cap);
+    if (w == "l_val") return give(p.l_val, dst, cap);
+    if (w == "m_colptr") return give(p.m_colptr, dst, cap);
+    if (w == "m_rowidx") return give(p.m_rowidx, dst, cap);
+    if (w == "m_val") return give(p.m_val, dst, cap);
+    if (w == "x_base") return give(p.x_base, dst, cap);
+    if (w == "active_eq") return give(p.active_eq, dst, cap);
+    if (w == "tri_u") return give(p.tri_u, dst, cap);
+    if (w == "prog") return give(p.prog.bytes, dst, cap);
+    if (w == "stage_off") return give(p.prog.stage_off, dst, cap);
+    if (w == "eq_src") return give(h->eq_src_host, dst, cap);
+    if (w == "asm_eq_id") return give(p.asmplan.eq_id, dst, cap);
+    if (w == "asm_eq_u") return give(p.asmplan.eq_u, dst, cap);
+    if (w == "asm_row_perm") return give(p.asmplan.row_perm, dst, cap);
+    if (w == "asm_row_ptr") return give(p.asmplan.row_ptr, dst, cap);
+    if (w == "asm_inc") return give(p.asmplan.inc, dst, cap);
+    if (w == "asm_blocks") {
+        std::vector<int> b;
+        for (auto &x : p.asmplan.blocks) { b.push_back(x.eq_begin); b.push_back(x.eq_end); b.push_back(x.row_begin); b.push_back(x.row_end); }
+        return give(b, dst, cap);
+    }
+    if (w == "stats") {
+        std::vector<long long> s = {p.prog.n_slots, p.prog.n_pieces, p.prog.n_steps_fwd, p.prog.n_steps_bwd,
+                                    p.prog.n_entries, (long long)p.prog.stage_off.size() - 1,
+                                    (long long)p.prog.bytes.size(), p.asmplan.max_eq_per_block,
+                                    (long long)p.asmplan.eq_id.size(), (long long)p.asmplan.blocks.size(),
+                                    (long long)solve_smem_bytes(p.prog.n_slots)};
+        return give(s, dst, cap);
+    }
+    return -1;
+}

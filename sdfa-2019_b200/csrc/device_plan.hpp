@@ -1,0 +1,52 @@
+// device_plan.hpp -- what sdfa_create uploads and what the kernel launchers in kernels.cu consume.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sdfa {
+
+struct DevicePlan {
+    int device = -1;
+    int n_verts = 0, n_tris = 0, n_cnsts = 0, n_free = 0, n_eq = 0;
+    int sm_count = 0;
+    // ---- assembly (K2)
+    int n_asm_blocks = 0, asm_max_eq = 0, asm_max_rows = 0;
+    int4           *asm_blocks = nullptr;   // {eq_begin, eq_end, row_begin, row_end}
+    const int32_t  *asm_eq_id = nullptr;    // block-local equation -> equation block
+    const float    *asm_eq_u = nullptr;     // 6 floats per block-local equation
+    const int32_t  *asm_row_perm = nullptr;
+    const int32_t  *asm_row_ptr = nullptr;
+    const uint16_t *asm_inc = nullptr;
+    int32_t        *eq_src = nullptr;       // equation block -> source triangle (>=0), -1 identity, -2 zero block
+    int32_t        *eq_src_compact = nullptr; // same, into the compact decoded dgrad
+    // ---- solve (K3)
+    const uint8_t  *prog = nullptr;         // 16-byte aligned stage stream
+    const uint32_t *stage_off = nullptr;
+    int n_stages = 0, n_slots = 0;
+    const int32_t  *row_vert = nullptr;     // permuted row -> vertex index
+    float          *xbase_hi = nullptr, *xbase_lo = nullptr;   // [n_free*3] permuted order
+    // ---- constrained vertices (K4)
+    const int32_t  *cnst_vert = nullptr;    // [n_cnsts]
+    float          *cnst_pos = nullptr;     // [n_cnsts*3]
+    // ---- decode (K1)
+    int k_scale = 0, k_rotat = 0, n_needed = 0;   // n_needed = source triangles some active equation reads
+    float *w_scale = nullptr, *m_scale = nullptr;  // compact basis rows [n_needed*6, k_scale], means
+    float *w_rotat = nullptr, *m_rotat = nullptr;  // [n_needed*3, k_rotat]
+    float *wfull_scale = nullptr, *mfull_scale = nullptr, *wfull_rotat = nullptr, *mfull_rotat = nullptr;
+};
+
+enum AssemblyMode { ASM_DGRAD = 0, ASM_MATRIX = 1 };
+
+// All launchers are asynchronous on `stream` and return the cudaError_t of the launch.
+cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, const int32_t *eq_src,
+                            int n_frames, int mode, float *rhs, cudaStream_t stream);
+cudaError_t launch_solve(const DevicePlan &d, float *rhs_scratch, int n_frames, float *out, cudaStream_t stream);
+cudaError_t launch_fill_constraints(const DevicePlan &d, int n_frames, float *out, cudaStream_t stream);
+cudaError_t launch_decode(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
+                          bool full_layout, float *dgrad_out, cudaStream_t stream);
+cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, const uint32_t *tris, int n_tris,
+                               double eps, int as_matrix, double *out, cudaStream_t stream);
+size_t solve_smem_bytes(int n_slots);
+long long launch_counter();
+
+}  // namespace sdfa

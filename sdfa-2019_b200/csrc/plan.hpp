@@ -1,0 +1,128 @@
+// plan.hpp -- host-side analysis products and the binary formats the kernels consume.
+//
+// Everything here is computed once per template by sdfa_create() (the B200-native replacement of
+// TriangleDeformation::setStaticTarget, reference deformation/cpp/src/deform_triangle_impl.hpp:7-142)
+// in fp64 on the host and then uploaded; the per-frame work is CUDA only (kernels.cu).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sdfa {
+
+// ------------------------------------------------------------------------------------------
+// Geometry of the solve tile.  One CTA of the solve kernel owns FRAMES_PER_TILE frames; a state
+// "slot" holds one row of the (permuted) system for all those frames: [3 coords][COORD_STRIDE] floats.
+// COORD_STRIDE is odd (33) so that the transposing loads/stores (lanes run along rows) are bank
+// conflict free while the row sweeps (lanes run along frames) stay stride-1.
+constexpr int FRAMES_PER_TILE = 32;
+constexpr int COORD_STRIDE    = 33;
+constexpr int SLOT_WORDS      = 3 * COORD_STRIDE;     // 99
+constexpr int SLOT_BYTES      = SLOT_WORDS * 4;       // 396
+
+// ------------------------------------------------------------------------------------------
+// Solve program: a byte stream cut into stages of at most STAGE_BYTES that the producer warp streams
+// global -> shared with cp.async.bulk (TMA) into a ring, and the consumer warps interpret.
+constexpr int STAGE_BYTES = 8192;
+
+enum OpType : uint16_t {
+    OP_ROWS    = 1,   // a = n_tasks, b = byte offset (in stage) of the u32 task-offset table,
+                      // c = byte offset of the next op
+    OP_LOAD    = 2,   // a = first permuted row, b = n_rows, c = byte offset of the u32 slot table
+                      // (next op = c + 4*b rounded up to 16)
+    OP_STORE_Y = 3,   // same operands; writes slots back to the rhs/y scratch rows (in place)
+    OP_STORE_X = 4,   // same operands; writes x_base + x to out[frame][vertex(row)]
+};
+enum OpFlags : uint16_t {
+    OPF_SYNC_BEFORE = 1,   // consumer barrier before the op
+    OPF_SYNC_AFTER  = 2,   // consumer barrier after the op
+};
+struct OpHeader {        // 16 bytes, 16-byte aligned inside the stage
+    uint16_t type, flags;
+    uint32_t a, b, c;
+};
+struct StageHeader {     // first 16 bytes of every stage
+    uint32_t n_ops, bytes, reserved0, reserved1;
+};
+// Slot-table entry of OP_LOAD: low 24 bits = slot byte offset / 4 (word offset), bit 31 = accumulate
+// onto what the slot already holds (partial sums from earlier pieces) instead of overwriting.
+constexpr uint32_t LOAD_ADD_BIT = 0x80000000u;
+
+// Row task (OP_ROWS): 16-byte header followed by n entries of 8 bytes {float coeff; u32 src_byte_off}.
+//   acc = sum coeff * slot[src];  v = (OVERWRITE ? 0 : slot[target]) - acc;  if FINAL: v *= dinv
+struct TaskHeader {
+    uint32_t target_byte_off;
+    uint32_t n_entries_flags;   // low 24 bits count, bit 24 = FINAL (scale by dinv), bit 25 = OVERWRITE
+    float    dinv;
+    uint32_t reserved;
+};
+constexpr uint32_t TASK_FINAL = 1u << 24, TASK_OVERWRITE = 1u << 25;
+struct TaskEntry { float coeff; uint32_t src_byte_off; };
+
+struct SolveProgram {
+    std::vector<uint8_t>  bytes;        // all stages back to back, each padded to a multiple of 16
+    std::vector<uint32_t> stage_off;    // byte offset of each stage, n_stages + 1 entries
+    int n_slots = 0;                    // state slots a CTA needs (peak over both sweeps)
+    int n_pieces = 0, n_steps_fwd = 0, n_steps_bwd = 0;
+    long long n_entries = 0;            // multiply-adds per (frame, coordinate)
+};
+
+// ------------------------------------------------------------------------------------------
+// Assembly plan (kernel K2): the free rows are grouped into row blocks; a CTA handles one
+// (row block, frame): phase 1 computes the two corner vectors of every equation block that touches
+// the row block, phase 2 sums, per row, the corner vectors incident to it (CSR, no atomics).
+struct AssemblyBlock {
+    int eq_begin, eq_end;       // range in eq_* arrays (block-local equations, duplicates across blocks allowed)
+    int row_begin, row_end;     // range in row_* arrays
+};
+struct AssemblyPlan {
+    std::vector<AssemblyBlock> blocks;
+    // per block-local equation: which equation block it is (index into the active list) and the
+    // frame of its target triangle: U0[3], U1[3]  (rows of U = R^-1 Q^T, impl.hpp:98-100)
+    std::vector<int32_t> eq_id;         // global equation-block index (0..n_eq)
+    std::vector<float>   eq_u;          // 6 floats per entry
+    // per block-local row: permuted row index (where to write) and incidence range
+    std::vector<int32_t>  row_perm;
+    std::vector<int32_t>  row_ptr;      // size rows + 1 per block, concatenated with global offsets
+    std::vector<uint16_t> inc;          // incidence: local_eq * 3 + corner
+    int max_eq_per_block = 0, max_rows_per_block = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+struct HostPlan {
+    // template
+    int n_verts = 0, n_tris = 0, n_cnsts = 0, n_free = 0, n_eq = 0, n_active = 0;
+    double reg = 1e-10;
+    std::vector<float>    verts;        // [n_verts*3]
+    std::vector<uint32_t> tris;         // [n_tris*3]
+    std::vector<uint32_t> cnsts;        // [n_cnsts]
+    std::vector<uint32_t> corr_count;   // [] or [n_tris]
+    // reference column maps (impl.hpp:36-73)
+    std::vector<int> vi_to_free, vi_to_cnst, free_to_vi;
+    std::vector<int> eq_tri;            // equation block -> target triangle
+    std::vector<double> tri_u;          // per triangle: U0[3], U1[3] in fp64
+    std::vector<int> active_eq;         // equation blocks touching >= 1 free vertex
+    // system matrix M = A^T A + reg I (lower triangle, CSC, original free-column order)
+    std::vector<int> m_colptr, m_rowidx;
+    std::vector<double> m_val;
+    // ordering and factor: perm[new] = old free column; L in CSC (diagonal first in every column)
+    std::vector<int> perm, iperm, parent;
+    std::vector<int> l_colptr, l_rowidx;
+    std::vector<double> l_val;
+    // base solution for the current constraint positions: M^-1 A^T (stack(I) - A_r C), permuted order
+    std::vector<double> x_base;         // [n_free*3]
+    std::vector<float>  cnst_pos;       // [n_cnsts*3] currently active constraint positions
+    SolveProgram prog;
+    AssemblyPlan asmplan;
+};
+
+// analysis.cpp
+int  build_system(HostPlan &p, std::string &err);                 // maps, U, M
+int  order_and_factor(HostPlan &p, std::string &err);             // perm, etree, L
+void compute_base_solution(HostPlan &p, const float *cnst_pos);   // x_base
+void solve_factored(const HostPlan &p, std::vector<double> &rhs_perm /* [n_free*3] in/out */);
+// schedule.cpp
+void build_solve_program(HostPlan &p, int piece_cap);
+void build_assembly_plan(HostPlan &p, int rows_per_block);
+
+}  // namespace sdfa

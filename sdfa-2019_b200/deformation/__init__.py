@@ -1,0 +1,321 @@
+"""Drop-in ``deformation`` package backed by the B200-native CUDA library (no CPU fallback).
+
+Same names, keyword arguments, defaults, dtypes and return shapes as the reference's pybind module
+(reference: deformation/cpp/src/pybind.cpp:129-153, imported through deformation/__init__.py:6-13):
+
+    set_target(verts, faces, cnsts=[], corrs=[], reg=1e-10) -> bool
+    is_same(num_verts, num_faces, num_cnsts) -> bool
+    get_mesh(deform_grad, vert_cnsts=[], corr_count=[], corr_faces=[]) -> float32[n_verts,3]
+    get_mesh_from_dg            (alias of get_mesh)
+    get_mesh_from_dm(deform_mat, vert_cnsts=[]) -> float32[n_verts,3]
+    get_deform_grad(verts_a, verts_b, faces, eps=1e-6) -> float64[9*n_tris]
+    get_deform_mat(verts_a, verts_b, faces, eps=1e-6)  -> float64[9*n_tris]
+
+so ``speech_anime/viewer/frame.py:42,118-137`` runs unchanged against it.  Like the reference these act on
+one process-global solver (pybind.cpp:10).  Differences, all deliberate:
+  * argument errors raise ``SdfaError`` instead of logging and calling exit(1) (log.hpp:32-33);
+  * arithmetic is float32 on the GPU around an fp64-factorised system: results match the reference to
+    <= 1e-6 x bbox diagonal, not bit for bit.
+New, batched entry points (what the hot loops of speech_anime/model/model.py:201-212 and
+viewer/video.py:220-277 should call instead of one frame at a time):
+
+    get_mesh_batch(deform_grads[N, 9*n_tris]) -> float32[N, n_verts, 3]      (numpy or torch.cuda tensors)
+    set_pca(compT_scale, means_scale, compT_rotat, means_rotat)
+    decode_and_get_mesh(coeff_scale[N,Ks], coeff_rotat[N,Kr]) -> float32[N, n_verts, 3]
+    Reconstructor(...)            explicit-handle version of all of the above (one per device/template)
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native
+from ._native import SdfaError, check, lib, ptr
+
+__all__ = ["set_target", "is_same", "get_mesh", "get_mesh_from_dg", "get_mesh_from_dm", "get_deform_grad",
+           "get_deform_mat", "get_mesh_batch", "set_pca", "decode_and_get_mesh", "Reconstructor", "SdfaError"]
+
+
+def _f32c(a, what):
+    """py::array_t<float, c_style> semantics: C-contiguous + forcecast (pybind.cpp:14)."""
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32c(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _default_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+class Reconstructor:
+    """One template (+ constraint set, correspondences, PCA basis) on one CUDA device.
+
+    Construction = TriangleDeformation::setStaticTarget (deform_triangle_impl.hpp:7-142): builds
+    A^T A + reg*I, factors it (fp64, host), schedules the sweeps and uploads the plan.
+    ``device=-1`` keeps everything on the host for plan inspection; compute calls then raise.
+    """
+
+    def __init__(self, verts, faces, cnsts=(), corrs=(), reg=1e-10, device=None):
+        V = _f32c(verts, "verts")
+        F = _u32c(faces)
+        c = _u32c(cnsts).reshape(-1)
+        cc = _u32c(corrs).reshape(-1)
+        if not (1 <= V.ndim <= 2 and 1 <= F.ndim <= 2):                      # pybind.cpp:20-21
+            raise SdfaError(_native.ERR_ARG, "verts/faces must be 1-D or 2-D")
+        V = V.reshape(-1, 3)
+        F = F.reshape(-1, 3)
+        if cc.size not in (0, len(F)):
+            raise SdfaError(_native.ERR_ARG, "corrs must be empty or have one count per face")
+        self.n_verts, self.n_tris, self.n_cnsts = len(V), len(F), len(c)
+        self.device = _default_device() if device is None else int(device)
+        self._h = ctypes.c_void_p()
+        self._verts, self._faces, self._cnsts = V, F, c
+        check(lib.sdfa_create(ctypes.byref(self._h), ptr(V), len(V), ptr(F), len(F), ptr(c) if c.size else None,
+                              len(c), ptr(cc) if cc.size else None, float(reg), self.device))
+        nf, ne, na, nnz = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+        check(lib.sdfa_info(self._h, None, None, None, ctypes.byref(nf), ctypes.byref(ne), ctypes.byref(na),
+                            ctypes.byref(nnz)))
+        self.n_free, self.n_eq, self.n_active, self.nnz_l = nf.value, ne.value, na.value, nnz.value
+        self.n_src_tris = self.n_tris
+        self._corr_key = None
+        self._has_pca = False
+
+    # -------------------------------------------------------------------------------- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.sdfa_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def debug(self, what):
+        return _native.debug_get(self._h, what)
+
+    # ---------------------------------------------------------------------------------- state
+    def set_constraint_positions(self, vert_cnsts=None):
+        if vert_cnsts is None or np.size(vert_cnsts) == 0:
+            check(lib.sdfa_set_constraint_positions(self._h, None))
+            return
+        C = _f32c(vert_cnsts, "vert_cnsts").reshape(-1, 3)
+        if len(C) != self.n_cnsts:
+            raise SdfaError(_native.ERR_ARG, f"vert_cnsts has {len(C)} rows, template has {self.n_cnsts} constraints")
+        check(lib.sdfa_set_constraint_positions(self._h, ptr(C)))
+
+    def set_correspondences(self, corr_count=(), corr_faces=(), n_src_tris=None):
+        cc, cf = _u32c(corr_count).reshape(-1), _u32c(corr_faces).reshape(-1)
+        if cc.size == 0:
+            check(lib.sdfa_set_correspondences(self._h, None, None, self.n_tris))
+            self.n_src_tris = self.n_tris
+            return
+        if n_src_tris is None:
+            n_src_tris = int(cf.max()) + 1 if cf.size else 0
+        if cc.size != self.n_tris or cf.size < self.n_eq:
+            raise SdfaError(_native.ERR_ARG, "corr_count/corr_faces sizes do not match the template")
+        check(lib.sdfa_set_correspondences(self._h, ptr(cc), ptr(cf), int(n_src_tris)))
+        self.n_src_tris = int(n_src_tris)
+
+    def set_pca(self, compT_scale, means_scale, compT_rotat, means_rotat):
+        """PcaInversion buffers (output_module.py:94-113): compT [out, K], means [out]."""
+        cs, ms = _f32c(compT_scale, "compT_scale"), _f32c(means_scale, "means_scale").reshape(-1)
+        cr, mr = _f32c(compT_rotat, "compT_rotat"), _f32c(means_rotat, "means_rotat").reshape(-1)
+        nt = self.n_src_tris
+        if cs.shape[0] != nt * 6 or cr.shape[0] != nt * 3 or ms.size != nt * 6 or mr.size != nt * 3:
+            raise SdfaError(_native.ERR_ARG, "PCA basis shapes must be [n_tris*6,Ks], [n_tris*6], [n_tris*3,Kr], [n_tris*3]")
+        self.k_scale, self.k_rotat = cs.shape[1], cr.shape[1]
+        check(lib.sdfa_set_pca(self._h, ptr(cs), ptr(ms), self.k_scale, ptr(cr), ptr(mr), self.k_rotat))
+        self._has_pca = True
+
+    # ------------------------------------------------------------------------ single frame (legacy)
+    def get_mesh(self, deform_grad, vert_cnsts=(), corr_count=(), corr_faces=()):
+        dg = np.ascontiguousarray(deform_grad, dtype=np.float64).reshape(-1)
+        C = _f32c(vert_cnsts, "vert_cnsts").reshape(-1)
+        cc, cf = _u32c(corr_count).reshape(-1), _u32c(corr_faces).reshape(-1)
+        out = np.empty((self.n_verts, 3), dtype=np.float32)
+        if C.size not in (0, self.n_cnsts * 3):
+            raise SdfaError(_native.ERR_ARG, "vert_cnsts must have one row per constraint")
+        check(lib.sdfa_get_mesh_f64(self._h, ptr(dg), dg.size, ptr(C) if C.size else None,
+                                    ptr(cc) if cc.size else None, ptr(cf) if cc.size else None, cf.size, ptr(out)))
+        self.n_src_tris = dg.size // 9
+        return out
+
+    def get_mesh_from_dm(self, deform_mat, vert_cnsts=()):
+        dm = np.ascontiguousarray(deform_mat, dtype=np.float64).reshape(-1)
+        C = _f32c(vert_cnsts, "vert_cnsts").reshape(-1)
+        out = np.empty((self.n_verts, 3), dtype=np.float32)
+        check(lib.sdfa_get_mesh_from_dm_f64(self._h, ptr(dm), dm.size, ptr(C) if C.size else None, ptr(out)))
+        return out
+
+    # ----------------------------------------------------------------------------------- batched
+    def get_mesh_batch(self, deform_grads, out=None, stream=None):
+        """[N, 9*n_src_tris] float32 -> [N, n_verts, 3] float32.  torch.cuda tensors stay on the device
+        (stream-ordered, no synchronisation); numpy arrays go through pinned-size staging copies."""
+        if _is_torch(deform_grads):
+            import torch
+            x = deform_grads
+            if x.dtype != torch.float32 or not x.is_cuda:
+                raise SdfaError(_native.ERR_ARG, "torch input must be a float32 CUDA tensor")
+            x = x.reshape(x.shape[0], -1)
+            if x.stride(1) != 1:
+                x = x.contiguous()
+            if x.shape[1] != self.n_src_tris * 9:
+                raise SdfaError(_native.ERR_ARG, f"expected {self.n_src_tris * 9} values per frame, got {x.shape[1]}")
+            n = x.shape[0]
+            if out is None:
+                out = torch.empty((n, self.n_verts, 3), dtype=torch.float32, device=x.device)
+            s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+            check(lib.sdfa_reconstruct_dev(self._h, ptr(x.data_ptr()), x.stride(0), n, ptr(out.data_ptr()), ptr(s)))
+            return out
+        x = _f32c(deform_grads, "deform_grads")
+        x = x.reshape(x.shape[0], -1) if x.ndim > 1 else x.reshape(1, -1)
+        if x.shape[1] != self.n_src_tris * 9:
+            raise SdfaError(_native.ERR_ARG, f"expected {self.n_src_tris * 9} values per frame, got {x.shape[1]}")
+        res = np.empty((x.shape[0], self.n_verts, 3), dtype=np.float32) if out is None else out
+        check(lib.sdfa_reconstruct_host(self._h, ptr(x), x.shape[0], ptr(res)))
+        return res
+
+    def decode_and_get_mesh(self, coeff_scale, coeff_rotat, out=None, stream=None):
+        """PCA coefficients -> vertices: F.linear x2 + interleave + reconstruction in one call."""
+        if not self._has_pca:
+            raise SdfaError(_native.ERR_STATE, "set_pca() first")
+        if _is_torch(coeff_scale):
+            import torch
+            a, b = coeff_scale.contiguous(), coeff_rotat.contiguous()
+            if a.dtype != torch.float32 or b.dtype != torch.float32 or not a.is_cuda or not b.is_cuda:
+                raise SdfaError(_native.ERR_ARG, "torch inputs must be float32 CUDA tensors")
+            a, b = a.reshape(-1, self.k_scale), b.reshape(-1, self.k_rotat)
+            n = a.shape[0]
+            if out is None:
+                out = torch.empty((n, self.n_verts, 3), dtype=torch.float32, device=a.device)
+            s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
+            check(lib.sdfa_decode_reconstruct_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), n,
+                                                  ptr(out.data_ptr()), ptr(s)))
+            return out
+        a = _f32c(coeff_scale, "coeff_scale").reshape(-1, self.k_scale)
+        b = _f32c(coeff_rotat, "coeff_rotat").reshape(-1, self.k_rotat)
+        if len(a) != len(b):
+            raise SdfaError(_native.ERR_ARG, "coefficient batches differ in length")
+        res = np.empty((len(a), self.n_verts, 3), dtype=np.float32) if out is None else out
+        check(lib.sdfa_decode_reconstruct_host(self._h, ptr(a), ptr(b), len(a), ptr(res)))
+        return res
+
+    def decode_dgrad(self, coeff_scale, coeff_rotat, stream=None):
+        """data_to_anime_feat (model.py:246-257): coefficients -> full-layout dgrad [N, 9*n_tris] (torch.cuda only)."""
+        import torch
+        a = coeff_scale.contiguous().reshape(-1, self.k_scale)
+        b = coeff_rotat.contiguous().reshape(-1, self.k_rotat)
+        out = torch.empty((a.shape[0], self.n_src_tris * 9), dtype=torch.float32, device=a.device)
+        s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
+        check(lib.sdfa_decode_dgrad_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), a.shape[0],
+                                        ptr(out.data_ptr()), ptr(s)))
+        return out
+
+    # ------------------------------------------------------------------------------ measurement
+    def set_timing(self, enable=True):
+        check(lib.sdfa_set_timing(self._h, 1 if enable else 0))
+
+    def last_timing(self):
+        ms = (ctypes.c_float * 4)()
+        check(lib.sdfa_last_timing(self._h, ms))
+        return dict(decode_ms=ms[0], assembly_ms=ms[1], solve_ms=ms[2], fill_ms=ms[3])
+
+
+# =================================================================================================
+# The process-global singleton interface of the reference (pybind.cpp:10: gDeformManager).
+_global: Reconstructor | None = None
+_counts = (0, 0, 0)
+
+
+def set_target(verts, faces, cnsts=(), corrs=(), reg=1e-10) -> bool:
+    """SetTarget (pybind.cpp:13-33).  Returns False when the factorisation fails (impl.hpp:134-139)."""
+    global _global, _counts
+    if _global is not None:
+        _global.close()
+        _global = None
+    try:
+        _global = Reconstructor(verts, faces, cnsts, corrs, reg)
+    except SdfaError as e:
+        if e.code == _native.ERR_FACTOR:
+            print(f"solver error: {e}")
+            return False
+        raise
+    _counts = (_global.n_verts, _global.n_tris, _global.n_cnsts)
+    return True
+
+
+def is_same(num_verts, num_faces, num_cnsts) -> bool:
+    """IsSame (pybind.cpp:119-126): compares the three counts only."""
+    return _counts == (int(num_verts), int(num_faces), int(num_cnsts))
+
+
+def _need_target():
+    if _global is None:
+        raise SdfaError(_native.ERR_STATE, "set_target() has not been called")
+    return _global
+
+
+def get_mesh(deform_grad, vert_cnsts=(), corr_count=(), corr_faces=()):
+    """GetMeshFromGrad (pybind.cpp:101-117)."""
+    return _need_target().get_mesh(deform_grad, vert_cnsts, corr_count, corr_faces)
+
+
+get_mesh_from_dg = get_mesh
+
+
+def get_mesh_from_dm(deform_mat, vert_cnsts=()):
+    """GetMeshFromMat (pybind.cpp:60-74)."""
+    return _need_target().get_mesh_from_dm(deform_mat, vert_cnsts)
+
+
+def _inverse(verts_a, verts_b, faces, eps, as_matrix):
+    A, B = _f32c(verts_a, "verts_a"), _f32c(verts_b, "verts_b")
+    F = _u32c(faces)
+    if A.size != B.size:                                                     # pybind.cpp:47,88
+        raise SdfaError(_native.ERR_ARG, "verts_a and verts_b differ in size")
+    A, B, F = A.reshape(-1, 3), B.reshape(-1, 3), F.reshape(-1, 3)
+    out = np.empty(len(F) * 9, dtype=np.float64)
+    check(lib.sdfa_get_deform_grad_host(ptr(A), ptr(B), len(A), ptr(F), len(F), float(eps), as_matrix,
+                                        _default_device(), ptr(out)))
+    return out
+
+
+def get_deform_grad(verts_a, verts_b, faces, eps=1e-6):
+    """GetDeformGrad (pybind.cpp:78-99)."""
+    return _inverse(verts_a, verts_b, faces, eps, 0)
+
+
+def get_deform_mat(verts_a, verts_b, faces, eps=1e-6):
+    """GetDeformMat (pybind.cpp:37-58)."""
+    return _inverse(verts_a, verts_b, faces, eps, 1)
+
+
+def get_mesh_batch(deform_grads, vert_cnsts=None, out=None):
+    r = _need_target()
+    r.set_constraint_positions(vert_cnsts)
+    return r.get_mesh_batch(deform_grads, out=out)
+
+
+def set_pca(compT_scale, means_scale, compT_rotat, means_rotat):
+    _need_target().set_pca(compT_scale, means_scale, compT_rotat, means_rotat)
+
+
+def decode_and_get_mesh(coeff_scale, coeff_rotat, vert_cnsts=None, out=None):
+    r = _need_target()
+    r.set_constraint_positions(vert_cnsts)
+    return r.decode_and_get_mesh(coeff_scale, coeff_rotat, out=out)

@@ -1,0 +1,182 @@
+"""GPU tier (pytest -m gpu, run on a B200 through gpurun): the CUDA path, called through the C ABI /
+the drop-in ``deformation`` package, against the oracle on identical inputs.
+
+Tolerance (BASELINE.json north_star): max per-vertex deviation <= 1e-6 x template bounding-box diagonal
+(4.4e-7 m for FLAME).  The checker is the compiled reference (oracle/_ref) when it travelled with the
+snapshot, else the numpy restatement (oracle/dgrad_oracle.py); committed golden outputs are checked too."""
+import numpy as np
+import pytest
+
+import deformation as D
+from deformation import workloads as W
+from oracle import ref_loader
+from oracle.dgrad_oracle import TriangleDeformationOracle, pca_decode
+
+pytestmark = pytest.mark.gpu
+
+
+def _checker(V, F, cnsts=(), corrs=()):
+    if ref_loader.ref_available():
+        o = ref_loader.RefSolver(1)
+    else:
+        o = TriangleDeformationOracle()
+    assert o.set_target(V, F, cnsts=cnsts, corrs=corrs)
+    return o
+
+
+@pytest.fixture(scope="module")
+def rec(flame):
+    return D.Reconstructor(flame["V"], flame["F"], cnsts=flame["nfv"], device=0)
+
+
+@pytest.fixture(scope="module")
+def chk(flame):
+    return _checker(flame["V"], flame["F"], flame["nfv"])
+
+
+def test_native_library_is_what_runs(rec):
+    before = D.lib.sdfa_launch_count()
+    rec.get_mesh_batch(np.zeros((1, 9976 * 9), dtype=np.float32))
+    assert D.lib.sdfa_launch_count() >= before + 3      # assembly + solve + fill kernels
+
+
+def test_kat_zero_dgrad_is_template(rec, flame):
+    V, nfv = flame["V"], flame["nfv"]
+    out = rec.get_mesh(np.zeros(9976 * 9), vert_cnsts=V[nfv])
+    assert out.dtype == np.float32 and out.shape == (5023, 3)
+    assert np.abs(out - V).max() <= 1e-9
+    assert np.array_equal(out[nfv], V[nfv])
+
+
+def test_config1_120_frames_vs_golden_and_checker(rec, chk, flame, golden_flame):
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    dg = W.iid_dgrad(120, len(F), sigma=0.01, seed=0)
+    out = rec.get_mesh_batch(dg)
+    assert out.shape == (120, 5023, 3)
+    assert np.abs(out[:8, free] - golden_flame["iid_free_verts"]).max() <= tol
+    assert np.abs(out.astype(np.float64).sum(axis=(1, 2)) - golden_flame["iid_checksum"]).max() < 5023 * 3 * tol
+    for i in (0, 31, 32, 64, 119):
+        ref = chk.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(out[i] - ref).max() <= tol
+        assert np.array_equal(out[i][nfv], V[nfv])
+    # the legacy one-frame float64 entry point gives the same vertices as the batch
+    one = rec.get_mesh(dg[5].astype(np.float64), vert_cnsts=V[nfv])
+    assert np.array_equal(one, out[5])
+
+
+def test_integrable_deformations_vs_golden(rec, flame, golden_flame):
+    V, F, nfv, nft, tol = flame["V"], flame["F"], flame["nfv"], flame["nft"], flame["tol"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    active = np.setdiff1d(np.arange(len(F)), nft)
+    for amp in (2, 10, 30):
+        full = np.zeros((len(F), 9), dtype=np.float32)
+        full[active] = golden_flame[f"integ{amp}_dgrad_active"]
+        out = rec.get_mesh(full.reshape(-1).astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(out[free] - golden_flame[f"integ{amp}_free_verts"]).max() <= tol, amp
+
+
+def test_large_sigma_and_partial_tiles(rec, chk, flame):
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    for n in (1, 31, 33, 97):
+        dg = W.iid_dgrad(n, len(F), sigma=0.2, seed=100 + n)
+        out = rec.get_mesh_batch(dg)
+        for i in sorted({0, n // 2, n - 1}):
+            ref = chk.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[nfv])
+            assert np.abs(out[i] - ref).max() <= tol, (n, i)
+    assert rec.get_mesh_batch(np.zeros((0, len(F) * 9), dtype=np.float32)).shape == (0, 5023, 3)
+
+
+def test_moved_constraints(rec, flame, golden_flame):
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    rng = np.random.default_rng(11)
+    C = V[nfv]
+    C2 = (C + np.float32(0.002) + (1e-4 * rng.standard_normal(C.shape)).astype(np.float32)).astype(np.float32)
+    dg = W.iid_dgrad(1, len(F), sigma=0.01, seed=0)[0]
+    out = rec.get_mesh(dg.astype(np.float64), vert_cnsts=C2)
+    assert np.abs(out[free] - golden_flame["moved_cnst_free_verts"]).max() <= tol
+    assert np.array_equal(out[nfv], C2)
+    out = rec.get_mesh(dg.astype(np.float64), vert_cnsts=C)      # and back to the template positions
+    assert np.abs(out[free] - golden_flame["iid_free_verts"][0]).max() <= tol
+
+
+def test_torch_device_tensors_and_linearity_of_batching(rec, flame):
+    import torch
+    F = flame["F"]
+    dg = torch.from_numpy(W.iid_dgrad(200, len(F), sigma=0.03, seed=5)).cuda()
+    out = rec.get_mesh_batch(dg)
+    assert out.is_cuda and out.shape == (200, 5023, 3)
+    # size-independent property: a frame's result does not depend on its batch or tile position
+    perm = torch.randperm(200, generator=torch.Generator().manual_seed(0)).cuda()
+    out2 = rec.get_mesh_batch(dg[perm].contiguous())
+    assert torch.equal(out2, out[perm])
+    # strided input rows
+    wide = torch.zeros((50, len(F) * 9 + 64), dtype=torch.float32, device="cuda")
+    wide[:, : len(F) * 9] = dg[:50]
+    out3 = rec.get_mesh_batch(wide[:, : len(F) * 9])
+    assert torch.equal(out3, out[:50])
+
+
+def test_dropin_singleton_call_pattern(flame, golden_flame):
+    """The exact sequence of speech_anime/viewer/frame.py:42,118-137."""
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    assert D.set_target(verts=np.reshape(V, (-1, 3)), faces=np.reshape(F, (-1, 3)), cnsts=list(nfv), corrs=[]) is True
+    assert D.is_same(V.shape[0], F.shape[0], len(nfv))
+    assert not D.is_same(V.shape[0], F.shape[0], 0)
+    frame = W.iid_dgrad(1, len(F), sigma=0.01, seed=0)[0]
+    out = D.get_mesh(deform_grad=frame.astype(np.float64), vert_cnsts=np.reshape(V, (-1, 3))[nfv],
+                     corr_count=[], corr_faces=[])
+    assert out.shape == (5023, 3) and out.dtype == np.float32
+    assert np.abs(out[free] - golden_flame["iid_free_verts"][0]).max() <= tol
+    assert np.array_equal(D.get_mesh_from_dg(deform_grad=frame.astype(np.float64), vert_cnsts=V[nfv]), out)
+
+
+def test_small_mesh_modes_vs_golden(golden_small):
+    V, F, border = W.grid_mesh()
+    tol = 1e-6 * W.bbox_diag(V)
+    dg = W.iid_dgrad(4, len(F), sigma=0.05, seed=7)
+    r = D.Reconstructor(V, F, cnsts=border, device=0)
+    assert np.abs(r.get_mesh_batch(dg) - golden_small["cnst_verts"]).max() <= tol
+    assert np.abs(r.get_mesh_from_dm(golden_small["deform_mat"], vert_cnsts=V[border])
+                  - golden_small["from_dm_verts"]).max() <= tol
+    Cm = (V[border] + np.float32(0.001)).astype(np.float32)
+    assert np.abs(r.get_mesh(dg[0].astype(np.float64), vert_cnsts=Cm) - golden_small["moved_cnst_verts"]).max() <= tol
+    with pytest.raises(D.SdfaError):
+        r.get_mesh(dg[0].astype(np.float64))                      # constraints but no vert_cnsts (impl.hpp:274)
+    # correspondences (frame.py passes them on every call)
+    cc, cf = golden_small["corr_count"], golden_small["corr_faces"]
+    rc = D.Reconstructor(V, F, cnsts=border, corrs=cc, device=0)
+    src = W.iid_dgrad(1, 11, sigma=0.05, seed=9)[0]
+    out = rc.get_mesh(src.astype(np.float64), vert_cnsts=V[border], corr_count=cc, corr_faces=cf)
+    assert np.abs(out - golden_small["corr_verts"]).max() <= tol
+    # unconstrained: defined modulo a translation
+    ru = D.Reconstructor(V, F, device=0)
+    out = ru.get_mesh(dg[2].astype(np.float64))
+    ref = golden_small["uncnst_verts"]
+    assert np.abs((out - out.mean(0)) - (ref - ref.mean(0))).max() <= 5e-6
+
+
+def test_decode_and_reconstruct_config2(rec, chk, flame):
+    """Config 2: 240 frames of PCA coefficients -> vertices; oracle = fp32 F.linear + cat + reference get_mesh."""
+    import torch
+    V, F, nfv, nft, tol = flame["V"], flame["F"], flame["nfv"], flame["nft"], flame["tol"]
+    cs, ms, cr, mr = W.random_pca(len(F), seed=1)
+    xs, xr = W.random_coeffs(240, seed=2)
+    rec.set_pca(cs, ms, cr, mr)
+    out = rec.decode_and_get_mesh(xs, xr)
+    assert out.shape == (240, 5023, 3)
+    # decode alone: the tensor data_to_anime_feat returns (model.py:246-257), vs torch CPU fp32 F.linear
+    dg_dev = rec.decode_dgrad(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda()).cpu().numpy()
+    lin_s = torch.nn.functional.linear(torch.from_numpy(xs), torch.from_numpy(cs), torch.from_numpy(ms))
+    lin_r = torch.nn.functional.linear(torch.from_numpy(xr), torch.from_numpy(cr), torch.from_numpy(mr))
+    dg_ref = torch.cat((lin_s.view(240, -1, 6), lin_r.view(240, -1, 3)), dim=-1).view(240, -1).numpy()
+    dg64 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float64)
+    assert np.abs(dg_dev - dg64).max() <= 2 * np.abs(dg_ref - dg64).max() + 1e-7
+    for i in (0, 100, 239):
+        ref = chk.get_mesh(dg_ref[i].astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(out[i] - ref).max() <= tol
+    # torch path == numpy path
+    out_t = rec.decode_and_get_mesh(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda())
+    assert np.array_equal(out_t.cpu().numpy(), out)

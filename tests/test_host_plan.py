@@ -1,0 +1,154 @@
+"""CPU tier: the C ABI loads and exports what include/sdfa_b200.h declares, and the host-side analysis
+(system matrix, ordering, Cholesky factor, solve program, assembly plan) is right -- checked by running
+the uploaded plans through the test-only numpy interpreter (tests/plan_emulator.py) against the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import deformation as D
+from deformation import _native, workloads as W
+from oracle.dgrad_oracle import TriangleDeformationOracle
+from tests import plan_emulator as E
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sdfa_b200.h")).read()
+    declared = set(re.findall(r"\b(sdfa_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("sdfa_handle")
+    assert declared == set(_native.EXPORTS)
+    lib = ctypes.CDLL(os.path.abspath(_native.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_device_means_error_not_fallback(flame):
+    r = D.Reconstructor(flame["V"], flame["F"], cnsts=flame["nfv"], device=-1)
+    with pytest.raises(D.SdfaError) as ei:
+        r.get_mesh_batch(np.zeros((1, 9976 * 9), dtype=np.float32))
+    assert ei.value.code == _native.ERR_CUDA
+    with pytest.raises(D.SdfaError):
+        r.get_mesh(np.zeros(9976 * 9), vert_cnsts=flame["V"][flame["nfv"]])
+
+
+def test_argument_errors_raise(flame):
+    V, F = flame["V"], flame["F"]
+    with pytest.raises(D.SdfaError):
+        D.Reconstructor(V, F, cnsts=[0, 0], device=-1)             # duplicate constraint
+    with pytest.raises(D.SdfaError):
+        D.Reconstructor(V, F, cnsts=[len(V)], device=-1)           # out of range
+    bad = F.copy(); bad[0, 0] = len(V)
+    with pytest.raises(D.SdfaError):
+        D.Reconstructor(V, bad, device=-1)
+    with pytest.raises(D.SdfaError):
+        D.Reconstructor(V, F, cnsts=np.arange(len(V)), device=-1)  # nothing left to solve
+
+
+@pytest.fixture(scope="module")
+def flame_rec(flame):
+    return D.Reconstructor(flame["V"], flame["F"], cnsts=flame["nfv"], device=-1)
+
+
+@pytest.fixture(scope="module")
+def flame_oracle(flame):
+    o = TriangleDeformationOracle()
+    assert o.set_target(flame["V"], flame["F"], cnsts=flame["nfv"])
+    return o
+
+
+def _csc(colptr, rowidx, val, n):
+    return sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
+
+
+def test_system_matrix_and_factor(flame_rec, flame_oracle):
+    r, o = flame_rec, flame_oracle
+    n = r.n_free
+    assert (r.n_free, r.n_eq, r.n_active) == (1261, 9976, 2601)
+    Ml = _csc(r.debug("m_colptr"), r.debug("m_rowidx"), r.debug("m_val"), n)
+    M = Ml + sp.tril(Ml, -1).T
+    assert abs(M - o.AtA).max() < 1e-9 * abs(o.AtA).max()
+    perm = r.debug("perm")
+    assert sorted(perm) == list(range(n))
+    L = _csc(r.debug("l_colptr"), r.debug("l_rowidx"), r.debug("l_val"), n)
+    assert sp.triu(L, 1).nnz == 0
+    PMP = M.tocsr()[perm][:, perm]
+    assert abs(L @ L.T - PMP).max() < 1e-10 * abs(PMP).max()
+    assert r.nnz_l < 30000                      # fill stays near AMD's 20 385
+    parent = r.debug("parent")
+    assert all(parent[j] > j or parent[j] < 0 for j in range(n))   # postordered elimination tree
+
+
+def test_program_budget(flame_rec):
+    n_slots, n_pieces, st_f, st_b, n_entries, n_stages, nbytes, max_eq, _, _, smem = flame_rec.debug("stats")[:11]
+    assert n_entries == 2 * (flame_rec.nnz_l - flame_rec.n_free)
+    assert smem <= 227 * 1024
+    assert max_eq * 36 <= 48 * 1024
+
+
+def test_emulated_flame_frames_match_oracle(flame_rec, flame_oracle, flame, golden_flame):
+    V, F, nfv = flame["V"], flame["F"], flame["nfv"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    dg = W.iid_dgrad(2, len(F), sigma=0.01, seed=0)
+    out, st = E.solve(flame_rec, E.assemble(flame_rec, dg))
+    assert st["max_slot_used"] < st["n_slots"]
+    assert not np.isnan(out).any()
+    for i in range(2):
+        assert np.abs(out[i][free] - golden_flame["iid_free_verts"][i]).max() < 0.1 * flame["tol"]
+        assert np.array_equal(out[i][nfv], V[nfv])
+
+
+def test_emulated_large_deformation(flame_rec, flame_oracle, flame, golden_flame):
+    V, F, nfv, nft = flame["V"], flame["F"], flame["nfv"], flame["nft"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    active = np.setdiff1d(np.arange(len(F)), nft)
+    full = np.zeros((1, len(F), 9), dtype=np.float32)
+    full[0, active] = golden_flame["integ30_dgrad_active"]
+    out, _ = E.solve(flame_rec, E.assemble(flame_rec, full.reshape(1, -1)))
+    assert np.abs(out[0][free] - golden_flame["integ30_free_verts"]).max() < flame["tol"]
+
+
+def test_emulated_small_mesh_modes(golden_small):
+    V, F, border = W.grid_mesh()
+    dg = W.iid_dgrad(4, len(F), sigma=0.05, seed=7)
+    tol = 1e-6 * W.bbox_diag(V)
+    r = D.Reconstructor(V, F, cnsts=border, device=-1)
+    out, _ = E.solve(r, E.assemble(r, dg))
+    assert np.abs(out - golden_small["cnst_verts"]).max() < tol
+    # raw matrices
+    dm = golden_small["deform_mat"].astype(np.float32).reshape(1, -1)
+    out, _ = E.solve(r, E.assemble(r, dm, mode="matrix"))
+    assert np.abs(out[0] - golden_small["from_dm_verts"]).max() < tol
+    # moved constraints: the base solution is recomputed on the host
+    Cm = (V[border] + np.float32(0.001)).astype(np.float32)
+    r.set_constraint_positions(Cm)
+    out, _ = E.solve(r, E.assemble(r, dg[:1]), cnst_pos=Cm)
+    assert np.abs(out[0] - golden_small["moved_cnst_verts"]).max() < tol
+    # single constraint
+    r1 = D.Reconstructor(V, F, cnsts=[5], device=-1)
+    out, _ = E.solve(r1, E.assemble(r1, dg[1:2]))
+    assert np.abs(out[0] - golden_small["one_cnst_verts"]).max() < 5 * tol    # cond ~1e8: fp32 sweeps
+    # correspondences
+    cc, cf = golden_small["corr_count"], golden_small["corr_faces"]
+    rc = D.Reconstructor(V, F, cnsts=border, corrs=cc, device=-1)
+    rc.set_correspondences(cc, cf, n_src_tris=11)
+    src = W.iid_dgrad(1, 11, sigma=0.05, seed=9)
+    out, _ = E.solve(rc, E.assemble(rc, src))
+    assert np.abs(out[0] - golden_small["corr_verts"]).max() < tol
+
+
+def test_emulated_tile_boundaries():
+    """33 frames = one full tile + a 1-frame tile; every frame must equal its single-frame result."""
+    V, F, border = W.grid_mesh()
+    r = D.Reconstructor(V, F, cnsts=border, device=-1)
+    dg = W.iid_dgrad(33, len(F), sigma=0.05, seed=3)
+    out, _ = E.solve(r, E.assemble(r, dg))
+    one, _ = E.solve(r, E.assemble(r, dg[32:33]))
+    assert np.array_equal(out[32], one[0])
+    o = TriangleDeformationOracle(); o.set_target(V, F, cnsts=border)
+    ref = o.get_mesh(dg[17].astype(np.float64), vert_cnsts=V[border])
+    assert np.abs(out[17] - ref).max() < 1e-6 * W.bbox_diag(V)
