@@ -250,7 +250,7 @@ def main():
 
     # per-kernel device time (library's own CUDA events on the launch stream), separate pass
     rec.set_timing(True)
-    stage = {"decode_ms": 0.0, "assembly_ms": 0.0, "solve_ms": 0.0, "fill_ms": 0.0}
+    stage = {"decode_ms": 0.0, "assembly_ms": 0.0, "solve_ms": 0.0, "output_ms": 0.0}
     reps = max(3, min(args.steps, 10))
     for i in range(reps + 1):
         flush.zero_()

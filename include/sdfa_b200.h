@@ -126,7 +126,7 @@ int sdfa_get_deform_grad_host(const float *verts_a, const float *verts_b, int n_
 long long sdfa_launch_count(void);
 
 /* Per-stage device time of the most recent *_dev / *_host reconstruct call when timing is enabled
- * with sdfa_set_timing(h, 1): ms[0]=decode, ms[1]=assembly, ms[2]=solve, ms[3]=fill.  Enabling
+ * with sdfa_set_timing(h, 1): ms[0]=decode, ms[1]=assembly, ms[2]=solve, ms[3]=output.  Enabling
  * timing adds event records + a synchronise per call. */
 int sdfa_set_timing(sdfa_handle *h, int enable);
 int sdfa_last_timing(const sdfa_handle *h, float ms[4]);

@@ -36,7 +36,7 @@ struct sdfa_handle {
     bool has_pca = false, has_full_pca = false;
     std::vector<int32_t> needed_tris;     // source triangles the active equations read (decode keeps these)
     // growable scratch
-    float *rhs = nullptr; size_t rhs_cap = 0;          // [frames][n_free][3]
+    float *rhs = nullptr; size_t rhs_cap = 0;          // tile-major scratch [tiles][n_free][3][32]
     float *dgrad_c = nullptr; size_t dgrad_c_cap = 0;  // compact decoded dgrad
     float *io_in = nullptr; size_t io_in_cap = 0;      // staging for *_host entry points
     float *io_out = nullptr; size_t io_out_cap = 0;
@@ -141,7 +141,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         if ((rc = build_system(p, err)) != 0) { delete h; return fail(SDFA_ERR_ARG, "sdfa_create: " + err); }
         if ((rc = order_and_factor(p, err)) != 0) { delete h; return fail(SDFA_ERR_FACTOR, "sdfa_create: " + err); }
         compute_base_solution(p, nullptr);
-        build_solve_program(p, /*piece_cap=*/64);
+        build_solve_program(p, /*piece_cap=*/64, /*supernode_cap=*/32);
         build_assembly_plan(p, /*rows_per_block=*/128);
     } catch (const std::exception &e) {
         delete h;
@@ -181,16 +181,19 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             if ((r = upload_mut(h, tmp, &d.eq_src_compact))) return r;
             if ((r = upload(h, p.prog.bytes, &d.prog))) return r;
             if ((r = upload(h, p.prog.stage_off, &d.stage_off))) return r;
+            if ((r = upload(h, p.prog.io_desc, &d.io_desc))) return r;
+            if ((r = upload(h, p.prog.io_phase, &d.io_phase))) return r;
             d.n_stages = (int)p.prog.stage_off.size() - 1;
             d.n_slots = p.prog.n_slots;
-            std::vector<int32_t> row_vert(p.n_free);
-            for (int i = 0; i < p.n_free; ++i) row_vert[i] = p.free_to_vi[p.perm[i]];
-            if ((r = upload(h, row_vert, &d.row_vert))) return r;
+            d.n_phases_fwd = p.prog.n_phases_fwd;
+            d.n_phases_bwd = p.prog.n_phases_bwd;
+            std::vector<int32_t> vert_row(p.n_verts);
+            for (int v = 0; v < p.n_verts; ++v)
+                vert_row[v] = p.vi_to_free[v] >= 0 ? p.iperm[p.vi_to_free[v]] : -1 - p.vi_to_cnst[v];
+            if ((r = upload(h, vert_row, &d.vert_row))) return r;
             std::vector<float> z((size_t)p.n_free * 3, 0.f);
             if ((r = upload_mut(h, z, &d.xbase_hi))) return r;
             if ((r = upload_mut(h, z, &d.xbase_lo))) return r;
-            std::vector<int32_t> cv(p.cnsts.begin(), p.cnsts.end());
-            if ((r = upload(h, cv, &d.cnst_vert))) return r;
             std::vector<float> cz((size_t)p.n_cnsts * 3, 0.f);
             if ((r = upload_mut(h, cz, &d.cnst_pos))) return r;
             if ((r = upload_base(h))) return r;
@@ -301,13 +304,14 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
 static int reconstruct_core(sdfa_handle *h, const float *dgrad_dev, long long stride, const int32_t *eq_src, int mode,
                             int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
     int rc;
-    if ((rc = grow(&h->rhs, &h->rhs_cap, (size_t)n_frames * h->dev.n_free * 3))) return rc;
+    const size_t n_tiles = ((size_t)n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
+    if ((rc = grow(&h->rhs, &h->rhs_cap, n_tiles * h->dev.n_free * SLOT_WORDS))) return rc;
     if ((rc = time_mark(h, 1, s))) return rc;
     CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, eq_src, n_frames, mode, h->rhs, s));
     if ((rc = time_mark(h, 2, s))) return rc;
-    CUDA_TRY(launch_solve(h->dev, h->rhs, n_frames, out_dev, s));
+    CUDA_TRY(launch_solve(h->dev, h->rhs, n_frames, s));
     if ((rc = time_mark(h, 3, s))) return rc;
-    CUDA_TRY(launch_fill_constraints(h->dev, n_frames, out_dev, s));
+    CUDA_TRY(launch_output(h->dev, h->rhs, n_frames, out_dev, s));
     if ((rc = time_mark(h, 4, s))) return rc;
     return time_finish(h, s, decoded);
 }
@@ -501,6 +505,8 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
     if (w == "tri_u") return give(p.tri_u, dst, cap);
     if (w == "prog") return give(p.prog.bytes, dst, cap);
     if (w == "stage_off") return give(p.prog.stage_off, dst, cap);
+    if (w == "io_desc") return give(p.prog.io_desc, dst, cap);
+    if (w == "io_phase") return give(p.prog.io_phase, dst, cap);
     if (w == "eq_src") return give(h->eq_src_host, dst, cap);
     if (w == "asm_eq_id") return give(p.asmplan.eq_id, dst, cap);
     if (w == "asm_eq_u") return give(p.asmplan.eq_u, dst, cap);
@@ -513,11 +519,12 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
         return give(b, dst, cap);
     }
     if (w == "stats") {
-        std::vector<long long> s = {p.prog.n_slots, p.prog.n_pieces, p.prog.n_steps_fwd, p.prog.n_steps_bwd,
+        std::vector<long long> s = {p.prog.n_slots, p.prog.n_phases_fwd, p.prog.n_steps_fwd, p.prog.n_steps_bwd,
                                     p.prog.n_entries, (long long)p.prog.stage_off.size() - 1,
                                     (long long)p.prog.bytes.size(), p.asmplan.max_eq_per_block,
                                     (long long)p.asmplan.eq_id.size(), (long long)p.asmplan.blocks.size(),
-                                    (long long)solve_smem_bytes(p.prog.n_slots)};
+                                    (long long)solve_smem_bytes(p.prog.n_slots), p.prog.n_supernodes,
+                                    (long long)p.prog.io_desc.size()};
         return give(s, dst, cap);
     }
     return -1;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "plan.hpp"
 
 namespace sdfa {
 
@@ -22,11 +23,12 @@ struct DevicePlan {
     // ---- solve (K3)
     const uint8_t  *prog = nullptr;         // 16-byte aligned stage stream
     const uint32_t *stage_off = nullptr;
-    int n_stages = 0, n_slots = 0;
-    const int32_t  *row_vert = nullptr;     // permuted row -> vertex index
+    const IoDesc   *io_desc = nullptr;
+    const IoPhase  *io_phase = nullptr;
+    int n_stages = 0, n_slots = 0, n_phases_fwd = 0, n_phases_bwd = 0;
+    // ---- output (K5)
+    const int32_t  *vert_row = nullptr;     // vertex -> permuted row (>= 0) or -1 - constraint index
     float          *xbase_hi = nullptr, *xbase_lo = nullptr;   // [n_free*3] permuted order
-    // ---- constrained vertices (K4)
-    const int32_t  *cnst_vert = nullptr;    // [n_cnsts]
     float          *cnst_pos = nullptr;     // [n_cnsts*3]
     // ---- decode (K1)
     int k_scale = 0, k_rotat = 0, n_needed = 0;   // n_needed = source triangles some active equation reads
@@ -40,8 +42,8 @@ enum AssemblyMode { ASM_DGRAD = 0, ASM_MATRIX = 1 };
 // All launchers are asynchronous on `stream` and return the cudaError_t of the launch.
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, const int32_t *eq_src,
                             int n_frames, int mode, float *rhs, cudaStream_t stream);
-cudaError_t launch_solve(const DevicePlan &d, float *rhs_scratch, int n_frames, float *out, cudaStream_t stream);
-cudaError_t launch_fill_constraints(const DevicePlan &d, int n_frames, float *out, cudaStream_t stream);
+cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream);
+cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream);
 cudaError_t launch_decode(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                           bool full_layout, float *dgrad_out, cudaStream_t stream);
 cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, const uint32_t *tris, int n_tris,

@@ -21,12 +21,15 @@ long long launch_counter() { return g_launches.load(); }
 // =============================================================================================
 // K2: per-equation transform + A^T (T^T - I) assembly.
 //
-// grid = (row blocks, frame lanes); a CTA owns one row block of one frame at a time.
+// grid = (row blocks, frame tiles); a CTA owns one row block for the 32 frames of one tile.  Per frame:
 //   phase 1  thread per block-local equation: E = R*S - I from the 9 dgrad values
 //            (impl.hpp:226-244; rotation_log_exp::exp, rotation/utils_rotation.cpp:20-51), then the two
 //            corner vectors g2 = E*U0, g3 = E*U1 and g1 = -(g2+g3) (coefficients of impl.hpp:106-116)
 //            -> shared memory [eq][corner][3] (stride 9 words: conflict free)
-//   phase 2  thread per row: sum the corner vectors incident to the row (CSR), write rhs[frame][row][3]
+//   phase 2  thread per row: sum the corner vectors incident to the row (CSR, no atomics) into a
+//            [row*3+c][33] transpose buffer
+// and after the 32 frames the buffer is written out as the solve kernel's tile-major rows
+// scratch[tile][row][c][frame] (one coalesced 128-byte line per warp instruction).
 // E is evaluated without ever forming 1 + small:  E u = t + Q (u + t),  t = Es u,
 //   Q v = a W v + b W (W v),  a = sin(th)/th,  b = (1 - cos th)/th^2 = 2 sin^2(th/2)/th^2.
 struct AsmParams {
@@ -39,7 +42,7 @@ struct AsmParams {
     const float *dgrad;
     long long frame_stride;
     float *rhs;
-    int n_frames, n_free, mode;
+    int n_frames, n_free, mode, max_eq;
 };
 
 __device__ __forceinline__ void corner_vec(const float *d, float a, float b, const float *u, float *g) {
@@ -60,13 +63,21 @@ __device__ __forceinline__ void corner_vec(const float *d, float a, float b, con
     g[2] = t2 + a * p2 + b * q2;
 }
 
-__global__ void __launch_bounds__(128) k_assemble(AsmParams P) {
-    extern __shared__ float g_sh[];
+constexpr int ASM_THREADS = 128;
+constexpr int TPAD = 33;          // transpose-buffer row stride (odd: conflict free both ways)
+
+__global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
+    extern __shared__ float sh[];
+    float *g_sh = sh;                               // [max_eq][9]
+    float *t_sh = sh + P.max_eq * 9;                // [rows*3][33]
     const int4 blk = P.blocks[blockIdx.x];
     const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
-    for (int frame = blockIdx.y; frame < P.n_frames; frame += gridDim.y) {
-        const float *row = P.dgrad + (long long)frame * P.frame_stride;
-        for (int e = threadIdx.x; e < n_eq; e += blockDim.x) {
+    const int tile = blockIdx.y;
+    const int frame0 = tile * FRAMES_PER_TILE;
+    const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
+    for (int f = 0; f < nvalid; ++f) {
+        const float *row = P.dgrad + (long long)(frame0 + f) * P.frame_stride;
+        for (int e = threadIdx.x; e < n_eq; e += ASM_THREADS) {
             const int ge = blk.x + e;
             const int src = P.eq_src[P.eq_id[ge]];
             float u0[3], u1[3], g2[3], g3[3];
@@ -81,9 +92,9 @@ __global__ void __launch_bounds__(128) k_assemble(AsmParams P) {
                     float th = sqrtf(th2);
                     float a = 0.f, b = 0.f;
                     if (th >= 1e-6f) {          // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
-                        float sh = sinf(0.5f * th);
+                        float sh2 = sinf(0.5f * th);
                         a = sinf(th) / th;
-                        b = 2.f * sh * sh / th2;
+                        b = 2.f * sh2 * sh2 / th2;
                     }
                     corner_vec(d, a, b, u0, g2);
                     corner_vec(d, a, b, u1, g3);
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(128) k_assemble(AsmParams P) {
             for (int c = 0; c < 3; ++c) { g[c] = -(g2[c] + g3[c]); g[3 + c] = g2[c]; g[6 + c] = g3[c]; }
         }
         __syncthreads();
-        for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        for (int r = threadIdx.x; r < n_rows; r += ASM_THREADS) {
             const int gr = blk.z + r;
             const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -116,51 +127,64 @@ __global__ void __launch_bounds__(128) k_assemble(AsmParams P) {
                 const float *g = g_sh + 3 * (int)P.inc[q];
                 s0 += g[0]; s1 += g[1]; s2 += g[2];
             }
-            float *dst = P.rhs + ((long long)frame * P.n_free + P.row_perm[gr]) * 3;
-            dst[0] = s0; dst[1] = s1; dst[2] = s2;
+            float *t = t_sh + (3 * r) * TPAD + f;
+            t[0] = s0; t[TPAD] = s1; t[2 * TPAD] = s2;
         }
         __syncthreads();
     }
+    // transposed write-out: line (row, c) = 32 consecutive frames = 128 bytes
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *dst_tile = P.rhs + (long long)tile * P.n_free * SLOT_WORDS;
+    for (int line = warp; line < n_rows * 3; line += ASM_THREADS / 32) {
+        const int r = line / 3, c = line - 3 * r;
+        const float v = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
+        dst_tile[(long long)P.row_perm[blk.z + r] * SLOT_WORDS + c * COORD_STRIDE + lane] = v;
+    }
+}
+
+static size_t asm_smem_bytes(const DevicePlan &d) {
+    return ((size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * TPAD) * sizeof(float);
 }
 
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, const int32_t *eq_src,
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     AsmParams P{d.asm_blocks, d.asm_eq_id, d.asm_eq_u, d.asm_row_perm, d.asm_row_ptr, d.asm_inc, eq_src,
-                dgrad, frame_stride, rhs, n_frames, d.n_free, mode};
-    size_t smem = (size_t)d.asm_max_eq * 9 * sizeof(float);
+                dgrad, frame_stride, rhs, n_frames, d.n_free, mode, d.asm_max_eq};
+    const size_t smem = asm_smem_bytes(d);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid((unsigned)d.n_asm_blocks, (unsigned)(n_frames < 32768 ? n_frames : 32768));
-    k_assemble<<<grid, 128, smem, stream>>>(P);
+    const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
+    dim3 grid((unsigned)d.n_asm_blocks, (unsigned)n_tiles);
+    k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
 }
 
 // =============================================================================================
-// K3: batched multi-RHS sparse triangular solve (forward + backward) -- interpreter of the solve program
-// built by schedule.cpp.  One CTA = one tile of 32 frames (lane = frame, 3 coordinates per lane).
-//   warp 0            producer: streams the program's stages global -> shared ring with cp.async.bulk
-//                     (TMA), completion on mbarriers
-//   warps 1..NCW      consumers: interpret the ops; rows of a level are dealt round-robin to the warps,
-//                     levels are separated by a named barrier over the consumer warps only
-// The state (piece + root-path rows, 396 B per row) lives in shared memory; finished rows are spilled to
-// the rhs scratch in global memory (L2 resident) and re-read by the backward sweep.
-constexpr int RING = 4;
-constexpr int NCW = 8;                          // consumer warps
-constexpr int SOLVE_THREADS = 32 * (NCW + 1);
+// K3: batched multi-RHS sparse triangular solve (forward + backward): level-scheduled supernodal sweeps
+// over the program built by schedule.cpp.  One CTA = one tile of 32 frames (lane = frame, 3 coordinates
+// per lane); persistent CTAs loop over tiles.  Warp roles:
+//   warp 0   streamer : copies the task lists' stages global -> shared ring (cp.async.bulk + mbarrier)
+//   warp 1   IO       : per phase, TMA bulk-loads the piece's rows scratch -> state slots (prefetched one
+//                       phase ahead) and bulk-stores finished rows state -> scratch
+//   warps 2+ consumers: run the row tasks of a level (dealt round-robin), one named barrier per level
+// The factor is never re-read from HBM per frame: every task entry fetched from the ring is applied to
+// 96 right-hand sides (32 frames x 3 coordinates) of the tile.
+constexpr int RING = 3;
+constexpr int NCW = 12;                         // consumer warps
+constexpr int SOLVE_THREADS = 32 * (NCW + 2);
 
 struct SolveParams {
     const uint8_t *prog;
     const uint32_t *stage_off;
-    int n_stages, n_slots;
-    float *rhs;                                 // [n_frames][n_free][3] in: rhs, scratch: y
-    float *out;                                 // [n_frames][n_verts][3]
-    const int32_t *row_vert;
-    const float *xb_hi, *xb_lo;
-    int n_frames, n_free, n_verts, n_tiles;
+    const IoDesc *io_desc;
+    const IoPhase *io_phase;
+    int n_stages, n_slots, n_phases_fwd, n_phases_bwd;
+    float *scratch;                             // [n_tiles][n_free][3][32]: rhs in, x out (in place)
+    int n_free, n_tiles;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -187,6 +211,13 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 
 __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state_lane) {
@@ -204,43 +235,49 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
         b0 = fmaf(c1, s1[0], b0); b1 = fmaf(c1, s1[COORD_STRIDE], b1); b2 = fmaf(c1, s1[2 * COORD_STRIDE], b2);
     }
     float *t = reinterpret_cast<float *>(state_lane + th.x);
-    const float dinv = __uint_as_float(th.z);                      // 1.0 for partial (non-final) rows
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     if (!(th.y & TASK_OVERWRITE)) { v0 = t[0]; v1 = t[COORD_STRIDE]; v2 = t[2 * COORD_STRIDE]; }
-    t[0] = (v0 - (a0 + b0)) * dinv;
-    t[COORD_STRIDE] = (v1 - (a1 + b1)) * dinv;
-    t[2 * COORD_STRIDE] = (v2 - (a2 + b2)) * dinv;
+    t[0] = v0 - (a0 + b0);
+    t[COORD_STRIDE] = v1 - (a1 + b1);
+    t[2 * COORD_STRIDE] = v2 - (a2 + b2);
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveParams P) {
+// shared memory map: [ring RING*STAGE_BYTES][barriers 8*(2*RING+4)][pad to 128][state n_slots*384]
+constexpr int SOLVE_BAR_BYTES = 128;
+constexpr int BAR_FULL = 0, BAR_EMPTY = RING, BAR_LD = 2 * RING, BAR_DONE = 2 * RING + 2;
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *ring = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING * STAGE_BYTES);   // full[RING], empty[RING]
-    float *state = reinterpret_cast<float *>(smem + RING * STAGE_BYTES + 2 * RING * 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING * STAGE_BYTES);
+    uint8_t *state = smem + RING * STAGE_BYTES + SOLVE_BAR_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // zero the state: padding entries of row tasks multiply slot 0 by 0.0, which must not be NaN
-    for (int i = threadIdx.x; i < P.n_slots * SLOT_WORDS; i += blockDim.x) state[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < RING; ++s) {
-            mbar_init(smem_u32(&bars[s]), 1);            // full: the producer's arrive.expect_tx
-            mbar_init(smem_u32(&bars[RING + s]), NCW);   // empty: one arrive per consumer warp
+            mbar_init(smem_u32(&bars[BAR_FULL + s]), 1);        // streamer's arrive.expect_tx
+            mbar_init(smem_u32(&bars[BAR_EMPTY + s]), NCW);     // one arrive per consumer warp
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bars[BAR_LD + s]), 1);          // IO warp's arrive.expect_tx
+            mbar_init(smem_u32(&bars[BAR_DONE + s]), NCW);      // one arrive per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_async_smem();
     }
     __syncthreads();
+    const int n_phases = P.n_phases_fwd + P.n_phases_bwd;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ producer
+        // ------------------------------------------------------------------ streamer
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                 for (int s = 0; s < P.n_stages; ++s, ++it) {
                     const uint32_t slot = it % RING, phase = (it / RING) & 1u;
-                    mbar_wait(smem_u32(&bars[RING + slot]), phase ^ 1u);
+                    mbar_wait(smem_u32(&bars[BAR_EMPTY + slot]), phase ^ 1u);
                     const uint32_t off = P.stage_off[s], bytes = P.stage_off[s + 1] - off;
-                    const uint32_t full = smem_u32(&bars[slot]);
+                    const uint32_t full = smem_u32(&bars[BAR_FULL + slot]);
                     mbar_arrive_expect_tx(full, bytes);
                     tma_bulk_g2s(smem_u32(ring + slot * STAGE_BYTES), P.prog + off, bytes, full);
                 }
@@ -248,73 +285,92 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveParams P) {
         }
         return;
     }
+    if (warp == 1) {
+        // ------------------------------------------------------------------ IO
+        if (lane == 0) {
+            uint32_t g = 0;                                     // running phase counter (consumers count alike)
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                uint8_t *tile_base = reinterpret_cast<uint8_t *>(P.scratch + (long long)tile * P.n_free * SLOT_WORDS);
+                auto issue_loads = [&](int q, uint32_t gq) {
+                    const IoPhase ph = P.io_phase[q];
+                    uint32_t bytes = 0;
+                    for (uint32_t i = ph.load_begin; i < ph.load_end; ++i) bytes += P.io_desc[i].n_rows * SLOT_BYTES;
+                    const uint32_t bar = smem_u32(&bars[BAR_LD + (gq & 1u)]);
+                    mbar_arrive_expect_tx(bar, bytes);
+                    for (uint32_t i = ph.load_begin; i < ph.load_end; ++i) {
+                        const IoDesc d = P.io_desc[i];
+                        tma_bulk_g2s(smem_u32(state + (size_t)d.slot * SLOT_BYTES), tile_base + (size_t)d.row * SLOT_BYTES,
+                                     d.n_rows * SLOT_BYTES, bar);
+                    }
+                };
+                int q0 = 0;
+                for (int sweep = 0; sweep < 2; ++sweep) {
+                    const int nq = sweep == 0 ? P.n_phases_fwd : P.n_phases_bwd;
+                    issue_loads(q0, g);
+                    if (nq > 1) issue_loads(q0 + 1, g + 1);
+                    for (int q = 0; q < nq; ++q, ++g) {
+                        mbar_wait(smem_u32(&bars[BAR_DONE + (g & 1u)]), (g >> 1) & 1u);   // consumers finished phase q
+                        const IoPhase ph = P.io_phase[q0 + q];
+                        for (uint32_t i = ph.store_begin; i < ph.store_end; ++i) {
+                            const IoDesc d = P.io_desc[i];
+                            tma_bulk_s2g(tile_base + (size_t)d.row * SLOT_BYTES, smem_u32(state + (size_t)d.slot * SLOT_BYTES),
+                                         d.n_rows * SLOT_BYTES);
+                        }
+                        tma_commit();
+                        if (q + 2 < nq) {
+                            tma_wait_read0();                   // the stored slots may be reused by these loads
+                            issue_loads(q0 + q + 2, g + 2);
+                        }
+                    }
+                    tma_wait_all0();                            // the next sweep / tile re-reads what was stored
+                    q0 += nq;
+                }
+            }
+        }
+        return;
+    }
     // ---------------------------------------------------------------------- consumers
-    const int cw = warp - 1;
-    uint8_t *state_lane = reinterpret_cast<uint8_t *>(state + lane);
-    uint32_t it = 0;
+    const int cw = warp - 2;
+    uint8_t *state_lane = state + lane * 4;
+    uint32_t it = 0, g = 0;
+    (void)n_phases;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const int frame0 = tile * FRAMES_PER_TILE;
-        const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
         for (int s = 0; s < P.n_stages; ++s, ++it) {
             const uint32_t slot = it % RING, phase = (it / RING) & 1u;
-            mbar_wait(smem_u32(&bars[slot]), phase);
+            mbar_wait(smem_u32(&bars[BAR_FULL + slot]), phase);
             const uint8_t *stage = ring + slot * STAGE_BYTES;
             const int n_ops = (int)reinterpret_cast<const uint32_t *>(stage)[0];
             uint32_t at = 16;
             for (int o = 0; o < n_ops; ++o) {
                 const uint4 hw = *reinterpret_cast<const uint4 *>(stage + at);   // OpHeader
                 const uint32_t type = hw.x & 0xFFFFu, flags = hw.x >> 16;
-                if (flags & OPF_SYNC_BEFORE) consumer_bar();
                 if (type == OP_ROWS) {
                     const uint32_t *table = reinterpret_cast<const uint32_t *>(stage + hw.z);
                     for (uint32_t t = cw; t < hw.y; t += NCW) run_row_task(stage + table[t], state_lane);
                     at = hw.w;
-                } else {
-                    const int row0 = (int)hw.y, n_rows = (int)hw.z, ne = 3 * n_rows;
-                    const uint32_t *table = reinterpret_cast<const uint32_t *>(stage + hw.w);
-                    for (int f = cw; f < nvalid; f += NCW) {
-                        if (type == OP_LOAD) {
-                            const float *src = P.rhs + ((long long)(frame0 + f) * P.n_free + row0) * 3;
-                            for (int e = lane; e < ne; e += 32) {
-                                const int r = e / 3, c = e - 3 * r;
-                                const uint32_t w = table[r];
-                                float *dst = state + (w & 0xFFFFFFu) + c * COORD_STRIDE + f;
-                                float v = src[e];
-                                if (w & LOAD_ADD_BIT) v += *dst;
-                                *dst = v;
-                            }
-                        } else if (type == OP_STORE_Y) {
-                            float *dst = P.rhs + ((long long)(frame0 + f) * P.n_free + row0) * 3;
-                            for (int e = lane; e < ne; e += 32) {
-                                const int r = e / 3, c = e - 3 * r;
-                                dst[e] = state[(table[r] & 0xFFFFFFu) + c * COORD_STRIDE + f];
-                            }
-                        } else {   // OP_STORE_X
-                            float *dst = P.out + (long long)(frame0 + f) * P.n_verts * 3;
-                            for (int e = lane; e < ne; e += 32) {
-                                const int r = e / 3, c = e - 3 * r;
-                                const float v = state[(table[r] & 0xFFFFFFu) + c * COORD_STRIDE + f];
-                                const int row = row0 + r;
-                                dst[(long long)__ldg(P.row_vert + row) * 3 + c] =
-                                    __ldg(P.xb_hi + row * 3 + c) + (__ldg(P.xb_lo + row * 3 + c) + v);
-                            }
-                        }
-                    }
-                    at = hw.w + (((uint32_t)n_rows * 4u + 15u) & ~15u);
+                    if (flags & OPF_SYNC_AFTER) consumer_bar();
+                } else if (type == OP_PHASE_BEGIN) {
+                    mbar_wait(smem_u32(&bars[BAR_LD + (g & 1u)]), (g >> 1) & 1u);
+                    at += 16;
+                } else {   // OP_PHASE_END: the level barrier before it has ordered all consumer writes
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars[BAR_DONE + (g & 1u)]));
+                    ++g;
+                    at += 16;
                 }
-                if (flags & OPF_SYNC_AFTER) consumer_bar();
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars[RING + slot]));
+            if (lane == 0) mbar_arrive(smem_u32(&bars[BAR_EMPTY + slot]));
         }
     }
 }
 
 size_t solve_smem_bytes(int n_slots) {
-    return (size_t)RING * STAGE_BYTES + 2 * RING * 8 + (size_t)n_slots * SLOT_BYTES;
+    return (size_t)RING * STAGE_BYTES + SOLVE_BAR_BYTES + (size_t)n_slots * SLOT_BYTES;
 }
 
-cudaError_t launch_solve(const DevicePlan &d, float *rhs_scratch, int n_frames, float *out, cudaStream_t stream) {
+cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     const size_t smem = solve_smem_bytes(d.n_slots);
     static int configured_device = -1;
@@ -330,8 +386,8 @@ cudaError_t launch_solve(const DevicePlan &d, float *rhs_scratch, int n_frames, 
         configured_smem = smem;
     }
     const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
-    SolveParams P{d.prog, d.stage_off, d.n_stages, d.n_slots, rhs_scratch, out, d.row_vert, d.xbase_hi, d.xbase_lo,
-                  n_frames, d.n_free, d.n_verts, n_tiles};
+    SolveParams P{d.prog, d.stage_off, d.io_desc, d.io_phase, d.n_stages, d.n_slots, d.n_phases_fwd, d.n_phases_bwd,
+                  scratch, d.n_free, n_tiles};
     int grid = d.sm_count * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
     k_solve<<<grid, SOLVE_THREADS, smem, stream>>>(P);
@@ -340,25 +396,54 @@ cudaError_t launch_solve(const DevicePlan &d, float *rhs_scratch, int n_frames, 
 }
 
 // =============================================================================================
-// K4: constrained vertices are copied through unchanged (impl.hpp:302-308).
-__global__ void k_fill_constraints(const int32_t *cnst_vert, const float *cnst_pos, int n_cnsts, int n_verts,
-                                   int n_frames, float *out) {
-    const int ne = n_cnsts * 3;
-    for (int frame = blockIdx.y; frame < n_frames; frame += gridDim.y) {
-        float *dst = out + (long long)frame * n_verts * 3;
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-            const int i = e / 3, c = e - 3 * i;
-            dst[(long long)__ldg(cnst_vert + i) * 3 + c] = __ldg(cnst_pos + e);
+// K5: output.  Transposes the solved displacement rows scratch[tile][row][c][frame] into the reference
+// layout out[frame][vertex][3] (pybind.cpp:108), adds the fp64-computed base solution (kept as a
+// hi/lo float pair) and copies the constrained vertices through (impl.hpp:295-308) -- every output
+// byte is written exactly once, coalesced.
+constexpr int OUT_VC = 64;                       // vertices per CTA
+struct OutParams {
+    const float *scratch;
+    const int32_t *vert_row;                     // vertex -> permuted row, or -1-(constraint index)
+    const float *xb_hi, *xb_lo, *cnst_pos;
+    float *out;
+    int n_frames, n_free, n_verts;
+};
+
+__global__ void __launch_bounds__(256) k_output(OutParams P) {
+    __shared__ float t_sh[OUT_VC * 3 * TPAD];
+    const int v0 = blockIdx.x * OUT_VC;
+    const int nv = min(OUT_VC, P.n_verts - v0);
+    const int tile = blockIdx.y;
+    const int frame0 = tile * FRAMES_PER_TILE;
+    const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *src_tile = P.scratch + (long long)tile * P.n_free * SLOT_WORDS;
+    for (int line = warp; line < nv * 3; line += 8) {
+        const int vl = line / 3, c = line - 3 * vl;
+        const int row = __ldg(P.vert_row + v0 + vl);
+        float v;
+        if (row >= 0) {
+            const float x = src_tile[(long long)row * SLOT_WORDS + c * COORD_STRIDE + lane];
+            v = __ldg(P.xb_hi + row * 3 + c) + (__ldg(P.xb_lo + row * 3 + c) + x);
+        } else {
+            v = __ldg(P.cnst_pos + (-1 - row) * 3 + c);
         }
+        t_sh[line * TPAD + lane] = v;
+    }
+    __syncthreads();
+    const int ne = nv * 3;
+    for (int f = warp; f < nvalid; f += 8) {
+        float *dst = P.out + ((long long)(frame0 + f) * P.n_verts + v0) * 3;
+        for (int e = lane; e < ne; e += 32) dst[e] = t_sh[e * TPAD + f];
     }
 }
 
-cudaError_t launch_fill_constraints(const DevicePlan &d, int n_frames, float *out, cudaStream_t stream) {
-    if (n_frames <= 0 || d.n_cnsts == 0) return cudaSuccess;
-    int bx = (d.n_cnsts * 3 + 255) / 256;
-    if (bx > 64) bx = 64;
-    dim3 grid((unsigned)bx, (unsigned)(n_frames < 32768 ? n_frames : 32768));
-    k_fill_constraints<<<grid, 256, 0, stream>>>(d.cnst_vert, d.cnst_pos, d.n_cnsts, d.n_verts, n_frames, out);
+cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    OutParams P{scratch, d.vert_row, d.xbase_hi, d.xbase_lo, d.cnst_pos, out, n_frames, d.n_free, d.n_verts};
+    const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
+    dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)n_tiles);
+    k_output<<<grid, 256, 0, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
 }

@@ -11,31 +11,31 @@
 namespace sdfa {
 
 // ------------------------------------------------------------------------------------------
-// Geometry of the solve tile.  One CTA of the solve kernel owns FRAMES_PER_TILE frames; a state
-// "slot" holds one row of the (permuted) system for all those frames: [3 coords][COORD_STRIDE] floats.
-// COORD_STRIDE is odd (33) so that the transposing loads/stores (lanes run along rows) are bank
-// conflict free while the row sweeps (lanes run along frames) stay stride-1.
+// Geometry of the solve tile.  One CTA of the solve kernel owns FRAMES_PER_TILE frames (lane = frame).
+// A state "slot" holds one row of the permuted system for all those frames: [3 coords][32 frames] floats
+// = 384 bytes, which is also the layout of one row in the global scratch ("tile-major":
+// scratch[tile][row][coord][frame]), so rows move between global and shared memory with plain TMA bulk copies.
 constexpr int FRAMES_PER_TILE = 32;
-constexpr int COORD_STRIDE    = 33;
-constexpr int SLOT_WORDS      = 3 * COORD_STRIDE;     // 99
-constexpr int SLOT_BYTES      = SLOT_WORDS * 4;       // 396
+constexpr int COORD_STRIDE    = 32;
+constexpr int SLOT_WORDS      = 3 * COORD_STRIDE;     // 96
+constexpr int SLOT_BYTES      = SLOT_WORDS * 4;       // 384
 
 // ------------------------------------------------------------------------------------------
-// Solve program: a byte stream cut into stages of at most STAGE_BYTES that the producer warp streams
-// global -> shared with cp.async.bulk (TMA) into a ring, and the consumer warps interpret.
+// Solve program.  Two sweeps (forward L y = b, backward L^T x = y), each a sequence of PHASES; a phase
+// handles one "piece" (a contiguous range of supernodes of the postordered elimination tree):
+//     data loads (TMA, IO warp)  ->  levels of row tasks (consumer warps)  ->  data stores (TMA, IO warp)
+// The task lists are a byte stream cut into stages of at most STAGE_BYTES that the streamer warp copies
+// global -> shared with cp.async.bulk into a ring; the IO warp follows the separate IoPhase/IoDesc tables.
 constexpr int STAGE_BYTES = 8192;
 
 enum OpType : uint16_t {
-    OP_ROWS    = 1,   // a = n_tasks, b = byte offset (in stage) of the u32 task-offset table,
-                      // c = byte offset of the next op
-    OP_LOAD    = 2,   // a = first permuted row, b = n_rows, c = byte offset of the u32 slot table
-                      // (next op = c + 4*b rounded up to 16)
-    OP_STORE_Y = 3,   // same operands; writes slots back to the rhs/y scratch rows (in place)
-    OP_STORE_X = 4,   // same operands; writes x_base + x to out[frame][vertex(row)]
+    OP_ROWS        = 1,   // a = n_tasks, b = byte offset (in stage) of the u32 task-offset table,
+                          // c = byte offset of the next op
+    OP_PHASE_BEGIN = 2,   // wait until the phase's rows have landed in shared memory
+    OP_PHASE_END   = 3,   // make the phase's results visible to the async proxy and signal the IO warp
 };
 enum OpFlags : uint16_t {
-    OPF_SYNC_BEFORE = 1,   // consumer barrier before the op
-    OPF_SYNC_AFTER  = 2,   // consumer barrier after the op
+    OPF_SYNC_AFTER = 2,    // consumer barrier after the op (end of a level)
 };
 struct OpHeader {        // 16 bytes, 16-byte aligned inside the stage
     uint16_t type, flags;
@@ -44,26 +44,29 @@ struct OpHeader {        // 16 bytes, 16-byte aligned inside the stage
 struct StageHeader {     // first 16 bytes of every stage
     uint32_t n_ops, bytes, reserved0, reserved1;
 };
-// Slot-table entry of OP_LOAD: low 24 bits = slot byte offset / 4 (word offset), bit 31 = accumulate
-// onto what the slot already holds (partial sums from earlier pieces) instead of overwriting.
-constexpr uint32_t LOAD_ADD_BIT = 0x80000000u;
 
 // Row task (OP_ROWS): 16-byte header followed by n entries of 8 bytes {float coeff; u32 src_byte_off}.
-//   acc = sum coeff * slot[src];  v = (OVERWRITE ? 0 : slot[target]) - acc;  if FINAL: v *= dinv
+//   acc = sum coeff * slot[src];   slot[target] = (OVERWRITE ? 0 : slot[target]) - acc
 struct TaskHeader {
     uint32_t target_byte_off;
-    uint32_t n_entries_flags;   // low 24 bits count, bit 24 = FINAL (scale by dinv), bit 25 = OVERWRITE
-    float    dinv;
-    uint32_t reserved;
+    uint32_t n_entries_flags;   // low 24 bits count (even), bit 25 = OVERWRITE
+    uint32_t reserved0, reserved1;
 };
-constexpr uint32_t TASK_FINAL = 1u << 24, TASK_OVERWRITE = 1u << 25;
+constexpr uint32_t TASK_OVERWRITE = 1u << 25;
 struct TaskEntry { float coeff; uint32_t src_byte_off; };
+
+// IO tables: n_rows consecutive permuted rows <-> n_rows consecutive slots, one cp.async.bulk each.
+struct IoDesc { uint32_t row, n_rows, slot, reserved; };
+struct IoPhase { uint32_t load_begin, load_end, store_begin, store_end; };   // ranges in the IoDesc array
 
 struct SolveProgram {
     std::vector<uint8_t>  bytes;        // all stages back to back, each padded to a multiple of 16
     std::vector<uint32_t> stage_off;    // byte offset of each stage, n_stages + 1 entries
+    std::vector<IoDesc>   io_desc;
+    std::vector<IoPhase>  io_phase;     // forward phases then backward phases
+    int n_phases_fwd = 0, n_phases_bwd = 0;
     int n_slots = 0;                    // state slots a CTA needs (peak over both sweeps)
-    int n_pieces = 0, n_steps_fwd = 0, n_steps_bwd = 0;
+    int n_steps_fwd = 0, n_steps_bwd = 0, n_supernodes = 0;
     long long n_entries = 0;            // multiply-adds per (frame, coordinate)
 };
 
@@ -122,7 +125,7 @@ int  order_and_factor(HostPlan &p, std::string &err);             // perm, etree
 void compute_base_solution(HostPlan &p, const float *cnst_pos);   // x_base
 void solve_factored(const HostPlan &p, std::vector<double> &rhs_perm /* [n_free*3] in/out */);
 // schedule.cpp
-void build_solve_program(HostPlan &p, int piece_cap);
+void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap);
 void build_assembly_plan(HostPlan &p, int rows_per_block);
 
 }  // namespace sdfa

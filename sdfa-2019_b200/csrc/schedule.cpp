@@ -29,7 +29,6 @@ namespace {
 struct Task {
     int target_slot;
     uint32_t flags;
-    float dinv;
     std::vector<TaskEntry> entries;
 };
 
@@ -37,13 +36,12 @@ class Emitter {
 public:
     explicit Emitter(SolveProgram &prog) : prog_(prog) { open_stage(); }
 
+    // one level: independent row tasks, dealt round-robin to the consumer warps by the kernel
     void rows(std::vector<Task> &tasks, bool sync_after) {
-        // longest first so the round-robin warp assignment of the kernel is balanced
         std::stable_sort(tasks.begin(), tasks.end(),
                          [](const Task &a, const Task &b) { return a.entries.size() > b.entries.size(); });
         size_t i = 0;
         while (i < tasks.size()) {
-            // how many tasks fit into what is left of this stage
             size_t room = STAGE_BYTES - cur_.size();
             size_t n = 0, bytes = sizeof(OpHeader);
             while (i + n < tasks.size()) {
@@ -73,11 +71,16 @@ public:
                 uint32_t off = (uint32_t)cur_.size();
                 std::memcpy(&cur_[table_at + t * 4], &off, 4);
                 size_t ne = tk.entries.size() + (tk.entries.size() & 1);   // pad to even -> 16 B multiple
-                TaskHeader th{(uint32_t)tk.target_slot * SLOT_BYTES, (uint32_t)ne | tk.flags, tk.dinv, 0};
+                TaskHeader th{(uint32_t)tk.target_slot * SLOT_BYTES, (uint32_t)ne | tk.flags, 0, 0};
                 cur_.resize(off + sizeof(TaskHeader) + ne * sizeof(TaskEntry), 0);
                 std::memcpy(&cur_[off], &th, sizeof(th));
                 if (!tk.entries.empty())
                     std::memcpy(&cur_[off + sizeof(TaskHeader)], tk.entries.data(), tk.entries.size() * sizeof(TaskEntry));
+                if (tk.entries.size() & 1) {
+                    // padding entry: coefficient 0 on the task's own first source (always a live, finite slot)
+                    TaskEntry pad{0.f, tk.entries[0].src_byte_off};
+                    std::memcpy(&cur_[off + sizeof(TaskHeader) + tk.entries.size() * sizeof(TaskEntry)], &pad, sizeof(pad));
+                }
                 prog_.n_entries += (long long)tk.entries.size();
             }
             uint32_t next = (uint32_t)cur_.size();
@@ -85,17 +88,14 @@ public:
             ++n_ops_;
             i += n;
         }
-        if (tasks.empty() && sync_after) { /* nothing to wait for */ }
     }
 
-    void rowspan(OpType type, int first_row, const std::vector<uint32_t> &table, uint16_t flags) {
-        size_t need = sizeof(OpHeader) + (table.size() * 4 + 15) / 16 * 16;
-        if (cur_.size() + need > STAGE_BYTES) { close_stage(); open_stage(); }
+    void marker(OpType type) {
+        if (cur_.size() + sizeof(OpHeader) > STAGE_BYTES) { close_stage(); open_stage(); }
+        OpHeader h{(uint16_t)type, 0, 0, 0, 0};
         size_t op_at = cur_.size();
-        OpHeader h{(uint16_t)type, flags, (uint32_t)first_row, (uint32_t)table.size(), (uint32_t)(op_at + sizeof(OpHeader))};
-        cur_.resize(op_at + need, 0);
+        cur_.resize(op_at + sizeof(OpHeader), 0);
         std::memcpy(&cur_[op_at], &h, sizeof(h));
-        std::memcpy(&cur_[op_at + sizeof(OpHeader)], table.data(), table.size() * 4);
         ++n_ops_;
     }
 
@@ -126,153 +126,329 @@ private:
     int n_ops_ = 0;
 };
 
+// Slot allocator with the reuse delay the kernel's prefetching needs: the loads of phase q+2 are issued
+// while phase q+1 computes, so a slot released at the end of phase q may be handed out again no earlier
+// than for phase q+2.
 class SlotPool {
 public:
-    int alloc() {
-        int s;
-        if (!free_.empty()) { s = free_.back(); free_.pop_back(); }
-        else s = next_++;
-        ++live_;
-        peak_ = std::max(peak_, next_);
-        return s;
+    // contiguous range if one exists below the high-water mark, else grows the pool
+    int alloc_range(int n) {
+        int run = 0;
+        for (int s = 0; s < (int)used_.size(); ++s) {
+            run = used_[s] ? 0 : run + 1;
+            if (run == n) { int b = s - n + 1; mark(b, n); return b; }
+        }
+        int b = (int)used_.size() - run;               // extend a free tail
+        used_.resize(b + n, 0);
+        mark(b, n);
+        return b;
     }
-    void release(int s) { free_.push_back(s); --live_; }
-    int peak() const { return peak_; }
-    // hand out the lowest free ids first: keeps pieces mostly contiguous
-    void sort_free() { std::sort(free_.begin(), free_.end(), std::greater<int>()); }
+    int alloc() { return alloc_range(1); }
+    void release_at_end_of(int phase, int slot) { pending_.push_back({phase, slot}); }
+    // make everything released in phases <= phase available
+    void reclaim(int phase) {
+        size_t k = 0;
+        for (auto &pr : pending_) {
+            if (pr.first <= phase) used_[pr.second] = 0;
+            else pending_[k++] = pr;
+        }
+        pending_.resize(k);
+    }
+    int peak() const { return (int)used_.size(); }
 private:
-    std::vector<int> free_;
-    int next_ = 0, live_ = 0, peak_ = 0;
+    void mark(int b, int n) { for (int s = b; s < b + n; ++s) used_[s] = 1; }
+    std::vector<char> used_;
+    std::vector<std::pair<int, int>> pending_;
+};
+
+// merge (row, slot) pairs into runs of consecutive rows landing in consecutive slots
+void make_descs(std::vector<std::pair<int, int>> &rows_slots, std::vector<IoDesc> &out) {
+    std::sort(rows_slots.begin(), rows_slots.end());
+    for (size_t i = 0; i < rows_slots.size();) {
+        size_t j = i + 1;
+        while (j < rows_slots.size() && rows_slots[j].first == rows_slots[j - 1].first + 1 &&
+               rows_slots[j].second == rows_slots[j - 1].second + 1)
+            ++j;
+        out.push_back({(uint32_t)rows_slots[i].first, (uint32_t)(j - i), (uint32_t)rows_slots[i].second, 0});
+        i = j;
+    }
+}
+
+struct Supernode {
+    int c0, c1;                    // columns [c0, c1)
+    std::vector<int> below;        // rows below the diagonal block (pattern of the last column)
+    std::vector<double> linv;      // w x w row-major: inverse of the dense diagonal block (lower triangular)
+    std::vector<double> wmat;      // h x w row-major: L[below, J] * inv(L[J, J])
+    int parent = -1;
 };
 
 }  // namespace
 
-void build_solve_program(HostPlan &p, int piece_cap) {
+// Supernodes: maximal runs of columns j, j+1, ... where j+1 is j's parent and only child and the
+// pattern of j+1 is the pattern of j minus row j+1 (so the diagonal block and the block below are
+// dense), cut at `cap` columns.  Inverting the small diagonal blocks on the host (fp64) turns the
+// in-supernode chain of dependent rows into independent dot products:
+//      y_J = inv(L_JJ) t_J,     t_I -= (L_IJ inv(L_JJ)) t_J          (forward)
+//      x_J = inv(L_JJ)^T y_J - (L_IJ inv(L_JJ))^T x_I                (backward)
+// so a sweep needs one barrier per LEVEL OF THE SUPERNODAL TREE instead of one per column.
+static std::vector<Supernode> find_supernodes(const HostPlan &p, int cap) {
+    const int n = p.n_free;
+    std::vector<int> nchild(n, 0);
+    for (int j = 0; j < n; ++j) if (p.parent[j] >= 0) nchild[p.parent[j]]++;
+    auto cnt = [&](int j) { return p.l_colptr[j + 1] - p.l_colptr[j]; };
+    // A pivot that is ~reg next to the matrix scale marks a direction the constraints do not fix (no
+    // constraints: one translation per connected component).  The fp64 reference resolves it
+    // through the 1e-10 regulariser into an arbitrary, noise-driven translation; float32 sweeps cannot
+    // (1/pivot ~ 1e5 amplifies rounding), so the displacement of that row is pinned to zero instead
+    // (its inverse pivot is taken as 0) -- the result differs from the reference by exactly that gauge.
+    double max_diag = 0.0;
+    for (int c = 0; c < n; ++c)
+        for (int q = p.m_colptr[c]; q < p.m_colptr[c + 1]; ++q)
+            if (p.m_rowidx[q] == c) max_diag = std::max(max_diag, p.m_val[q]);
+    const double tiny_pivot2 = 1e-9 * max_diag;
+    std::vector<Supernode> sn;
+    int start = 0;
+    for (int j = 1; j <= n; ++j) {
+        bool join = j < n && p.parent[j - 1] == j && nchild[j] == 1 && cnt(j) == cnt(j - 1) - 1 && (j - start) < cap;
+        if (join) continue;
+        Supernode s;
+        s.c0 = start; s.c1 = j;
+        const int last = j - 1, w = j - start;
+        for (int q = p.l_colptr[last] + 1; q < p.l_colptr[last + 1]; ++q) s.below.push_back(p.l_rowidx[q]);
+        const int h = (int)s.below.size();
+        // dense diagonal block T (lower) and block below B
+        std::vector<double> T((size_t)w * w, 0.0), B((size_t)h * w, 0.0);
+        for (int b = 0; b < w; ++b) {
+            int col = start + b;
+            for (int q = p.l_colptr[col]; q < p.l_colptr[col + 1]; ++q) {
+                int r = p.l_rowidx[q];
+                if (r < j) T[(size_t)(r - start) * w + b] = p.l_val[q];
+                else {
+                    int k = (int)(std::lower_bound(s.below.begin(), s.below.end(), r) - s.below.begin());
+                    B[(size_t)k * w + b] = p.l_val[q];
+                }
+            }
+        }
+        // inverse of T by forward substitution on the identity
+        s.linv.assign((size_t)w * w, 0.0);
+        for (int c = 0; c < w; ++c)
+            for (int r = c; r < w; ++r) {
+                double v = (r == c) ? 1.0 : 0.0;
+                for (int k = c; k < r; ++k) v -= T[(size_t)r * w + k] * s.linv[(size_t)k * w + c];
+                const double piv = T[(size_t)r * w + r];
+                s.linv[(size_t)r * w + c] = (piv * piv < tiny_pivot2) ? 0.0 : v / piv;
+            }
+        s.wmat.assign((size_t)h * w, 0.0);
+        for (int k = 0; k < h; ++k)
+            for (int c = 0; c < w; ++c) {
+                double v = 0.0;
+                for (int b = c; b < w; ++b) v += B[(size_t)k * w + b] * s.linv[(size_t)b * w + c];
+                s.wmat[(size_t)k * w + c] = v;
+            }
+        sn.push_back(std::move(s));
+        start = j;
+    }
+    std::vector<int> sn_of(n);
+    for (int i = 0; i < (int)sn.size(); ++i) for (int c = sn[i].c0; c < sn[i].c1; ++c) sn_of[c] = i;
+    for (auto &s : sn) { int pr = p.parent[s.c1 - 1]; s.parent = pr >= 0 ? sn_of[pr] : -1; }
+    return sn;
+}
+
+namespace {
+// Slots come from two pools so that long-lived rows cannot fragment the space the short-lived piece
+// blocks rotate through: "ext" slots (rows that outlive the phase that first touches them -- partial
+// sums of ancestors in the forward sweep, solved ancestors in the backward sweep) and "piece" slots
+// (released at the end of their phase).  Ids are symbolic until both sweeps are simulated and the size
+// of the ext pool is known: final slot = ext ? id : n_ext + id.
+constexpr int EXT_FLAG = 1 << 30;
+
+struct PhaseData {
+    std::vector<std::vector<Task>> levels;
+    std::vector<std::pair<int, int>> loads, stores;     // (row, symbolic slot)
+};
+}  // namespace
+
+void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
     const int n = p.n_free;
     SolveProgram &prog = p.prog;
     prog = SolveProgram();
-    Emitter em(prog);
-
-    // row-wise view of the strict lower triangle
-    std::vector<int> rptr(n + 1, 0);
-    for (int j = 0; j < n; ++j)
-        for (int q = p.l_colptr[j] + 1; q < p.l_colptr[j + 1]; ++q) rptr[p.l_rowidx[q] + 1]++;
-    for (int i = 0; i < n; ++i) rptr[i + 1] += rptr[i];
-    std::vector<int> rcol(rptr[n]);
-    std::vector<float> rval(rptr[n]);
-    {
-        std::vector<int> fill(rptr.begin(), rptr.end() - 1);
-        for (int j = 0; j < n; ++j)
-            for (int q = p.l_colptr[j] + 1; q < p.l_colptr[j + 1]; ++q) {
-                int i = p.l_rowidx[q];
-                rcol[fill[i]] = j;                      // ascending j because columns are visited in order
-                rval[fill[i]++] = (float)p.l_val[q];
-            }
+    std::vector<Supernode> sn = find_supernodes(p, supernode_cap);
+    const int ns = (int)sn.size();
+    prog.n_supernodes = ns;
+    // pieces: consecutive supernodes, about piece_cap rows each
+    std::vector<std::pair<int, int>> pieces;       // supernode ranges [s0, s1)
+    for (int s0 = 0; s0 < ns;) {
+        int s1 = s0, rows = 0;
+        while (s1 < ns && (rows == 0 || rows + (sn[s1].c1 - sn[s1].c0) <= piece_cap)) { rows += sn[s1].c1 - sn[s1].c0; ++s1; }
+        pieces.push_back({s0, s1});
+        s0 = s1;
     }
-    std::vector<float> dinv(n);
-    for (int j = 0; j < n; ++j) dinv[j] = (float)(1.0 / p.l_val[p.l_colptr[j]]);
+    const int np = (int)pieces.size();
+    std::vector<int> piece_of_row(n);
+    for (int pi = 0; pi < np; ++pi)
+        for (int s = pieces[pi].first; s < pieces[pi].second; ++s)
+            for (int c = sn[s].c0; c < sn[s].c1; ++c) piece_of_row[c] = pi;
+    std::vector<int> lvl(ns, 0);
+    std::vector<PhaseData> phases;
+    int n_ext = 0, n_piece = 0;
 
-    std::vector<std::pair<int, int>> pieces;
-    for (int a = 0; a < n; a += piece_cap) pieces.push_back({a, std::min(n, a + piece_cap)});
-    prog.n_pieces = (int)pieces.size();
-
-    std::vector<int> slot_of(n, -1), lvl(n, 0);
     // ---------------------------------------------------------------- forward sweep
     {
-        SlotPool pool;
-        for (auto [a, b] : pieces) {
-            std::vector<uint32_t> table;
-            for (int i = a; i < b; ++i) {
-                uint32_t add = 0;
-                if (slot_of[i] < 0) slot_of[i] = pool.alloc();
-                else add = LOAD_ADD_BIT;                 // holds partial sums pushed by earlier pieces
-                table.push_back((uint32_t)(slot_of[i] * SLOT_WORDS) | add);
+        SlotPool pool_p, pool_e;
+        std::vector<int> tslot(n, -1), yslot(n, -1);
+        auto prepare = [&](int q) {
+            const int s0 = pieces[q].first, s1 = pieces[q].second;
+            const int a = sn[s0].c0, b = sn[s1 - 1].c1;
+            PhaseData ph;
+            // t-slots: rows of the piece that no earlier piece has touched yet, as one contiguous block
+            std::vector<int> fresh;
+            for (int i = a; i < b; ++i) if (tslot[i] < 0) fresh.push_back(i);
+            if (!fresh.empty()) {
+                int base = pool_p.alloc_range((int)fresh.size());
+                for (size_t k = 0; k < fresh.size(); ++k) { tslot[fresh[k]] = base + (int)k; ph.loads.push_back({fresh[k], base + (int)k}); }
             }
-            em.rowspan(OP_LOAD, a, table, OPF_SYNC_AFTER);
-            std::vector<std::vector<Task>> levels;
-            auto put = [&](int level, Task &&t) {
-                if ((int)levels.size() <= level) levels.resize(level + 1);
-                levels[level].push_back(std::move(t));
-            };
-            for (int i = a; i < b; ++i) {
-                Task t{slot_of[i], TASK_FINAL, dinv[i], {}};
-                int l = 0;
-                for (int q = rptr[i]; q < rptr[i + 1]; ++q) {
-                    int j = rcol[q];
-                    if (j < a) continue;                 // already pushed into the slot by j's piece
-                    l = std::max(l, lvl[j] + 1);
-                    t.entries.push_back({rval[q], (uint32_t)(slot_of[j] * SLOT_BYTES)});
+            int ybase = pool_p.alloc_range(b - a);
+            for (int i = a; i < b; ++i) { yslot[i] = ybase + (i - a); ph.stores.push_back({i, yslot[i]}); }
+            // rows above the piece that receive a contribution for the first time: bring in their rhs
+            for (int s = s0; s < s1; ++s)
+                for (int i : sn[s].below)
+                    if (i >= b && tslot[i] < 0) { tslot[i] = EXT_FLAG | pool_e.alloc(); ph.loads.push_back({i, tslot[i]}); }
+            // tasks, by level of the supernodal tree inside the piece
+            std::vector<std::map<int, Task>> ext_levels;
+            for (int s = s0; s < s1; ++s) lvl[s] = 0;
+            for (int s = s0; s < s1; ++s) {
+                const Supernode &S = sn[s];
+                const int l = lvl[s], w = S.c1 - S.c0;
+                if (S.parent >= 0 && S.parent < s1) lvl[S.parent] = std::max(lvl[S.parent], l + 1);
+                if ((int)ph.levels.size() <= l) { ph.levels.resize(l + 1); ext_levels.resize(l + 1); }
+                for (int r = 0; r < w; ++r) {              // y_i = sum_b linv[r][b] t_b  (target overwritten)
+                    Task t{yslot[S.c0 + r], TASK_OVERWRITE, {}};
+                    for (int c = 0; c <= r; ++c)
+                        t.entries.push_back({(float)(-S.linv[(size_t)r * w + c]), (uint32_t)tslot[S.c0 + c]});
+                    ph.levels[l].push_back(std::move(t));
                 }
-                lvl[i] = l;
-                put(l, std::move(t));
+                for (size_t k = 0; k < S.below.size(); ++k) {   // t_i -= sum_b W[k][b] t_b
+                    int i = S.below[k];
+                    auto it = ext_levels[l].find(i);
+                    if (it == ext_levels[l].end()) it = ext_levels[l].emplace(i, Task{tslot[i], 0, {}}).first;
+                    for (int c = 0; c < w; ++c)
+                        it->second.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)tslot[S.c0 + c]});
+                }
             }
-            // contributions of this piece to rows above it
-            std::map<int, Task> ext;
-            std::map<int, int> ext_lvl;
-            for (int j = a; j < b; ++j)
-                for (int q = p.l_colptr[j] + 1; q < p.l_colptr[j + 1]; ++q) {
-                    int i = p.l_rowidx[q];
-                    if (i < b) continue;
-                    auto it = ext.find(i);
-                    if (it == ext.end()) {
-                        uint32_t fl = 0;
-                        if (slot_of[i] < 0) { slot_of[i] = pool.alloc(); fl = TASK_OVERWRITE; }
-                        it = ext.emplace(i, Task{slot_of[i], fl, 1.f, {}}).first;
-                        ext_lvl[i] = 0;
-                    }
-                    it->second.entries.push_back({(float)p.l_val[q], (uint32_t)(slot_of[j] * SLOT_BYTES)});
-                    ext_lvl[i] = std::max(ext_lvl[i], lvl[j] + 1);
-                }
-            for (auto &kv : ext) put(ext_lvl[kv.first], std::move(kv.second));
-            for (auto &lv : levels) { em.rows(lv, true); prog.n_steps_fwd++; }
-            for (auto &w : table) w &= ~LOAD_ADD_BIT;
-            em.rowspan(OP_STORE_Y, a, table, OPF_SYNC_AFTER);
-            for (int i = a; i < b; ++i) { pool.release(slot_of[i]); slot_of[i] = -1; }
-            pool.sort_free();
+            for (size_t l = 0; l < ph.levels.size(); ++l)
+                for (auto &kv : ext_levels[l]) ph.levels[l].push_back(std::move(kv.second));
+            prog.n_steps_fwd += (int)ph.levels.size();
+            phases.push_back(std::move(ph));
+        };
+        auto retire = [&](int q) {
+            const int a = sn[pieces[q].first].c0, b = sn[pieces[q].second - 1].c1;
+            for (int i = a; i < b; ++i) {
+                if (tslot[i] & EXT_FLAG) pool_e.release_at_end_of(q, tslot[i] & ~EXT_FLAG);
+                else pool_p.release_at_end_of(q, tslot[i]);
+                pool_p.release_at_end_of(q, yslot[i]);
+            }
+        };
+        prepare(0);
+        if (np > 1) prepare(1);
+        for (int q = 0; q < np; ++q) {
+            retire(q);
+            if (q + 2 < np) { pool_p.reclaim(q); pool_e.reclaim(q); prepare(q + 2); }
         }
-        prog.n_slots = std::max(prog.n_slots, pool.peak());
+        prog.n_phases_fwd = np;
+        n_ext = std::max(n_ext, pool_e.peak());
+        n_piece = std::max(n_piece, pool_p.peak());
     }
     // ---------------------------------------------------------------- backward sweep
     {
-        SlotPool pool;
-        std::fill(slot_of.begin(), slot_of.end(), -1);
-        // row i must stay resident until the piece holding the smallest column of its row pattern is done
-        std::vector<int> piece_of(n);
-        for (int pi = 0; pi < (int)pieces.size(); ++pi)
-            for (int i = pieces[pi].first; i < pieces[pi].second; ++i) piece_of[i] = pi;
-        std::vector<std::vector<int>> release_after(pieces.size());
-        for (int i = 0; i < n; ++i) {
-            int last = (rptr[i + 1] > rptr[i]) ? piece_of[rcol[rptr[i]]] : piece_of[i];
-            release_after[last].push_back(i);
-        }
-        for (int pi = (int)pieces.size() - 1; pi >= 0; --pi) {
-            auto [a, b] = pieces[pi];
-            std::vector<uint32_t> table;
+        SlotPool pool_p, pool_e;
+        std::vector<int> yslot(n, -1), xslot(n, -1);
+        // x of row i stays resident until the piece holding the first column that has i below it is done
+        std::vector<int> last_use(n);
+        for (int i = 0; i < n; ++i) last_use[i] = piece_of_row[i];
+        for (int s = 0; s < ns; ++s)
+            for (int i : sn[s].below) last_use[i] = std::min(last_use[i], piece_of_row[sn[s].c0]);
+        std::vector<std::vector<int>> release_after(np);
+        for (int i = 0; i < n; ++i) release_after[last_use[i]].push_back(i);
+        auto prepare = [&](int q) {                 // phase q of the sweep handles piece np-1-q
+            const int pi = np - 1 - q;
+            const int s0 = pieces[pi].first, s1 = pieces[pi].second;
+            const int a = sn[s0].c0, b = sn[s1 - 1].c1;
+            PhaseData ph;
+            int ybase = pool_p.alloc_range(b - a);
+            std::vector<int> shortlived;
             for (int i = a; i < b; ++i) {
-                slot_of[i] = pool.alloc();
-                table.push_back((uint32_t)(slot_of[i] * SLOT_WORDS));
+                yslot[i] = ybase + (i - a);
+                ph.loads.push_back({i, yslot[i]});
+                if (last_use[i] == pi) shortlived.push_back(i);
+                else xslot[i] = EXT_FLAG | pool_e.alloc();
             }
-            em.rowspan(OP_LOAD, a, table, OPF_SYNC_AFTER);
-            std::vector<std::vector<Task>> levels;
-            for (int j = b - 1; j >= a; --j) {
-                Task t{slot_of[j], TASK_FINAL, dinv[j], {}};
-                int l = 0;
-                for (int q = p.l_colptr[j] + 1; q < p.l_colptr[j + 1]; ++q) {
-                    int i = p.l_rowidx[q];
-                    assert(slot_of[i] >= 0);
-                    if (i < b) l = std::max(l, lvl[i] + 1);
-                    t.entries.push_back({(float)p.l_val[q], (uint32_t)(slot_of[i] * SLOT_BYTES)});
+            if (!shortlived.empty()) {
+                int xbase = pool_p.alloc_range((int)shortlived.size());
+                for (size_t k = 0; k < shortlived.size(); ++k) xslot[shortlived[k]] = xbase + (int)k;
+            }
+            for (int i = a; i < b; ++i) ph.stores.push_back({i, xslot[i]});
+            for (int s = s1 - 1; s >= s0; --s) {
+                const Supernode &S = sn[s];
+                const int w = S.c1 - S.c0;
+                const int l = (S.parent >= 0 && S.parent < s1) ? lvl[S.parent] + 1 : 0;
+                lvl[s] = l;
+                if ((int)ph.levels.size() <= l) ph.levels.resize(l + 1);
+                for (int c = 0; c < w; ++c) {              // x_j = sum_r linv[r][c] y_r - sum_k W[k][c] x_below[k]
+                    Task t{xslot[S.c0 + c], TASK_OVERWRITE, {}};
+                    for (int r = c; r < w; ++r)
+                        t.entries.push_back({(float)(-S.linv[(size_t)r * w + c]), (uint32_t)yslot[S.c0 + r]});
+                    for (size_t k = 0; k < S.below.size(); ++k) {
+                        assert(xslot[S.below[k]] >= 0);
+                        t.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)xslot[S.below[k]]});
+                    }
+                    ph.levels[l].push_back(std::move(t));
                 }
-                lvl[j] = l;
-                if ((int)levels.size() <= l) levels.resize(l + 1);
-                levels[l].push_back(std::move(t));
             }
-            for (auto &lv : levels) { em.rows(lv, true); prog.n_steps_bwd++; }
-            em.rowspan(OP_STORE_X, a, table, OPF_SYNC_AFTER);
-            for (int i : release_after[pi]) { pool.release(slot_of[i]); slot_of[i] = -1; }
-            pool.sort_free();
+            prog.n_steps_bwd += (int)ph.levels.size();
+            phases.push_back(std::move(ph));
+        };
+        auto retire = [&](int q) {
+            const int pi = np - 1 - q;
+            const int a = sn[pieces[pi].first].c0, b = sn[pieces[pi].second - 1].c1;
+            for (int i = a; i < b; ++i) pool_p.release_at_end_of(q, yslot[i]);
+            for (int i : release_after[pi]) {
+                if (xslot[i] & EXT_FLAG) pool_e.release_at_end_of(q, xslot[i] & ~EXT_FLAG);
+                else pool_p.release_at_end_of(q, xslot[i]);
+            }
+        };
+        prepare(0);
+        if (np > 1) prepare(1);
+        for (int q = 0; q < np; ++q) {
+            retire(q);
+            if (q + 2 < np) { pool_p.reclaim(q); pool_e.reclaim(q); prepare(q + 2); }
         }
-        prog.n_slots = std::max(prog.n_slots, pool.peak());
+        prog.n_phases_bwd = np;
+        n_ext = std::max(n_ext, pool_e.peak());
+        n_piece = std::max(n_piece, pool_p.peak());
+    }
+    // ---------------------------------------------------------------- resolve slots and emit
+    prog.n_slots = n_ext + n_piece;
+    auto resolve = [&](int sym) { return (sym & EXT_FLAG) ? (sym & ~EXT_FLAG) : n_ext + sym; };
+    Emitter em(prog);
+    for (auto &ph : phases) {
+        for (auto &rs : ph.loads) rs.second = resolve(rs.second);
+        for (auto &rs : ph.stores) rs.second = resolve(rs.second);
+        IoPhase io;
+        io.load_begin = (uint32_t)prog.io_desc.size();
+        make_descs(ph.loads, prog.io_desc);
+        io.load_end = io.store_begin = (uint32_t)prog.io_desc.size();
+        make_descs(ph.stores, prog.io_desc);
+        io.store_end = (uint32_t)prog.io_desc.size();
+        prog.io_phase.push_back(io);
+        em.marker(OP_PHASE_BEGIN);
+        for (auto &lv : ph.levels) {
+            for (auto &t : lv) {
+                t.target_slot = resolve(t.target_slot);
+                for (auto &e : t.entries) e.src_byte_off = (uint32_t)resolve((int)e.src_byte_off) * SLOT_BYTES;
+            }
+            em.rows(lv, true);
+        }
+        em.marker(OP_PHASE_END);
     }
     em.finish();
 }

@@ -183,7 +183,8 @@ class Reconstructor:
             check(lib.sdfa_reconstruct_dev(self._h, ptr(x.data_ptr()), x.stride(0), n, ptr(out.data_ptr()), ptr(s)))
             return out
         x = _f32c(deform_grads, "deform_grads")
-        x = x.reshape(x.shape[0], -1) if x.ndim > 1 else x.reshape(1, -1)
+        x = x.reshape(x.shape[0], self.n_src_tris * 9) if (x.ndim > 1 and x.size == 0) else (
+            x.reshape(x.shape[0], -1) if x.ndim > 1 else x.reshape(1, -1))
         if x.shape[1] != self.n_src_tris * 9:
             raise SdfaError(_native.ERR_ARG, f"expected {self.n_src_tris * 9} values per frame, got {x.shape[1]}")
         res = np.empty((x.shape[0], self.n_verts, 3), dtype=np.float32) if out is None else out
@@ -233,7 +234,7 @@ class Reconstructor:
     def last_timing(self):
         ms = (ctypes.c_float * 4)()
         check(lib.sdfa_last_timing(self._h, ms))
-        return dict(decode_ms=ms[0], assembly_ms=ms[1], solve_ms=ms[2], fill_ms=ms[3])
+        return dict(decode_ms=ms[0], assembly_ms=ms[1], solve_ms=ms[2], output_ms=ms[3])
 
 
 # =================================================================================================

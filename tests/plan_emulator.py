@@ -7,11 +7,10 @@ op encoding) without a GPU.  It is NOT a fallback: nothing under ``sdfa-2019_b20
 """
 import numpy as np
 
-F, CS = 32, 33                      # FRAMES_PER_TILE, COORD_STRIDE (csrc/plan.hpp)
+F, CS = 32, 32                      # FRAMES_PER_TILE, COORD_STRIDE (csrc/plan.hpp)
 SLOT_WORDS = 3 * CS
-OP_ROWS, OP_LOAD, OP_STORE_Y, OP_STORE_X = 1, 2, 3, 4
-LOAD_ADD = 0x80000000
-TASK_FINAL, TASK_OVERWRITE = 1 << 24, 1 << 25
+OP_ROWS, OP_PHASE_BEGIN, OP_PHASE_END = 1, 2, 3
+TASK_OVERWRITE = 1 << 25
 f32 = np.float32
 
 
@@ -97,11 +96,59 @@ class _Hazards:
             self.w[s] = me
 
 
-def solve(rec, rhs, cnst_pos=None):
-    """K3 + K4: rhs [N, n_free, 3] f32 -> verts [N, n_verts, 3] f32.  Also returns bookkeeping stats."""
+def _parse_phases(rec):
+    """Splits the stage stream into phases: list of levels, each a list of (target_slot, overwrite, coeff[], src_slot[])."""
     prog, stage_off = rec.debug("prog"), rec.debug("stage_off")
+    phases, cur, level = [], None, []
+    for s in range(len(stage_off) - 1):
+        st = prog[stage_off[s]:stage_off[s + 1]]
+        n_ops, nbytes = st[:8].view(np.uint32)
+        assert nbytes == len(st) and nbytes <= 8192 and nbytes % 16 == 0
+        at = 16
+        for _ in range(n_ops):
+            typ, flags = st[at:at + 4].view(np.uint16)
+            a, b, c = st[at + 4:at + 16].view(np.uint32)
+            if typ == OP_PHASE_BEGIN:
+                assert cur is None
+                cur, level = [], []
+                at += 16
+            elif typ == OP_PHASE_END:
+                assert cur is not None and not level, "phase must end on a level barrier"
+                phases.append(cur)
+                cur = None
+                at += 16
+            else:
+                assert typ == OP_ROWS and cur is not None
+                table = st[b:b + 4 * a].view(np.uint32)
+                for off in table:
+                    tgt, nf = st[off:off + 8].view(np.uint32)
+                    n = int(nf & 0xFFFFFF)
+                    assert n % 2 == 0 and off % 16 == 0 and tgt % (4 * SLOT_WORDS) == 0
+                    ent = st[off + 16: off + 16 + 8 * n]
+                    src = ent.view(np.uint32)[1::2]
+                    assert (src % (4 * SLOT_WORDS) == 0).all()
+                    level.append((int(tgt) // 4 // SLOT_WORDS, bool(nf & TASK_OVERWRITE), ent.view(f32)[0::2].copy(),
+                                  (src // 4 // SLOT_WORDS).astype(np.int64)))
+                if flags & 2:
+                    cur.append(level)
+                    level = []
+                at = int(c)
+        assert at <= nbytes
+    assert cur is None
+    return phases
+
+
+def solve(rec, rhs, cnst_pos=None):
+    """K3 + K5: rhs [N, n_free, 3] f32 (permuted rows) -> verts [N, n_verts, 3] f32, following the kernel's
+    real-time order of TMA loads, levels and stores (loads of phase q+2 are issued right after the stores of
+    phase q), with NaN-poisoned shared memory and a slot-level race check inside every level."""
     stats = rec.debug("stats")
     n_slots = int(stats[0])
+    io_desc = rec.debug("io_desc").reshape(-1, 4)
+    io_phase = rec.debug("io_phase").reshape(-1, 4)
+    phases = _parse_phases(rec)
+    nf_, nb_ = int(stats[1]), len(io_phase) - int(stats[1])
+    assert len(phases) == len(io_phase)
     perm, free_to_vi = rec.debug("perm"), rec.debug("free_to_vi")
     row_vert = free_to_vi[perm]
     xb = rec.debug("x_base").reshape(-1, 3)
@@ -109,82 +156,56 @@ def solve(rec, rhs, cnst_pos=None):
     xb_lo = (xb - xb_hi.astype(np.float64)).astype(f32)
     N = rhs.shape[0]
     out = np.full((N, rec.n_verts, 3), np.nan, dtype=f32)
-    scratch = np.array(rhs, dtype=f32, copy=True)
-    max_slot_used = 0
-    n_sync = 0
+    max_slot = 0
     for t0 in range(0, N, F):
         nv = min(F, N - t0)
-        state = np.zeros(n_slots * SLOT_WORDS, dtype=f32)
-        hz = _Hazards()
-        lanes = np.arange(nv)
-        for s in range(len(stage_off) - 1):
-            st = prog[stage_off[s]:stage_off[s + 1]]
-            n_ops, nbytes = st[:8].view(np.uint32)
-            assert nbytes == len(st) and nbytes <= 8192 and nbytes % 16 == 0
-            at = 16
-            for _ in range(n_ops):
-                hdr = st[at:at + 16]
-                typ, flags = hdr[:4].view(np.uint16)
-                a, b, c = hdr[4:16].view(np.uint32)
-                n_sync += bool(flags & 1) + bool(flags & 2)
-                if flags & 1:
-                    hz.sync()
-                if typ == OP_ROWS:
-                    table = st[b:b + 4 * a].view(np.uint32)
-                    written = set()
-                    for off in table:
-                        tgt, nf, dinv_bits, _ = st[off:off + 16].view(np.uint32)
-                        n = int(nf & 0xFFFFFF)
-                        assert n % 2 == 0 and off % 16 == 0
-                        ent = st[off + 16: off + 16 + 8 * n]
-                        coeff = ent.view(f32)[0::2]
-                        src = ent.view(np.uint32)[1::2]
-                        assert tgt % 4 == 0 and tgt // 4 % SLOT_WORDS == 0
-                        assert tgt not in written, "two tasks of one step write the same row"
-                        written.add(int(tgt))
-                        reads = set(int(x) // 4 // SLOT_WORDS for x, cf in zip(src, coeff) if cf != 0)
-                        hz.access(reads, {int(tgt) // 4 // SLOT_WORDS})
-                        max_slot_used = max(max_slot_used, tgt // 4 // SLOT_WORDS, *(src // 4 // SLOT_WORDS)) if n else max_slot_used
-                        dinv = np.array([dinv_bits], dtype=np.uint32).view(f32)[0]
-                        acc = np.zeros((3, nv), dtype=f32)
-                        for k in range(n):
-                            base = src[k] // 4
-                            for cdim in range(3):
-                                acc[cdim] += coeff[k] * state[base + cdim * CS + lanes]
-                        for cdim in range(3):
-                            w = tgt // 4 + cdim * CS + lanes
-                            v = np.zeros(nv, dtype=f32) if (nf & TASK_OVERWRITE) else state[w]
-                            state[w] = (v - acc[cdim]) * dinv
-                    at = int(c)
-                else:
-                    table = st[c:c + 4 * b].view(np.uint32)
-                    rows = np.arange(a, a + b)
-                    for r, w in zip(rows, table):
-                        base = int(w & 0xFFFFFF)
-                        max_slot_used = max(max_slot_used, base // SLOT_WORDS)
-                        for cdim in range(3):
-                            idx = base + cdim * CS + lanes
-                            if typ == OP_LOAD:
-                                v = scratch[t0:t0 + nv, r, cdim]
-                                state[idx] = (state[idx] + v) if (w & LOAD_ADD) else v
-                            elif typ == OP_STORE_Y:
-                                scratch[t0:t0 + nv, r, cdim] = state[idx]
-                            elif typ == OP_STORE_X:
-                                out[t0:t0 + nv, row_vert[r], cdim] = xb_hi[r, cdim] + (xb_lo[r, cdim] + state[idx])
-                            else:
-                                raise AssertionError(f"bad op {typ}")
-                    slots = set(int(w & 0xFFFFFF) // SLOT_WORDS for w in table)
-                    # every warp touches every row of a span op (frames are dealt to warps), so the op
-                    # conflicts with any other unsynchronised access to those slots
-                    if typ == OP_LOAD:
-                        hz.access(set(), slots)
-                    else:
-                        hz.access(slots, set())
-                    at = int(c) + (int(b) * 4 + 15) // 16 * 16
-                if flags & 2:
-                    hz.sync()
-            assert at <= nbytes
+        scratch = np.zeros((rec.n_free, 3, F), dtype=f32)         # tile-major rows; K2 zero-fills idle lanes
+        scratch[:, :, :nv] = np.transpose(rhs[t0:t0 + nv], (1, 2, 0))
+        state = np.full((n_slots, 3, F), np.nan, dtype=f32)
+        busy = np.zeros(n_slots, dtype=bool)                       # slots some live phase may still touch
+
+        def loads(q):
+            for row, n, slot, _ in io_desc[io_phase[q][0]:io_phase[q][1]]:
+                state[slot:slot + n] = scratch[row:row + n]
+
+        def stores(q):
+            for row, n, slot, _ in io_desc[io_phase[q][2]:io_phase[q][3]]:
+                assert not np.isnan(state[slot:slot + n]).any()
+                scratch[row:row + n] = state[slot:slot + n]
+
+        def compute(q):
+            nonlocal max_slot
+            for level in phases[q]:
+                hz = _Hazards()
+                results = []
+                for tgt, overwrite, coeff, src in level:
+                    hz.access(set(int(x) for x, cf in zip(src, coeff) if cf != 0), {tgt})
+                    max_slot = max(max_slot, tgt, int(src.max()) if len(src) else 0)
+                    acc = np.zeros((3, F), dtype=f32)
+                    for k in range(len(coeff)):
+                        acc += coeff[k] * state[src[k]]
+                    base = np.zeros((3, F), dtype=f32) if overwrite else state[tgt]
+                    results.append((tgt, base - acc))
+                for tgt, v in results:                              # all reads of a level precede its writes
+                    state[tgt] = v
+
+        q0 = 0
+        for nq in (nf_, nb_):
+            loads(q0)
+            if nq > 1:
+                loads(q0 + 1)
+            for q in range(nq):
+                compute(q0 + q)
+                stores(q0 + q)
+                if q + 2 < nq:
+                    loads(q0 + q + 2)
+            q0 += nq
+        x = scratch[:, :, :nv]                                      # [row][c][frame]
+        assert not np.isnan(x).any()
+        val = xb_hi[:, :, None] + (xb_lo[:, :, None] + x)
+        out[t0:t0 + nv, row_vert] = np.transpose(val, (2, 0, 1))
     if rec.n_cnsts:
         C = rec._verts[rec._cnsts] if cnst_pos is None else np.asarray(cnst_pos, dtype=f32).reshape(-1, 3)
         out[:, rec._cnsts] = C[None]
-    return out, dict(max_slot_used=int(max_slot_used), n_slots=n_slots, syncs_per_tile=n_sync // max(1, (N + F - 1) // F))
+    return out, dict(max_slot_used=int(max_slot), n_slots=n_slots,
+                     levels_per_tile=sum(len(p) for p in phases))

@@ -151,11 +151,13 @@ def test_small_mesh_modes_vs_golden(golden_small):
     src = W.iid_dgrad(1, 11, sigma=0.05, seed=9)[0]
     out = rc.get_mesh(src.astype(np.float64), vert_cnsts=V[border], corr_count=cc, corr_faces=cf)
     assert np.abs(out - golden_small["corr_verts"]).max() <= tol
-    # unconstrained: defined modulo a translation
+    # unconstrained: defined modulo a translation; the reference's own translation is
+    # fp64 rounding noise amplified by 1/reg, ours pins one vertex, so compare centred
     ru = D.Reconstructor(V, F, device=0)
     out = ru.get_mesh(dg[2].astype(np.float64))
     ref = golden_small["uncnst_verts"]
-    assert np.abs((out - out.mean(0)) - (ref - ref.mean(0))).max() <= 5e-6
+    assert np.abs((out - out.mean(0)) - (ref - ref.mean(0))).max() <= 2e-6
+    assert np.abs(out).max() < 1.0            # and it stays near the template instead of drifting off
 
 
 def test_decode_and_reconstruct_config2(rec, chk, flame):
