@@ -142,7 +142,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         if ((rc = order_and_factor(p, err)) != 0) { delete h; return fail(SDFA_ERR_FACTOR, "sdfa_create: " + err); }
         compute_base_solution(p, nullptr);
         build_solve_program(p, /*piece_cap=*/64, /*supernode_cap=*/32);
-        build_assembly_plan(p, /*rows_per_block=*/128);
+        build_assembly_plan(p, /*rows_per_block=*/128, ASM_MAX_EQ);
     } catch (const std::exception &e) {
         delete h;
         return fail(SDFA_ERR_UNSUPPORTED, std::string("sdfa_create: ") + e.what());

@@ -75,26 +75,49 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     const int tile = blockIdx.y;
     const int frame0 = tile * FRAMES_PER_TILE;
     const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
+    // frame-invariant per-equation data stays in registers: thread t owns equations t, t+128, ...
+    constexpr int KMAX = ASM_MAX_EQ / ASM_THREADS;
+    int src_k[KMAX];
+    float u_k[KMAX][6];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int e = threadIdx.x + k * ASM_THREADS;
+        src_k[k] = -1;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) u_k[k][j] = 0.f;
+        if (e < n_eq) {
+            src_k[k] = P.eq_src[P.eq_id[blk.x + e]];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) u_k[k][j] = __ldg(P.eq_u + (blk.x + e) * 6 + j);
+        }
+    }
     for (int f = 0; f < nvalid; ++f) {
         const float *row = P.dgrad + (long long)(frame0 + f) * P.frame_stride;
-        for (int e = threadIdx.x; e < n_eq; e += ASM_THREADS) {
-            const int ge = blk.x + e;
-            const int src = P.eq_src[P.eq_id[ge]];
-            float u0[3], u1[3], g2[3], g3[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { u0[k] = __ldg(P.eq_u + ge * 6 + k); u1[k] = __ldg(P.eq_u + ge * 6 + 3 + k); }
+        for (int k = 0; k < KMAX; ++k) {
+            const int e = threadIdx.x + k * ASM_THREADS;
+            if (e >= n_eq) break;
+            const int src = src_k[k];
+            const float *u0 = &u_k[k][0], *u1 = &u_k[k][3];
+            float g2[3], g3[3];
             if (src >= 0) {
                 float d[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) d[k] = __ldg(row + (long long)src * 9 + k);
+                for (int j = 0; j < 9; ++j) d[j] = __ldg(row + (long long)src * 9 + j);
                 if (P.mode == ASM_DGRAD) {
-                    float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
-                    float th = sqrtf(th2);
+                    const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
                     float a = 0.f, b = 0.f;
-                    if (th >= 1e-6f) {          // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
-                        float sh2 = sinf(0.5f * th);
-                        a = sinf(th) / th;
-                        b = 2.f * sh2 * sh2 / th2;
+                    if (th2 >= 1e-12f) {        // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
+                        if (th2 <= 1.f) {
+                            // Taylor series in th^2 (remainder < 3e-8 for th <= 1): no sqrt, sin or division
+                            a = 1.f - th2 * (1.f / 6.f) * (1.f - th2 * (1.f / 20.f) * (1.f - th2 * (1.f / 42.f) * (1.f - th2 * (1.f / 72.f))));
+                            b = 0.5f - th2 * (1.f / 24.f) * (1.f - th2 * (1.f / 30.f) * (1.f - th2 * (1.f / 56.f) * (1.f - th2 * (1.f / 90.f))));
+                        } else {
+                            const float th = sqrtf(th2);
+                            const float sh2 = sinf(0.5f * th);
+                            a = sinf(th) / th;
+                            b = 2.f * sh2 * sh2 / th2;
+                        }
                     }
                     corner_vec(d, a, b, u0, g2);
                     corner_vec(d, a, b, u1, g3);

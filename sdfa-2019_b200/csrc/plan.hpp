@@ -126,6 +126,7 @@ void compute_base_solution(HostPlan &p, const float *cnst_pos);   // x_base
 void solve_factored(const HostPlan &p, std::vector<double> &rhs_perm /* [n_free*3] in/out */);
 // schedule.cpp
 void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap);
-void build_assembly_plan(HostPlan &p, int rows_per_block);
+void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block);
+constexpr int ASM_MAX_EQ = 512;   // equations per row block the assembly kernel keeps in registers/shared memory
 
 }  // namespace sdfa

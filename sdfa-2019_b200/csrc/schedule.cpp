@@ -313,14 +313,18 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
             for (int s = s0; s < s1; ++s)
                 for (int i : sn[s].below)
                     if (i >= b && tslot[i] < 0) { tslot[i] = EXT_FLAG | pool_e.alloc(); ph.loads.push_back({i, tslot[i]}); }
-            // tasks, by level of the supernodal tree inside the piece
-            std::vector<std::map<int, Task>> ext_levels;
+            // tasks, by level of the supernodal tree inside the piece.  The piece's pushes into a row above
+            // its supernodes are merged into ONE task per target row: it reads the t-values of every
+            // contributing supernode (they stay intact, y goes to separate slots) and runs in the level
+            // of the last contributor -- always before the level of the target's own supernode.
+            std::map<int, Task> ext;
+            std::map<int, int> ext_lvl;
             for (int s = s0; s < s1; ++s) lvl[s] = 0;
             for (int s = s0; s < s1; ++s) {
                 const Supernode &S = sn[s];
                 const int l = lvl[s], w = S.c1 - S.c0;
                 if (S.parent >= 0 && S.parent < s1) lvl[S.parent] = std::max(lvl[S.parent], l + 1);
-                if ((int)ph.levels.size() <= l) { ph.levels.resize(l + 1); ext_levels.resize(l + 1); }
+                if ((int)ph.levels.size() <= l) ph.levels.resize(l + 1);
                 for (int r = 0; r < w; ++r) {              // y_i = sum_b linv[r][b] t_b  (target overwritten)
                     Task t{yslot[S.c0 + r], TASK_OVERWRITE, {}};
                     for (int c = 0; c <= r; ++c)
@@ -329,14 +333,14 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
                 }
                 for (size_t k = 0; k < S.below.size(); ++k) {   // t_i -= sum_b W[k][b] t_b
                     int i = S.below[k];
-                    auto it = ext_levels[l].find(i);
-                    if (it == ext_levels[l].end()) it = ext_levels[l].emplace(i, Task{tslot[i], 0, {}}).first;
+                    auto it = ext.find(i);
+                    if (it == ext.end()) { it = ext.emplace(i, Task{tslot[i], 0, {}}).first; ext_lvl[i] = 0; }
                     for (int c = 0; c < w; ++c)
                         it->second.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)tslot[S.c0 + c]});
+                    ext_lvl[i] = std::max(ext_lvl[i], l);
                 }
             }
-            for (size_t l = 0; l < ph.levels.size(); ++l)
-                for (auto &kv : ext_levels[l]) ph.levels[l].push_back(std::move(kv.second));
+            for (auto &kv : ext) ph.levels[ext_lvl[kv.first]].push_back(std::move(kv.second));
             prog.n_steps_fwd += (int)ph.levels.size();
             phases.push_back(std::move(ph));
         };
@@ -454,44 +458,78 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
 }
 
 // ------------------------------------------------------------------------------------------
-void build_assembly_plan(HostPlan &p, int rows_per_block) {
+void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) {
     AssemblyPlan &ap = p.asmplan;
     ap = AssemblyPlan();
     const int n = p.n_free;
     // incidences per free column: (equation block, corner)
     std::vector<std::vector<std::pair<int, int>>> inc(n);
+    std::vector<std::vector<int>> rows_of_eq(p.n_eq);
     for (int k : p.active_eq) {
         const uint32_t *t = &p.tris[(size_t)p.eq_tri[k] * 3];
         for (int c = 0; c < 3; ++c) {
             int f = p.vi_to_free[t[c]];
-            if (f >= 0) inc[f].push_back({k, c});
+            if (f >= 0) { inc[f].push_back({k, c}); rows_of_eq[k].push_back(f); }
         }
     }
-    // group rows whose equations sit close together in the dgrad row: sort by smallest incident equation
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
     std::vector<int> key(n, 0x7fffffff);
     for (int f = 0; f < n; ++f)
         for (auto &kc : inc[f]) key[f] = std::min(key[f], kc.first);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
+    // Row blocks by greedy growth over the mesh: start at the unassigned row with the smallest equation
+    // index and keep adding the neighbouring row that brings the fewest new equations, so that few
+    // equations are evaluated by more than one block (FLAME: 1.17x instead of 1.67x for index-sorted rows).
+    std::vector<char> taken(n, 0), in_eqs(p.n_eq, 0);
+    std::vector<int> by_key(n);
+    std::iota(by_key.begin(), by_key.end(), 0);
+    std::stable_sort(by_key.begin(), by_key.end(), [&](int x, int y) { return key[x] < key[y]; });
+    size_t seed_pos = 0;
     ap.row_ptr.push_back(0);
-    for (int start = 0; start < n; start += rows_per_block) {
-        int stop = std::min(n, start + rows_per_block);
+    int n_taken = 0;
+    while (n_taken < n) {
+        while (taken[by_key[seed_pos]]) ++seed_pos;
+        std::vector<int> rows, eqs, cand;
+        std::vector<char> is_cand(n, 0);
+        auto add_row = [&](int f) {
+            taken[f] = 1; ++n_taken; rows.push_back(f);
+            for (auto &kc : inc[f]) {
+                if (!in_eqs[kc.first]) { in_eqs[kc.first] = 1; eqs.push_back(kc.first); }
+                for (int g : rows_of_eq[kc.first]) if (!taken[g] && !is_cand[g]) { is_cand[g] = 1; cand.push_back(g); }
+            }
+        };
+        add_row(by_key[seed_pos]);
+        while ((int)rows.size() < rows_per_block && n_taken < n) {
+            int best = -1, best_new = 1 << 30;
+            size_t w = 0;
+            for (size_t i = 0; i < cand.size(); ++i) {
+                int g = cand[i];
+                if (taken[g]) continue;
+                cand[w++] = g;
+                int fresh = 0;
+                for (auto &kc : inc[g]) fresh += !in_eqs[kc.first];
+                if (fresh < best_new || (fresh == best_new && key[g] < key[best])) { best = g; best_new = fresh; }
+            }
+            cand.resize(w);
+            if (best < 0) {                         // component exhausted: continue from the next seed
+                while (seed_pos < (size_t)n && taken[by_key[seed_pos]]) ++seed_pos;
+                if (seed_pos >= (size_t)n) break;
+                best = by_key[seed_pos];
+                best_new = 0;
+                for (auto &kc : inc[best]) best_new += !in_eqs[kc.first];
+            }
+            if ((int)eqs.size() + best_new > max_eq_per_block) break;
+            add_row(best);
+        }
+        for (int k : eqs) in_eqs[k] = 0;
+        std::sort(eqs.begin(), eqs.end());
         AssemblyBlock blk;
         blk.eq_begin = (int)ap.eq_id.size();
         blk.row_begin = (int)ap.row_perm.size();
-        std::vector<int> eqs;
-        for (int r = start; r < stop; ++r)
-            for (auto &kc : inc[order[r]]) eqs.push_back(kc.first);
-        std::sort(eqs.begin(), eqs.end());
-        eqs.erase(std::unique(eqs.begin(), eqs.end()), eqs.end());
         for (int k : eqs) {
             ap.eq_id.push_back(k);
             const double *u = &p.tri_u[(size_t)p.eq_tri[k] * 6];
             for (int d = 0; d < 6; ++d) ap.eq_u.push_back((float)u[d]);
         }
-        for (int r = start; r < stop; ++r) {
-            int f = order[r];
+        for (int f : rows) {
             ap.row_perm.push_back(p.iperm[f]);
             for (auto &kc : inc[f]) {
                 int local = (int)(std::lower_bound(eqs.begin(), eqs.end(), kc.first) - eqs.begin());

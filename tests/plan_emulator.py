@@ -32,12 +32,18 @@ def assemble(rec, dgrad, mode="dgrad"):
         if has.any():
             d = dg[:, src[has]]                               # [N, m, 9]
             if mode == "dgrad":
-                th2 = d[..., 6] ** 2 + d[..., 7] ** 2 + d[..., 8] ** 2
-                th = np.sqrt(th2)
-                ok = th >= f32(1e-6)
-                ths = np.where(ok, th, f32(1))
-                a = np.where(ok, np.sin(ths) / ths, f32(0)).astype(f32)
-                b = np.where(ok, f32(2) * np.sin(f32(0.5) * ths) ** 2 / np.where(ok, th2, f32(1)), f32(0)).astype(f32)
+                th2 = d[..., 6] * d[..., 6] + d[..., 7] * d[..., 7] + d[..., 8] * d[..., 8]
+                one = f32(1)
+                ts = np.minimum(th2, one)
+                a_s = one - ts * f32(1 / 6) * (one - ts * f32(1 / 20) * (one - ts * f32(1 / 42) * (one - ts * f32(1 / 72))))
+                b_s = f32(0.5) - ts * f32(1 / 24) * (one - ts * f32(1 / 30) * (one - ts * f32(1 / 56) * (one - ts * f32(1 / 90))))
+                thl = np.sqrt(np.maximum(th2, one))
+                a_l = np.sin(thl) / thl
+                b_l = f32(2) * np.sin(f32(0.5) * thl) ** 2 / np.maximum(th2, one)
+                a = np.where(th2 <= one, a_s, a_l)
+                b = np.where(th2 <= one, b_s, b_l)
+                a = np.where(th2 >= f32(1e-12), a, f32(0)).astype(f32)
+                b = np.where(th2 >= f32(1e-12), b, f32(0)).astype(f32)
 
                 def corner(u):
                     u = np.broadcast_to(u[None], d.shape[:2] + (3,))
