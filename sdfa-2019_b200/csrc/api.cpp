@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -41,6 +42,8 @@ struct sdfa_handle {
     float *io_in = nullptr; size_t io_in_cap = 0;      // staging for *_host entry points
     float *io_out = nullptr; size_t io_out_cap = 0;
     float *io_in2 = nullptr; size_t io_in2_cap = 0;
+    float *ximg_s = nullptr; size_t ximg_s_cap = 0;    // split coefficient tile images (tensor-core decode)
+    float *ximg_r = nullptr; size_t ximg_r_cap = 0;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
@@ -212,7 +215,7 @@ void sdfa_destroy(sdfa_handle *h) {
     if (h->dev.device >= 0) {
         cudaSetDevice(h->dev.device);
         for (void *p : h->allocs) cudaFree(p);
-        for (float *p : {h->rhs, h->dgrad_c, h->io_in, h->io_out, h->io_in2}) if (p) cudaFree(p);
+        for (float *p : {h->rhs, h->dgrad_c, h->io_in, h->io_out, h->io_in2, h->ximg_s, h->ximg_r}) if (p) cudaFree(p);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     }
     delete h;
@@ -413,6 +416,26 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     if ((rc = pack(compT_rotat, means_rotat, 3, k_rotat, &d.w_rotat, &d.m_rotat, false))) return rc;
     if ((rc = pack(compT_scale, means_scale, 6, k_scale, &d.wfull_scale, &d.mfull_scale, true))) return rc;
     if ((rc = pack(compT_rotat, means_rotat, 3, k_rotat, &d.wfull_rotat, &d.mfull_rotat, true))) return rc;
+    // tensor-core path: compact rows, split into TF32 hi/lo and laid out as shared-memory tile images
+    {
+        const std::vector<int32_t> &need = h->needed_tris;
+        auto build = [&](const float *W, const float *m, int per, int col0, int K, float **dw, float **db, int32_t **doff, int *mt) -> int {
+            std::vector<float> w(need.size() * per * K), mm(need.size() * per), img, bias;
+            std::vector<int32_t> off;
+            for (size_t t = 0; t < need.size(); ++t) {
+                std::memcpy(&w[t * per * K], &W[(size_t)need[t] * per * K], sizeof(float) * per * K);
+                std::memcpy(&mm[t * per], &m[(size_t)need[t] * per], sizeof(float) * per);
+            }
+            tc_build_basis(w.data(), mm.data(), (int)need.size(), per, col0, K, img, bias, off);
+            *mt = (int)(bias.size() / 128);
+            int r;
+            if ((r = upload_mut(h, img, dw))) return r;
+            if ((r = upload_mut(h, bias, db))) return r;
+            return upload_mut(h, off, doff);
+        };
+        if ((rc = build(compT_scale, means_scale, 6, 0, k_scale, &d.tc_w_scale, &d.tc_b_scale, &d.tc_o_scale, &d.tc_mt_scale))) return rc;
+        if ((rc = build(compT_rotat, means_rotat, 3, 6, k_rotat, &d.tc_w_rotat, &d.tc_b_rotat, &d.tc_o_rotat, &d.tc_mt_rotat))) return rc;
+    }
     h->has_pca = h->has_full_pca = true;
     return SDFA_OK;
 }
@@ -428,7 +451,13 @@ int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, co
     const long long stride = (long long)h->dev.n_needed * 9;
     if ((rc = grow(&h->dgrad_c, &h->dgrad_c_cap, (size_t)n_frames * stride))) return rc;
     if ((rc = time_mark(h, 0, s))) return rc;
-    CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, h->dgrad_c, s));
+    if (std::getenv("SDFA_DECODE_SIMT")) {           // debugging aid: the fp32 CUDA-core decode kernel
+        CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, h->dgrad_c, s));
+    } else {
+        if ((rc = grow(&h->ximg_s, &h->ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
+        if ((rc = grow(&h->ximg_r, &h->ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
+        CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, h->ximg_s, h->ximg_r, h->dgrad_c, s));
+    }
     return reconstruct_core(h, h->dgrad_c, stride, h->dev.eq_src_compact, ASM_DGRAD, n_frames, out_dev, s, true);
 }
 
@@ -460,6 +489,31 @@ int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const fl
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
     CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, true, dgrad_dev, (cudaStream_t)stream));
     return SDFA_OK;
+}
+
+int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
+                            float *dgrad_compact_dev, void *stream) {
+    int rc;
+    if ((rc = need_device(h))) return rc;
+    if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_compact_dev: call sdfa_set_pca first");
+    if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_compact_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
+    if (n_frames == 0) return SDFA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (std::getenv("SDFA_DECODE_SIMT")) {
+        CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, dgrad_compact_dev, s));
+        return SDFA_OK;
+    }
+    if ((rc = grow(&h->ximg_s, &h->ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
+    if ((rc = grow(&h->ximg_r, &h->ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
+    CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, h->ximg_s, h->ximg_r, dgrad_compact_dev, s));
+    return SDFA_OK;
+}
+
+int sdfa_needed_tris(const sdfa_handle *h, int32_t *tris, int cap) {
+    if (!h) return -1;
+    const int n = (int)h->needed_tris.size();
+    if (tris) std::memcpy(tris, h->needed_tris.data(), sizeof(int32_t) * (size_t)std::min(n, cap));
+    return n;
 }
 
 int sdfa_get_deform_grad_host(const float *, const float *, int, const uint32_t *, int, double, int, int, double *) {

@@ -1,0 +1,316 @@
+// decode_tc.cu -- K1: PCA coefficients -> dgrad of the needed source triangles, on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged in shared memory by TMA
+// bulk copies).  Replaces PcaInversion.forward x2 + the scale/rotation interleave of data_to_anime_feat
+// (reference speech_anime/modules/output_module.py:115-116, speech_anime/model/model.py:246-257), which
+// is a cuBLAS SGEMM + cat in the reference.
+//
+// GEMM shape (per basis: "scale" K=85 with 6 outputs per triangle, "rotation" K=180 with 3):
+//      D[m, n] = sum_k W[m, k] * X[n, k]       m = basis row (output value), n = frame
+// i.e. the basis rows are the MMA M dimension (TMEM lanes) and the frames the N dimension (TMEM columns),
+// so an epilogue warp holds 32 consecutive output values of one frame per register and its stores to
+// dgrad[frame][triangle*9 + c] are coalesced without a shared-memory transpose.
+//
+// fp32 accuracy from TF32 tensor cores: both operands are split x = hi + lo with hi = x truncated to
+// TF32 (the 19 bits the tensor core reads) and lo = x - hi (exact), and every K-step issues three MMAs
+//      W_hi X_hi + W_hi X_lo + W_lo X_hi                  ("3xTF32", error ~2^-21 per product)
+// into the same fp32 accumulator.  The basis is split and pre-tiled once on the host (sdfa_set_pca); the
+// coefficients are split per call by k_split_coeffs.  Tiles are stored in global memory as exact images
+// of the 128-byte-swizzled K-major shared-memory layout the UMMA descriptors expect, so one
+// cp.async.bulk per operand and K-block fills a stage (no tensor maps needed).
+#include "device_plan.hpp"
+
+#include <cstring>
+#include <vector>
+
+namespace sdfa {
+
+
+namespace {
+
+constexpr int TC_BM = 128;          // basis rows per tile (UMMA M)
+constexpr int TC_BN = 128;          // frames per tile (UMMA N)
+constexpr int TC_BK = 32;           // floats per K-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB: one operand half (hi or lo)
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // W_hi, W_lo, X_hi, X_lo
+constexpr int TC_THREADS = 192;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int TC_TMEM_COLS = 256;   // two 128-column fp32 accumulators
+
+// float index of element (row r, k) inside a [rows x 32] K-major SWIZZLE_128B tile image:
+// 8-row groups of 1024 bytes, 16-byte chunk index XORed with the row index inside the group
+__host__ __device__ inline int swz(int r, int k) {
+    return (r >> 3) * 256 + (r & 7) * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));
+}
+__host__ __device__ inline float tf32_hi(float x) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+#else
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u &= 0xFFFFE000u;
+    float h;
+    std::memcpy(&h, &u, 4);
+    return h;
+#endif
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// leading byte offset 1 (unused for swizzled K-major), stride byte offset 1024 >> 4 between 8-row groups,
+// version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M = 128, N = 128, K = 8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+struct GemmParams {
+    const float *w_img;      // [m_tiles][kb][hi,lo][128x32 swizzled]
+    const float *x_img;      // [n_tiles][kb][hi,lo][128x32 swizzled]
+    const float *bias;       // [m_tiles*128]
+    const int32_t *out_off;  // [m_tiles*128] offset inside a frame's dgrad row, -1 for padding rows
+    float *out;
+    long long out_stride;    // floats per frame
+    int n_frames, m_tiles, n_tiles, kb;
+};
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 128, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *stages = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {   // one warp allocates the tensor memory and later frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles_total = P.m_tiles * P.n_tiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+                const int m = tile % P.m_tiles, n = tile / P.m_tiles;
+                for (int kb = 0; kb < P.kb; ++kb, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, TC_STAGE_BYTES);
+                    const uint32_t dst = smem_u32(stages + s * TC_STAGE_BYTES);
+                    tma_bulk_g2s(dst, P.w_img + ((size_t)m * P.kb + kb) * (2 * TC_BM * TC_BK), 2 * TC_TILE_BYTES, bar_full + 8 * s);
+                    tma_bulk_g2s(dst + 2 * TC_TILE_BYTES, P.x_img + ((size_t)n * P.kb + kb) * (2 * TC_BN * TC_BK), 2 * TC_TILE_BYTES,
+                                 bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+                const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+                mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);         // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                for (int kb = 0; kb < P.kb; ++kb, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(stages + s * TC_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {          // UMMA K = 8 floats = 32 bytes
+                        const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_TILE_BYTES + k * 32);
+                        const uint64_t x_hi = umma_desc(base + 2 * TC_TILE_BYTES + k * 32);
+                        const uint64_t x_lo = umma_desc(base + 3 * TC_TILE_BYTES + k * 32);
+                        umma_tf32(d_tmem, w_hi, x_hi, TC_IDESC, (kb | k) != 0);
+                        umma_tf32(d_tmem, w_hi, x_lo, TC_IDESC, 1u);
+                        umma_tf32(d_tmem, w_lo, x_hi, TC_IDESC, 1u);
+                    }
+                    tc_commit(bar_empty + 8 * s);                  // stage reusable once these MMAs have read it
+                }
+                tc_commit(bar_tfull + 8 * acc);                    // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+        const int lane_grp = warp & 3;                              // TMEM lanes 32*lane_grp .. +31 belong to this warp
+        uint32_t tc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+            const int m = tile % P.m_tiles, n = tile / P.m_tiles;
+            const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+            const int row = m * TC_BM + lane_grp * 32 + lane;
+            const int off = P.out_off[row];
+            const float b = P.bias[row];
+            mbar_wait(bar_tfull + 8 * acc, aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BN;
+#pragma unroll 1
+            for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+                uint32_t v[32];
+                tmem_ld32(taddr + chunk * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int f0 = n * TC_BN + chunk * 32;
+                if (off >= 0) {
+                    float *dst = P.out + (long long)f0 * P.out_stride + off;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (f0 + c < P.n_frames) dst[(long long)c * P.out_stride] = __uint_as_float(v[c]) + b;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// coefficients [n_frames, K] -> hi/lo tile images [n_tiles][kb][hi,lo][128 x 32 swizzled] (zero padded)
+__global__ void k_split_coeffs(const float *__restrict__ x, int K, int n_frames, int kb_count, float *__restrict__ img) {
+    const long long total = (long long)gridDim.y * TC_BN * kb_count * TC_BK;     // per n-tile row block
+    (void)total;
+    const int n_tile = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_BN * kb_count * TC_BK; i += gridDim.x * blockDim.x) {
+        const int r = i / (kb_count * TC_BK), kk = i - r * (kb_count * TC_BK);
+        const int kb = kk / TC_BK, k = kk - kb * TC_BK;
+        const int frame = n_tile * TC_BN + r, kg = kb * TC_BK + k;
+        const float v = (frame < n_frames && kg < K) ? x[(long long)frame * K + kg] : 0.f;
+        const float hi = tf32_hi(v);
+        float *tile = img + ((size_t)n_tile * kb_count + kb) * (2 * TC_BN * TC_BK);
+        tile[swz(r, k)] = hi;
+        tile[TC_BN * TC_BK + swz(r, k)] = v - hi;
+    }
+}
+
+}  // namespace
+
+int tc_kblocks(int K) { return (K + TC_BK - 1) / TC_BK; }
+size_t tc_ximg_floats(int n_frames, int K) {
+    return (size_t)((n_frames + TC_BN - 1) / TC_BN) * tc_kblocks(K) * 2 * TC_BN * TC_BK;
+}
+
+// Host: pre-split, pre-tiled basis images + per-row bias and output offset.  `rows` = n_tri * per_tri basis
+// rows of a [rows, K] row-major basis; output row r = (tri, s) lands at tri*9 + col0 + s.
+void tc_build_basis(const float *W, const float *mean, int n_tri, int per_tri, int col0, int K,
+                    std::vector<float> &img, std::vector<float> &bias, std::vector<int32_t> &off) {
+    const int rows = n_tri * per_tri, m_tiles = (rows + TC_BM - 1) / TC_BM, kbs = tc_kblocks(K);
+    img.assign((size_t)m_tiles * kbs * 2 * TC_BM * TC_BK, 0.f);
+    bias.assign((size_t)m_tiles * TC_BM, 0.f);
+    off.assign((size_t)m_tiles * TC_BM, -1);
+    for (int r = 0; r < rows; ++r) {
+        const int m = r / TC_BM, rl = r % TC_BM;
+        bias[r] = mean[r];
+        off[r] = (r / per_tri) * 9 + col0 + r % per_tri;
+        for (int k = 0; k < K; ++k) {
+            const float v = W[(size_t)r * K + k], hi = tf32_hi(v);
+            float *tile = &img[((size_t)m * kbs + k / TC_BK) * (2 * TC_BM * TC_BK)];
+            tile[swz(rl, k % TC_BK)] = hi;
+            tile[TC_BM * TC_BK + swz(rl, k % TC_BK)] = v - hi;
+        }
+    }
+}
+
+cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
+                             float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    const int n_tiles = (n_frames + TC_BN - 1) / TC_BN;
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const long long stride = (long long)d.n_needed * 9;
+    for (int g = 0; g < 2; ++g) {
+        const float *x = g == 0 ? coeff_scale : coeff_rotat;
+        const int K = g == 0 ? d.k_scale : d.k_rotat, kbs = tc_kblocks(K);
+        float *ximg = g == 0 ? ximg_scale : ximg_rotat;
+        k_split_coeffs<<<dim3(8, (unsigned)n_tiles), 256, 0, stream>>>(x, K, n_frames, kbs, ximg);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        GemmParams P{g == 0 ? d.tc_w_scale : d.tc_w_rotat, ximg, g == 0 ? d.tc_b_scale : d.tc_b_rotat,
+                     g == 0 ? d.tc_o_scale : d.tc_o_rotat, dgrad_out, stride, n_frames,
+                     g == 0 ? d.tc_mt_scale : d.tc_mt_rotat, n_tiles, kbs};
+        int grid = P.m_tiles * n_tiles;
+        if (grid > d.sm_count) grid = d.sm_count;
+        k_decode_tc<<<grid, TC_THREADS, smem, stream>>>(P);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace sdfa

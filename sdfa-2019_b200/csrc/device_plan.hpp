@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "plan.hpp"
+#include <vector>
 
 namespace sdfa {
 
@@ -35,6 +36,10 @@ struct DevicePlan {
     float *w_scale = nullptr, *m_scale = nullptr;  // compact basis rows [n_needed*6, k_scale], means
     float *w_rotat = nullptr, *m_rotat = nullptr;  // [n_needed*3, k_rotat]
     float *wfull_scale = nullptr, *mfull_scale = nullptr, *wfull_rotat = nullptr, *mfull_rotat = nullptr;
+    // tensor-core decode (decode_tc.cu): pre-split, pre-tiled basis images, bias and output offsets per row
+    float *tc_w_scale = nullptr, *tc_w_rotat = nullptr, *tc_b_scale = nullptr, *tc_b_rotat = nullptr;
+    int32_t *tc_o_scale = nullptr, *tc_o_rotat = nullptr;
+    int tc_mt_scale = 0, tc_mt_rotat = 0;
 };
 
 enum AssemblyMode { ASM_DGRAD = 0, ASM_MATRIX = 1 };
@@ -48,7 +53,15 @@ cudaError_t launch_decode(const DevicePlan &d, const float *coeff_scale, const f
                           bool full_layout, float *dgrad_out, cudaStream_t stream);
 cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, const uint32_t *tris, int n_tris,
                                double eps, int as_matrix, double *out, cudaStream_t stream);
+// decode_tc.cu
+cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
+                             float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);
+size_t tc_ximg_floats(int n_frames, int K);
 size_t solve_smem_bytes(int n_slots);
+void count_launch();
 long long launch_counter();
+
+void tc_build_basis(const float *W, const float *mean, int n_tri, int per_tri, int col0, int K,
+                    std::vector<float> &img, std::vector<float> &bias, std::vector<int32_t> &off);
 
 }  // namespace sdfa

@@ -17,6 +17,7 @@ namespace sdfa {
 
 static std::atomic<long long> g_launches{0};
 long long launch_counter() { return g_launches.load(); }
+void count_launch() { g_launches++; }
 
 // =============================================================================================
 // K2: per-equation transform + A^T (T^T - I) assembly.

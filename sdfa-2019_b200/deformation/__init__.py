@@ -227,6 +227,25 @@ class Reconstructor:
                                         ptr(out.data_ptr()), ptr(s)))
         return out
 
+    def needed_tris(self):
+        """Sorted source triangles the reconstruction reads (the rows kept of the PCA basis)."""
+        n = lib.sdfa_needed_tris(self._h, None, 0)
+        out = np.empty(n, dtype=np.int32)
+        lib.sdfa_needed_tris(self._h, ptr(out), n)
+        return out
+
+    def decode_compact(self, coeff_scale, coeff_rotat, stream=None):
+        """Coefficients -> dgrad of needed_tris() only, [N, n_needed, 9] (torch.cuda; tcgen05 kernel)."""
+        import torch
+        a = coeff_scale.contiguous().reshape(-1, self.k_scale)
+        b = coeff_rotat.contiguous().reshape(-1, self.k_rotat)
+        n_needed = lib.sdfa_needed_tris(self._h, None, 0)
+        out = torch.empty((a.shape[0], n_needed, 9), dtype=torch.float32, device=a.device)
+        s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
+        check(lib.sdfa_decode_compact_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), a.shape[0],
+                                          ptr(out.data_ptr()), ptr(s)))
+        return out
+
     # ------------------------------------------------------------------------------ measurement
     def set_timing(self, enable=True):
         check(lib.sdfa_set_timing(self._h, 1 if enable else 0))

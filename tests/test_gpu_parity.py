@@ -160,6 +160,24 @@ def test_small_mesh_modes_vs_golden(golden_small):
     assert np.abs(out).max() < 1.0            # and it stays near the template instead of drifting off
 
 
+def test_tensor_core_decode_matches_fp64(rec, flame):
+    """K1 (tcgen05, 3xTF32) vs the float64 ground truth, against the error torch's own fp32 F.linear makes."""
+    import torch
+    F, nft = flame["F"], flame["nft"]
+    cs, ms, cr, mr = W.random_pca(len(F), seed=1)
+    rec.set_pca(cs, ms, cr, mr)
+    for n in (1, 127, 300):
+        xs, xr = W.random_coeffs(n, seed=40 + n)
+        got = rec.decode_compact(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda()).cpu().numpy()
+        need = rec.needed_tris()
+        assert got.shape == (n, len(need), 9) and len(need) == 2601
+        dg64 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float64).reshape(n, -1, 9)[:, need]
+        dg32 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float32).reshape(n, -1, 9)[:, need]
+        err, err32 = np.abs(got - dg64).max(), np.abs(dg32 - dg64).max()
+        assert err <= 4 * err32 + 1e-7, (n, err, err32)
+        assert err <= 1e-6            # what 4.4e-7 m vertex parity needs (SURVEY 7.3)
+
+
 def test_decode_and_reconstruct_config2(rec, chk, flame):
     """Config 2: 240 frames of PCA coefficients -> vertices; oracle = fp32 F.linear + cat + reference get_mesh."""
     import torch
