@@ -174,8 +174,10 @@ def test_tensor_core_decode_matches_fp64(rec, flame):
         dg64 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float64).reshape(n, -1, 9)[:, need]
         dg32 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float32).reshape(n, -1, 9)[:, need]
         err, err32 = np.abs(got - dg64).max(), np.abs(dg32 - dg64).max()
-        assert err <= 4 * err32 + 1e-7, (n, err, err32)
-        assert err <= 1e-6            # what 4.4e-7 m vertex parity needs
+        # 3xTF32 is a few times coarser than fp32 FMA accumulation (operands truncated to 2 x 11 bits,
+        # tensor-core accumulation) but must stay well inside what 4.4e-7 m vertex parity needs:
+        # |dgrad error| <~ 1e-6
+        assert err <= 5e-7, (n, err, err32)
 
 
 def test_decode_and_reconstruct_config2(rec, chk, flame):
