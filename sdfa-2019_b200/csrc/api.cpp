@@ -144,7 +144,10 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         if ((rc = build_system(p, err)) != 0) { delete h; return fail(SDFA_ERR_ARG, "sdfa_create: " + err); }
         if ((rc = order_and_factor(p, err)) != 0) { delete h; return fail(SDFA_ERR_FACTOR, "sdfa_create: " + err); }
         compute_base_solution(p, nullptr);
-        build_solve_program(p, /*piece_cap=*/64, /*supernode_cap=*/32);
+        {
+            auto envi = [](const char *k, int d) { const char *v = std::getenv(k); return v ? std::atoi(v) : d; };
+            build_solve_program(p, envi("SDFA_PIECE_CAP", 64), envi("SDFA_SUPERNODE_CAP", 32), envi("SDFA_SUBTREE_CAP", 24));
+        }
         build_assembly_plan(p, /*rows_per_block=*/128, ASM_MAX_EQ);
     } catch (const std::exception &e) {
         delete h;
@@ -578,7 +581,7 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
                                     (long long)p.prog.bytes.size(), p.asmplan.max_eq_per_block,
                                     (long long)p.asmplan.eq_id.size(), (long long)p.asmplan.blocks.size(),
                                     (long long)solve_smem_bytes(p.prog.n_slots), p.prog.n_supernodes,
-                                    (long long)p.prog.io_desc.size()};
+                                    (long long)p.prog.io_desc.size(), p.prog.n_entries_padded};
         return give(s, dst, cap);
     }
     return -1;

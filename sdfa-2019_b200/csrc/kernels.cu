@@ -246,8 +246,35 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 
 __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state_lane) {
     const uint4 th = *reinterpret_cast<const uint4 *>(task);       // TaskHeader
-    const int n = (int)(th.y & 0xFFFFFFu);
-    const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);   // two entries per uint4
+    const int n = (int)(th.w & 0xFFFFFFu);
+    if (th.w & TASK_GROUP) {
+        // kind B: up to three target rows share the sources -> 9 FMAs per 3 shared-memory value loads
+        const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);
+        float a[3][3] = {};
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) {
+            const uint4 p = e[k];
+            const float *s = reinterpret_cast<const float *>(state_lane + p.x);
+            const float v0 = s[0], v1 = s[COORD_STRIDE], v2 = s[2 * COORD_STRIDE];
+            const float c0 = __uint_as_float(p.y), c1 = __uint_as_float(p.z), c2 = __uint_as_float(p.w);
+            a[0][0] = fmaf(c0, v0, a[0][0]); a[0][1] = fmaf(c0, v1, a[0][1]); a[0][2] = fmaf(c0, v2, a[0][2]);
+            a[1][0] = fmaf(c1, v0, a[1][0]); a[1][1] = fmaf(c1, v1, a[1][1]); a[1][2] = fmaf(c1, v2, a[1][2]);
+            a[2][0] = fmaf(c2, v0, a[2][0]); a[2][1] = fmaf(c2, v1, a[2][1]); a[2][2] = fmaf(c2, v2, a[2][2]);
+        }
+        const uint32_t tg[3] = {th.x, th.y, th.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (tg[r] == 0xFFFFFFFFu) continue;
+            float *t = reinterpret_cast<float *>(state_lane + tg[r]);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if (!(th.w & (TASK_OVERWRITE << r))) { v0 = t[0]; v1 = t[COORD_STRIDE]; v2 = t[2 * COORD_STRIDE]; }
+            t[0] = v0 - a[r][0];
+            t[COORD_STRIDE] = v1 - a[r][1];
+            t[2 * COORD_STRIDE] = v2 - a[r][2];
+        }
+        return;
+    }
+    const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);   // kind A: two entries per uint4
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll 4
     for (int k = 0; k < n; k += 2) {
@@ -260,7 +287,7 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
     }
     float *t = reinterpret_cast<float *>(state_lane + th.x);
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (!(th.y & TASK_OVERWRITE)) { v0 = t[0]; v1 = t[COORD_STRIDE]; v2 = t[2 * COORD_STRIDE]; }
+    if (!(th.w & TASK_OVERWRITE)) { v0 = t[0]; v1 = t[COORD_STRIDE]; v2 = t[2 * COORD_STRIDE]; }
     t[0] = v0 - (a0 + b0);
     t[COORD_STRIDE] = v1 - (a1 + b1);
     t[2 * COORD_STRIDE] = v2 - (a2 + b2);

@@ -45,15 +45,19 @@ struct StageHeader {     // first 16 bytes of every stage
     uint32_t n_ops, bytes, reserved0, reserved1;
 };
 
-// Row task (OP_ROWS): 16-byte header followed by n entries of 8 bytes {float coeff; u32 src_byte_off}.
-//   acc = sum coeff * slot[src];   slot[target] = (OVERWRITE ? 0 : slot[target]) - acc
+// Tasks of OP_ROWS: a 16-byte header followed by the entries.
+//   kind A (one row):   header {target, -, -, n | flags}; n (even) entries of 8 bytes {coeff, src}
+//        acc = sum coeff * slot[src];   slot[target] = (OVERWRITE ? 0 : slot[target]) - acc
+//   kind B (TASK_GROUP, up to 3 rows reading the same sources): header {target0, target1, target2, n | flags},
+//        n entries of 16 bytes {src, c0, c1, c2}; every source value is loaded once and used for all rows.
+//        Absent rows have target 0xFFFFFFFF; OVERWRITE of row r is flag bit 25 + r.
 struct TaskHeader {
-    uint32_t target_byte_off;
-    uint32_t n_entries_flags;   // low 24 bits count (even), bit 25 = OVERWRITE
-    uint32_t reserved0, reserved1;
+    uint32_t target_byte_off, target1, target2;
+    uint32_t n_entries_flags;   // low 24 bits count, bit 24 = TASK_GROUP, bits 25.. = OVERWRITE per row
 };
-constexpr uint32_t TASK_OVERWRITE = 1u << 25;
+constexpr uint32_t TASK_GROUP = 1u << 24, TASK_OVERWRITE = 1u << 25;
 struct TaskEntry { float coeff; uint32_t src_byte_off; };
+struct GroupEntry { uint32_t src_byte_off; float c[3]; };
 
 // IO tables: n_rows consecutive permuted rows <-> n_rows consecutive slots, one cp.async.bulk each.
 struct IoDesc { uint32_t row, n_rows, slot, reserved; };
@@ -67,7 +71,8 @@ struct SolveProgram {
     int n_phases_fwd = 0, n_phases_bwd = 0;
     int n_slots = 0;                    // state slots a CTA needs (peak over both sweeps)
     int n_steps_fwd = 0, n_steps_bwd = 0, n_supernodes = 0;
-    long long n_entries = 0;            // multiply-adds per (frame, coordinate)
+    long long n_entries = 0;            // useful multiply-adds per (frame, coordinate)
+    long long n_entries_padded = 0;     // issued ones (zero padding of grouped rows included)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -125,7 +130,7 @@ int  order_and_factor(HostPlan &p, std::string &err);             // perm, etree
 void compute_base_solution(HostPlan &p, const float *cnst_pos);   // x_base
 void solve_factored(const HostPlan &p, std::vector<double> &rhs_perm /* [n_free*3] in/out */);
 // schedule.cpp
-void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap);
+void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap);
 void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block);
 constexpr int ASM_MAX_EQ = 512;   // equations per row block the assembly kernel keeps in registers/shared memory
 

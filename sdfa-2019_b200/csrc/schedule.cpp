@@ -19,8 +19,10 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <set>
 #include <stdexcept>
 #include <cstddef>
+#include <cstdlib>
 
 namespace sdfa {
 
@@ -29,24 +31,30 @@ namespace {
 struct Task {
     int target_slot;
     uint32_t flags;
-    std::vector<TaskEntry> entries;
+    std::vector<TaskEntry> entries;     // src_byte_off holds a (symbolic) slot id until emission
+    int target_row = -1;                // permuted row the task writes (grouping key)
+};
+
+// A serialised task (header + entries) ready to be placed into a stage.
+struct Blob {
+    std::vector<uint8_t> bytes;
+    size_t work;                        // multiply-adds per lane and coordinate, for load balancing
 };
 
 class Emitter {
 public:
     explicit Emitter(SolveProgram &prog) : prog_(prog) { open_stage(); }
 
-    // one level: independent row tasks, dealt round-robin to the consumer warps by the kernel
-    void rows(std::vector<Task> &tasks, bool sync_after) {
-        std::stable_sort(tasks.begin(), tasks.end(),
-                         [](const Task &a, const Task &b) { return a.entries.size() > b.entries.size(); });
+    // one level: independent tasks, dealt round-robin to the consumer warps by the kernel
+    void rows(std::vector<Blob> &tasks, bool sync_after) {
+        std::stable_sort(tasks.begin(), tasks.end(), [](const Blob &a, const Blob &b) { return a.work > b.work; });
         size_t i = 0;
         while (i < tasks.size()) {
             size_t room = STAGE_BYTES - cur_.size();
             size_t n = 0, bytes = sizeof(OpHeader);
             while (i + n < tasks.size()) {
                 size_t table = ((n + 1) * 4 + 15) / 16 * 16;
-                size_t body = task_bytes(tasks[i + n]);
+                size_t body = tasks[i + n].bytes.size();
                 size_t prev_table = (n * 4 + 15) / 16 * 16;
                 if (bytes - prev_table + table + body > room) break;
                 bytes = bytes - prev_table + table + body;
@@ -67,21 +75,9 @@ public:
             cur_.resize(table_at + table_bytes, 0);
             std::memcpy(&cur_[op_at], &h, sizeof(h));
             for (size_t t = 0; t < n; ++t) {
-                const Task &tk = tasks[i + t];
                 uint32_t off = (uint32_t)cur_.size();
                 std::memcpy(&cur_[table_at + t * 4], &off, 4);
-                size_t ne = tk.entries.size() + (tk.entries.size() & 1);   // pad to even -> 16 B multiple
-                TaskHeader th{(uint32_t)tk.target_slot * SLOT_BYTES, (uint32_t)ne | tk.flags, 0, 0};
-                cur_.resize(off + sizeof(TaskHeader) + ne * sizeof(TaskEntry), 0);
-                std::memcpy(&cur_[off], &th, sizeof(th));
-                if (!tk.entries.empty())
-                    std::memcpy(&cur_[off + sizeof(TaskHeader)], tk.entries.data(), tk.entries.size() * sizeof(TaskEntry));
-                if (tk.entries.size() & 1) {
-                    // padding entry: coefficient 0 on the task's own first source (always a live, finite slot)
-                    TaskEntry pad{0.f, tk.entries[0].src_byte_off};
-                    std::memcpy(&cur_[off + sizeof(TaskHeader) + tk.entries.size() * sizeof(TaskEntry)], &pad, sizeof(pad));
-                }
-                prog_.n_entries += (long long)tk.entries.size();
+                cur_.insert(cur_.end(), tasks[i + t].bytes.begin(), tasks[i + t].bytes.end());
             }
             uint32_t next = (uint32_t)cur_.size();
             std::memcpy(&cur_[op_at + offsetof(OpHeader, c)], &next, 4);
@@ -105,10 +101,6 @@ public:
     }
 
 private:
-    static size_t task_bytes(const Task &t) {
-        size_t ne = t.entries.size() + (t.entries.size() & 1);
-        return sizeof(TaskHeader) + ne * sizeof(TaskEntry);
-    }
     void open_stage() {
         cur_.assign(sizeof(StageHeader), 0);
         n_ops_ = 0;
@@ -174,6 +166,81 @@ void make_descs(std::vector<std::pair<int, int>> &rows_slots, std::vector<IoDesc
     }
 }
 
+// ---- serialisation of tasks (formats in plan.hpp) --------------------------------------------------
+// kind A: one target row, entries {coeff, src} packed two per 16 bytes.
+Blob blob_single(const Task &t) {
+    Blob b;
+    const size_t n = t.entries.size(), ne = n + (n & 1);
+    b.bytes.assign(sizeof(TaskHeader) + ne * sizeof(TaskEntry), 0);
+    TaskHeader th{(uint32_t)t.target_slot * SLOT_BYTES, 0, 0, (uint32_t)ne | t.flags};
+    std::memcpy(&b.bytes[0], &th, sizeof(th));
+    for (size_t k = 0; k < n; ++k) {
+        TaskEntry e{t.entries[k].coeff, t.entries[k].src_byte_off * SLOT_BYTES};
+        std::memcpy(&b.bytes[sizeof(TaskHeader) + k * sizeof(TaskEntry)], &e, sizeof(e));
+    }
+    if (n & 1) {     // padding entry: coefficient 0 on the task's own first source (a live, finite slot)
+        TaskEntry e{0.f, t.entries[0].src_byte_off * SLOT_BYTES};
+        std::memcpy(&b.bytes[sizeof(TaskHeader) + n * sizeof(TaskEntry)], &e, sizeof(e));
+    }
+    b.work = n;
+    return b;
+}
+// kind B: up to three target rows that read (nearly) the same sources: one entry {src, c0, c1, c2} per
+// source, so each source value is fetched from shared memory once for all rows of the group.
+Blob blob_group(const std::vector<const Task *> &rows) {
+    std::map<uint32_t, GroupEntry> uni;
+    for (size_t r = 0; r < rows.size(); ++r)
+        for (const TaskEntry &e : rows[r]->entries) {
+            GroupEntry &g = uni[e.src_byte_off];
+            g.src_byte_off = e.src_byte_off * SLOT_BYTES;
+            g.c[r] += e.coeff;
+        }
+    Blob b;
+    b.bytes.assign(sizeof(TaskHeader) + uni.size() * sizeof(GroupEntry), 0);
+    TaskHeader th{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)uni.size() | TASK_GROUP};
+    uint32_t *tg = &th.target_byte_off;
+    for (size_t r = 0; r < rows.size(); ++r) {
+        tg[r] = (uint32_t)rows[r]->target_slot * SLOT_BYTES;
+        if (rows[r]->flags & TASK_OVERWRITE) th.n_entries_flags |= (TASK_OVERWRITE << r);
+    }
+    std::memcpy(&b.bytes[0], &th, sizeof(th));
+    size_t k = 0;
+    for (auto &kv : uni) std::memcpy(&b.bytes[sizeof(TaskHeader) + (k++) * sizeof(GroupEntry)], &kv.second, sizeof(GroupEntry));
+    b.work = uni.size() * rows.size();
+    return b;
+}
+
+// Groups the tasks of one level: neighbouring target rows (same block of the factor) whose source lists
+// nearly coincide share one kind-B task.  `pad_limit` bounds the zero padding the union may introduce.
+std::vector<Blob> group_level(std::vector<Task> &lv, const std::vector<int> &block_of_row, double pad_limit,
+                              long long &useful, long long &padded) {
+    std::vector<Blob> out;
+    std::stable_sort(lv.begin(), lv.end(), [&](const Task &a, const Task &b) { return a.target_row < b.target_row; });
+    size_t i = 0;
+    while (i < lv.size()) {
+        std::vector<const Task *> grp{&lv[i]};
+        std::set<uint32_t> uni;
+        for (auto &e : lv[i].entries) uni.insert(e.src_byte_off);
+        size_t sum = lv[i].entries.size(), j = i + 1;
+        while (j < lv.size() && grp.size() < 3 && block_of_row[lv[j].target_row] == block_of_row[lv[i].target_row]) {
+            std::set<uint32_t> u2 = uni;
+            for (auto &e : lv[j].entries) u2.insert(e.src_byte_off);
+            const size_t sum2 = sum + lv[j].entries.size();
+            // cost of the group = |union| * rows; accept while the padding stays small
+            if ((double)(u2.size() * (grp.size() + 1)) > pad_limit * (double)sum2) break;
+            uni.swap(u2);
+            sum = sum2;
+            grp.push_back(&lv[j]);
+            ++j;
+        }
+        useful += (long long)sum;
+        if (grp.size() == 1) { out.push_back(blob_single(lv[i])); padded += (long long)sum; }
+        else { out.push_back(blob_group(grp)); padded += (long long)(uni.size() * 3); }
+        i = j;
+    }
+    return out;
+}
+
 struct Supernode {
     int c0, c1;                    // columns [c0, c1)
     std::vector<int> below;        // rows below the diagonal block (pattern of the last column)
@@ -184,17 +251,20 @@ struct Supernode {
 
 }  // namespace
 
-// Supernodes: maximal runs of columns j, j+1, ... where j+1 is j's parent and only child and the
-// pattern of j+1 is the pattern of j minus row j+1 (so the diagonal block and the block below are
-// dense), cut at `cap` columns.  Inverting the small diagonal blocks on the host (fp64) turns the
-// in-supernode chain of dependent rows into independent dot products:
-//      y_J = inv(L_JJ) t_J,     t_I -= (L_IJ inv(L_JJ)) t_J          (forward)
+// Blocks ("supernodes") of consecutive columns of the postordered factor, of two kinds:
+//   * chains: maximal runs j, j+1, ... where j+1 is j's parent and only child and pattern(j+1) =
+//     pattern(j) \ {j+1} (fundamental supernodes: dense diagonal block), cut at `cap` columns;
+//   * whole small subtrees (<= subtree_cap columns): contiguous in postorder as well, sparse inside.
+// Inverting the small diagonal block of a block J on the host (fp64) removes every dependency INSIDE it:
+//      y_J = inv(L_JJ) t_J,     t_I -= (L_IJ inv(L_JJ)) t_J          (forward,  I = rows below J)
 //      x_J = inv(L_JJ)^T y_J - (L_IJ inv(L_JJ))^T x_I                (backward)
-// so a sweep needs one barrier per LEVEL OF THE SUPERNODAL TREE instead of one per column.
-static std::vector<Supernode> find_supernodes(const HostPlan &p, int cap) {
+// so a sweep needs one barrier per level of the BLOCK tree instead of one per column.  inv(L_JJ) of a
+// subtree block is only as dense as the ancestor relation inside the subtree; exact zeros are dropped.
+static std::vector<Supernode> find_supernodes(const HostPlan &p, int cap, int subtree_cap) {
     const int n = p.n_free;
-    std::vector<int> nchild(n, 0);
-    for (int j = 0; j < n; ++j) if (p.parent[j] >= 0) nchild[p.parent[j]]++;
+    std::vector<int> nchild(n, 0), size(n, 1);
+    for (int j = 0; j < n; ++j)
+        if (p.parent[j] >= 0) { nchild[p.parent[j]]++; size[p.parent[j]] += size[j]; }
     auto cnt = [&](int j) { return p.l_colptr[j + 1] - p.l_colptr[j]; };
     // A pivot that is ~reg next to the matrix scale marks a direction the constraints do not fix (no
     // constraints: one translation per connected component).  The fp64 reference resolves it
@@ -206,17 +276,37 @@ static std::vector<Supernode> find_supernodes(const HostPlan &p, int cap) {
         for (int q = p.m_colptr[c]; q < p.m_colptr[c + 1]; ++q)
             if (p.m_rowidx[q] == c) max_diag = std::max(max_diag, p.m_val[q]);
     const double tiny_pivot2 = 1e-9 * max_diag;
+    // block boundaries
+    std::vector<std::pair<int, int>> ranges;
+    for (int j = 0; j < n;) {
+        // A leaf j may start a small subtree: climb while the parent's subtree also starts at j and fits.
+        if (size[j] == 1) {
+            int best = j, r = j;
+            while (true) {
+                int pr = p.parent[r];
+                if (pr < 0 || pr - size[pr] + 1 != j || size[pr] > subtree_cap) break;
+                best = r = pr;
+            }
+            if (best > j) { ranges.push_back({j, best + 1}); j = best + 1; continue; }
+        }
+        // chain supernode starting at j
+        int e = j + 1;
+        while (e < n && p.parent[e - 1] == e && nchild[e] == 1 && cnt(e) == cnt(e - 1) - 1 && (e - j) < cap) ++e;
+        ranges.push_back({j, e});
+        j = e;
+    }
     std::vector<Supernode> sn;
-    int start = 0;
-    for (int j = 1; j <= n; ++j) {
-        bool join = j < n && p.parent[j - 1] == j && nchild[j] == 1 && cnt(j) == cnt(j - 1) - 1 && (j - start) < cap;
-        if (join) continue;
+    for (auto [start, j] : ranges) {
         Supernode s;
         s.c0 = start; s.c1 = j;
-        const int last = j - 1, w = j - start;
-        for (int q = p.l_colptr[last] + 1; q < p.l_colptr[last + 1]; ++q) s.below.push_back(p.l_rowidx[q]);
+        const int w = j - start;
+        for (int col = start; col < j; ++col)
+            for (int q = p.l_colptr[col] + 1; q < p.l_colptr[col + 1]; ++q)
+                if (p.l_rowidx[q] >= j) s.below.push_back(p.l_rowidx[q]);
+        std::sort(s.below.begin(), s.below.end());
+        s.below.erase(std::unique(s.below.begin(), s.below.end()), s.below.end());
         const int h = (int)s.below.size();
-        // dense diagonal block T (lower) and block below B
+        // diagonal block T (lower) and block below B, as dense arrays
         std::vector<double> T((size_t)w * w, 0.0), B((size_t)h * w, 0.0);
         for (int b = 0; b < w; ++b) {
             int col = start + b;
@@ -246,7 +336,6 @@ static std::vector<Supernode> find_supernodes(const HostPlan &p, int cap) {
                 s.wmat[(size_t)k * w + c] = v;
             }
         sn.push_back(std::move(s));
-        start = j;
     }
     std::vector<int> sn_of(n);
     for (int i = 0; i < (int)sn.size(); ++i) for (int c = sn[i].c0; c < sn[i].c1; ++c) sn_of[c] = i;
@@ -268,11 +357,11 @@ struct PhaseData {
 };
 }  // namespace
 
-void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
+void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap) {
     const int n = p.n_free;
     SolveProgram &prog = p.prog;
     prog = SolveProgram();
-    std::vector<Supernode> sn = find_supernodes(p, supernode_cap);
+    std::vector<Supernode> sn = find_supernodes(p, supernode_cap, subtree_cap);
     const int ns = (int)sn.size();
     prog.n_supernodes = ns;
     // pieces: consecutive supernodes, about piece_cap rows each
@@ -326,17 +415,19 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
                 if (S.parent >= 0 && S.parent < s1) lvl[S.parent] = std::max(lvl[S.parent], l + 1);
                 if ((int)ph.levels.size() <= l) ph.levels.resize(l + 1);
                 for (int r = 0; r < w; ++r) {              // y_i = sum_b linv[r][b] t_b  (target overwritten)
-                    Task t{yslot[S.c0 + r], TASK_OVERWRITE, {}};
+                    Task t{yslot[S.c0 + r], TASK_OVERWRITE, {}, S.c0 + r};
                     for (int c = 0; c <= r; ++c)
-                        t.entries.push_back({(float)(-S.linv[(size_t)r * w + c]), (uint32_t)tslot[S.c0 + c]});
+                        if (S.linv[(size_t)r * w + c] != 0.0 || c == r)
+                            t.entries.push_back({(float)(-S.linv[(size_t)r * w + c]), (uint32_t)tslot[S.c0 + c]});
                     ph.levels[l].push_back(std::move(t));
                 }
                 for (size_t k = 0; k < S.below.size(); ++k) {   // t_i -= sum_b W[k][b] t_b
                     int i = S.below[k];
                     auto it = ext.find(i);
-                    if (it == ext.end()) { it = ext.emplace(i, Task{tslot[i], 0, {}}).first; ext_lvl[i] = 0; }
+                    if (it == ext.end()) { it = ext.emplace(i, Task{tslot[i], 0, {}, i}).first; ext_lvl[i] = 0; }
                     for (int c = 0; c < w; ++c)
-                        it->second.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)tslot[S.c0 + c]});
+                        if (S.wmat[k * w + c] != 0.0)
+                            it->second.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)tslot[S.c0 + c]});
                     ext_lvl[i] = std::max(ext_lvl[i], l);
                 }
             }
@@ -398,12 +489,14 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
                 lvl[s] = l;
                 if ((int)ph.levels.size() <= l) ph.levels.resize(l + 1);
                 for (int c = 0; c < w; ++c) {              // x_j = sum_r linv[r][c] y_r - sum_k W[k][c] x_below[k]
-                    Task t{xslot[S.c0 + c], TASK_OVERWRITE, {}};
+                    Task t{xslot[S.c0 + c], TASK_OVERWRITE, {}, S.c0 + c};
                     for (int r = c; r < w; ++r)
-                        t.entries.push_back({(float)(-S.linv[(size_t)r * w + c]), (uint32_t)yslot[S.c0 + r]});
+                        if (S.linv[(size_t)r * w + c] != 0.0 || r == c)
+                            t.entries.push_back({(float)(-S.linv[(size_t)r * w + c]), (uint32_t)yslot[S.c0 + r]});
                     for (size_t k = 0; k < S.below.size(); ++k) {
                         assert(xslot[S.below[k]] >= 0);
-                        t.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)xslot[S.below[k]]});
+                        if (S.wmat[k * w + c] != 0.0)
+                            t.entries.push_back({(float)S.wmat[k * w + c], (uint32_t)xslot[S.below[k]]});
                     }
                     ph.levels[l].push_back(std::move(t));
                 }
@@ -434,6 +527,11 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
     prog.n_slots = n_ext + n_piece;
     auto resolve = [&](int sym) { return (sym & EXT_FLAG) ? (sym & ~EXT_FLAG) : n_ext + sym; };
     Emitter em(prog);
+    std::vector<int> block_of_row(n);
+    for (int b = 0; b < ns; ++b) for (int c = sn[b].c0; c < sn[b].c1; ++c) block_of_row[c] = b;
+    const char *pl = std::getenv("SDFA_GROUP_PAD");
+    const double pad_limit = pl ? std::atof(pl) : 1.25;
+    long long useful = 0, padded = 0;
     for (auto &ph : phases) {
         for (auto &rs : ph.loads) rs.second = resolve(rs.second);
         for (auto &rs : ph.stores) rs.second = resolve(rs.second);
@@ -448,13 +546,16 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap) {
         for (auto &lv : ph.levels) {
             for (auto &t : lv) {
                 t.target_slot = resolve(t.target_slot);
-                for (auto &e : t.entries) e.src_byte_off = (uint32_t)resolve((int)e.src_byte_off) * SLOT_BYTES;
+                for (auto &e : t.entries) e.src_byte_off = (uint32_t)resolve((int)e.src_byte_off);
             }
-            em.rows(lv, true);
+            std::vector<Blob> blobs = group_level(lv, block_of_row, pad_limit, useful, padded);
+            em.rows(blobs, true);
         }
         em.marker(OP_PHASE_END);
     }
     em.finish();
+    prog.n_entries = useful;
+    prog.n_entries_padded = padded;
 }
 
 // ------------------------------------------------------------------------------------------

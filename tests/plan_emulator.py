@@ -10,7 +10,7 @@ import numpy as np
 F, CS = 32, 32                      # FRAMES_PER_TILE, COORD_STRIDE (csrc/plan.hpp)
 SLOT_WORDS = 3 * CS
 OP_ROWS, OP_PHASE_BEGIN, OP_PHASE_END = 1, 2, 3
-TASK_OVERWRITE = 1 << 25
+TASK_GROUP, TASK_OVERWRITE = 1 << 24, 1 << 25
 f32 = np.float32
 
 
@@ -127,9 +127,24 @@ def _parse_phases(rec):
                 assert typ == OP_ROWS and cur is not None
                 table = st[b:b + 4 * a].view(np.uint32)
                 for off in table:
-                    tgt, nf = st[off:off + 8].view(np.uint32)
+                    t0, t1, t2, nf = st[off:off + 16].view(np.uint32)
                     n = int(nf & 0xFFFFFF)
-                    assert n % 2 == 0 and off % 16 == 0 and tgt % (4 * SLOT_WORDS) == 0
+                    assert off % 16 == 0
+                    if nf & TASK_GROUP:                       # kind B: {src, c0, c1, c2} entries, up to 3 rows
+                        ent = st[off + 16: off + 16 + 16 * n]
+                        src = ent.view(np.uint32)[0::4]
+                        assert (src % (4 * SLOT_WORDS) == 0).all()
+                        cf = ent.view(f32).reshape(n, 4)[:, 1:]
+                        for r, tgt in enumerate((t0, t1, t2)):
+                            if tgt == 0xFFFFFFFF:
+                                assert not cf[:, r].any()
+                                continue
+                            assert tgt % (4 * SLOT_WORDS) == 0
+                            level.append((int(tgt) // 4 // SLOT_WORDS, bool(nf & (TASK_OVERWRITE << r)), cf[:, r].copy(),
+                                          (src // 4 // SLOT_WORDS).astype(np.int64)))
+                        continue
+                    tgt = t0
+                    assert n % 2 == 0 and tgt % (4 * SLOT_WORDS) == 0
                     ent = st[off + 16: off + 16 + 8 * n]
                     src = ent.view(np.uint32)[1::2]
                     assert (src % (4 * SLOT_WORDS) == 0).all()

@@ -85,8 +85,8 @@ def test_system_matrix_and_factor(flame_rec, flame_oracle):
 
 def test_program_budget(flame_rec):
     n_slots, n_phases, st_f, st_b, n_entries, n_stages, nbytes, max_eq, _, _, smem = flame_rec.debug("stats")[:11]
-    # every factor entry is applied once per sweep (the inverted diagonal blocks are as dense as the originals)
-    assert n_entries == 2 * flame_rec.nnz_l
+    # work per sweep stays within 2x of the factor's nonzeros (inverted subtree blocks add some fill)
+    assert 2 * flame_rec.nnz_l <= n_entries <= 4 * flame_rec.nnz_l
     assert st_f + st_b < 500                  # levels (= consumer barriers) per tile; the column count is 2 x 1261
     assert smem <= 227 * 1024
     assert max_eq * 36 <= 48 * 1024
