@@ -112,6 +112,7 @@ class CpuReference:
         import torch
         from oracle import ref_loader
         self.torch = torch
+        torch.set_num_threads(max(1, n_threads))     # torchrun pins OMP_NUM_THREADS=1; the reference arm may use every core
         self.cs, self.ms, self.cr, self.mr = (torch.from_numpy(a) for a in pca)
         self.C = V[nfv]
         if ref_loader.ref_available():

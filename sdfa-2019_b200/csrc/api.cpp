@@ -36,14 +36,18 @@ struct sdfa_handle {
     int n_src_tris = 0;
     bool has_pca = false, has_full_pca = false;
     std::vector<int32_t> needed_tris;     // source triangles the active equations read (decode keeps these)
-    // growable scratch
-    float *rhs = nullptr; size_t rhs_cap = 0;          // tile-major scratch [tiles][n_free][3][32]
-    float *dgrad_c = nullptr; size_t dgrad_c_cap = 0;  // compact decoded dgrad
-    float *io_in = nullptr; size_t io_in_cap = 0;      // staging for *_host entry points
-    float *io_out = nullptr; size_t io_out_cap = 0;
-    float *io_in2 = nullptr; size_t io_in2_cap = 0;
-    float *ximg_s = nullptr; size_t ximg_s_cap = 0;    // split coefficient tile images (tensor-core decode)
-    float *ximg_r = nullptr; size_t ximg_r_cap = 0;
+    // growable device scratch, two sets so that the *_host entry points can overlap the copies of one
+    // chunk with the kernels of the next (each set is used on its own stream)
+    struct Workspace {
+        float *rhs = nullptr; size_t rhs_cap = 0;          // tile-major scratch [tiles][n_free][3][32]
+        float *dgrad_c = nullptr; size_t dgrad_c_cap = 0;  // compact decoded dgrad
+        float *ximg_s = nullptr; size_t ximg_s_cap = 0;    // split coefficient tile images (tensor-core decode)
+        float *ximg_r = nullptr; size_t ximg_r_cap = 0;
+        float *io_in = nullptr; size_t io_in_cap = 0;      // staging for *_host entry points
+        float *io_in2 = nullptr; size_t io_in2_cap = 0;
+        float *io_out = nullptr; size_t io_out_cap = 0;
+        cudaStream_t stream = nullptr;
+    } ws[2];
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
@@ -218,7 +222,10 @@ void sdfa_destroy(sdfa_handle *h) {
     if (h->dev.device >= 0) {
         cudaSetDevice(h->dev.device);
         for (void *p : h->allocs) cudaFree(p);
-        for (float *p : {h->rhs, h->dgrad_c, h->io_in, h->io_out, h->io_in2, h->ximg_s, h->ximg_r}) if (p) cudaFree(p);
+        for (auto &w : h->ws) {
+            for (float *p : {w.rhs, w.dgrad_c, w.io_in, w.io_out, w.io_in2, w.ximg_s, w.ximg_r}) if (p) cudaFree(p);
+            if (w.stream) cudaStreamDestroy(w.stream);
+        }
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     }
     delete h;
@@ -307,17 +314,17 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
     return SDFA_OK;
 }
 
-static int reconstruct_core(sdfa_handle *h, const float *dgrad_dev, long long stride, const int32_t *eq_src, int mode,
-                            int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
+static int reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *dgrad_dev, long long stride,
+                            const int32_t *eq_src, int mode, int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
     int rc;
     const size_t n_tiles = ((size_t)n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
-    if ((rc = grow(&h->rhs, &h->rhs_cap, n_tiles * h->dev.n_free * SLOT_WORDS))) return rc;
+    if ((rc = grow(&w.rhs, &w.rhs_cap, n_tiles * h->dev.n_free * SLOT_WORDS))) return rc;
     if ((rc = time_mark(h, 1, s))) return rc;
-    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, eq_src, n_frames, mode, h->rhs, s));
+    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, eq_src, n_frames, mode, w.rhs, s));
     if ((rc = time_mark(h, 2, s))) return rc;
-    CUDA_TRY(launch_solve(h->dev, h->rhs, n_frames, s));
+    CUDA_TRY(launch_solve(h->dev, w.rhs, n_frames, s));
     if ((rc = time_mark(h, 3, s))) return rc;
-    CUDA_TRY(launch_output(h->dev, h->rhs, n_frames, out_dev, s));
+    CUDA_TRY(launch_output(h->dev, w.rhs, n_frames, out_dev, s));
     if ((rc = time_mark(h, 4, s))) return rc;
     return time_finish(h, s, decoded);
 }
@@ -328,21 +335,34 @@ int sdfa_reconstruct_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad
     if ((rc = need_device(h))) return rc;
     if (n_frames < 0 || (n_frames > 0 && (!dgrad_dev || !out_dev))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_dev: bad arguments");
     long long stride = dgrad_stride ? dgrad_stride : (long long)h->n_src_tris * 9;
-    return reconstruct_core(h, dgrad_dev, stride, h->dev.eq_src, ASM_DGRAD, n_frames, out_dev, (cudaStream_t)stream, false);
+    return reconstruct_core(h, h->ws[0], dgrad_dev, stride, h->dev.eq_src, ASM_DGRAD, n_frames, out_dev, (cudaStream_t)stream, false);
+}
+
+// Frames per chunk of the host-buffer entry points: copies of chunk i overlap the kernels of chunk i+1.
+static const int HOST_CHUNK = 4096;
+
+static int ws_stream(sdfa_handle::Workspace &w) {
+    if (!w.stream) CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    return SDFA_OK;
 }
 
 int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host) {
     int rc;
     if ((rc = need_device(h))) return rc;
     if (n_frames < 0 || (n_frames > 0 && (!dgrad_host || !out_host))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_host: bad arguments");
-    if (n_frames == 0) return SDFA_OK;
-    const size_t in_f = (size_t)n_frames * h->n_src_tris * 9, out_f = (size_t)n_frames * h->dev.n_verts * 3;
-    if ((rc = grow(&h->io_in, &h->io_in_cap, in_f))) return rc;
-    if ((rc = grow(&h->io_out, &h->io_out_cap, out_f))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h->io_in, dgrad_host, in_f * 4, cudaMemcpyHostToDevice, 0));
-    if ((rc = reconstruct_core(h, h->io_in, (long long)h->n_src_tris * 9, h->dev.eq_src, ASM_DGRAD, n_frames, h->io_out, 0, false))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_host, h->io_out, out_f * 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    const size_t row_in = (size_t)h->n_src_tris * 9, row_out = (size_t)h->dev.n_verts * 3;
+    for (int f0 = 0, k = 0; f0 < n_frames; f0 += HOST_CHUNK, k ^= 1) {
+        const int nf = std::min(HOST_CHUNK, n_frames - f0);
+        sdfa_handle::Workspace &w = h->ws[k];
+        if ((rc = ws_stream(w))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(w.stream));            // this set's previous chunk has left the device
+        if ((rc = grow(&w.io_in, &w.io_in_cap, (size_t)HOST_CHUNK * row_in))) return rc;
+        if ((rc = grow(&w.io_out, &w.io_out_cap, (size_t)HOST_CHUNK * row_out))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(w.io_in, dgrad_host + (size_t)f0 * row_in, (size_t)nf * row_in * 4, cudaMemcpyHostToDevice, w.stream));
+        if ((rc = reconstruct_core(h, w, w.io_in, (long long)row_in, h->dev.eq_src, ASM_DGRAD, nf, w.io_out, w.stream, false))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)f0 * row_out, w.io_out, (size_t)nf * row_out * 4, cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (auto &w : h->ws) if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
     return SDFA_OK;
 }
 
@@ -355,11 +375,13 @@ static int single_frame(sdfa_handle *h, const double *in, long long len, int mod
     if ((rc = sdfa_set_constraint_positions(h, p.n_cnsts > 0 ? cnst : nullptr))) return rc;
     std::vector<float> f32((size_t)len);
     for (long long i = 0; i < len; ++i) f32[(size_t)i] = (float)in[i];
-    if ((rc = grow(&h->io_in, &h->io_in_cap, (size_t)len))) return rc;
-    if ((rc = grow(&h->io_out, &h->io_out_cap, (size_t)p.n_verts * 3))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h->io_in, f32.data(), (size_t)len * 4, cudaMemcpyHostToDevice, 0));
-    if ((rc = reconstruct_core(h, h->io_in, len, h->dev.eq_src, mode, 1, h->io_out, 0, false))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_host, h->io_out, (size_t)p.n_verts * 12, cudaMemcpyDeviceToHost, 0));
+    sdfa_handle::Workspace &w = h->ws[0];
+    if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
+    if ((rc = grow(&w.io_in, &w.io_in_cap, (size_t)len))) return rc;
+    if ((rc = grow(&w.io_out, &w.io_out_cap, (size_t)p.n_verts * 3))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(w.io_in, f32.data(), (size_t)len * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = reconstruct_core(h, w, w.io_in, len, h->dev.eq_src, mode, 1, w.io_out, 0, false))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, w.io_out, (size_t)p.n_verts * 12, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
     return SDFA_OK;
 }
@@ -443,6 +465,22 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     return SDFA_OK;
 }
 
+static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *cs_dev, const float *cr_dev,
+                                   int n_frames, float *out_dev, cudaStream_t s) {
+    int rc;
+    const long long stride = (long long)h->dev.n_needed * 9;
+    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, (size_t)n_frames * stride))) return rc;
+    if ((rc = time_mark(h, 0, s))) return rc;
+    if (std::getenv("SDFA_DECODE_SIMT")) {           // debugging aid: the fp32 CUDA-core decode kernel
+        CUDA_TRY(launch_decode(h->dev, cs_dev, cr_dev, n_frames, false, w.dgrad_c, s));
+    } else {
+        if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
+        if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
+        CUDA_TRY(launch_decode_tc(h->dev, cs_dev, cr_dev, n_frames, w.ximg_s, w.ximg_r, w.dgrad_c, s));
+    }
+    return reconstruct_core(h, w, w.dgrad_c, stride, h->dev.eq_src_compact, ASM_DGRAD, n_frames, out_dev, s, true);
+}
+
 int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
                                 float *out_dev, void *stream) {
     int rc;
@@ -450,18 +488,7 @@ int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, co
     if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_reconstruct: call sdfa_set_pca first (and again after changing correspondences)");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !out_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
     if (n_frames == 0) return SDFA_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const long long stride = (long long)h->dev.n_needed * 9;
-    if ((rc = grow(&h->dgrad_c, &h->dgrad_c_cap, (size_t)n_frames * stride))) return rc;
-    if ((rc = time_mark(h, 0, s))) return rc;
-    if (std::getenv("SDFA_DECODE_SIMT")) {           // debugging aid: the fp32 CUDA-core decode kernel
-        CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, h->dgrad_c, s));
-    } else {
-        if ((rc = grow(&h->ximg_s, &h->ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
-        if ((rc = grow(&h->ximg_r, &h->ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
-        CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, h->ximg_s, h->ximg_r, h->dgrad_c, s));
-    }
-    return reconstruct_core(h, h->dgrad_c, stride, h->dev.eq_src_compact, ASM_DGRAD, n_frames, out_dev, s, true);
+    return decode_reconstruct_core(h, h->ws[0], coeff_scale_dev, coeff_rotat_dev, n_frames, out_dev, (cudaStream_t)stream);
 }
 
 int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host,
@@ -470,17 +497,21 @@ int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, 
     if ((rc = need_device(h))) return rc;
     if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_reconstruct: call sdfa_set_pca first");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_host || !coeff_rotat_host || !out_host))) return fail(SDFA_ERR_ARG, "bad arguments");
-    if (n_frames == 0) return SDFA_OK;
-    const size_t ns = (size_t)n_frames * h->dev.k_scale, nr = (size_t)n_frames * h->dev.k_rotat;
-    const size_t out_f = (size_t)n_frames * h->dev.n_verts * 3;
-    if ((rc = grow(&h->io_in, &h->io_in_cap, ns))) return rc;
-    if ((rc = grow(&h->io_in2, &h->io_in2_cap, nr))) return rc;
-    if ((rc = grow(&h->io_out, &h->io_out_cap, out_f))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h->io_in, coeff_scale_host, ns * 4, cudaMemcpyHostToDevice, 0));
-    CUDA_TRY(cudaMemcpyAsync(h->io_in2, coeff_rotat_host, nr * 4, cudaMemcpyHostToDevice, 0));
-    if ((rc = sdfa_decode_reconstruct_dev(h, h->io_in, h->io_in2, n_frames, h->io_out, nullptr))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_host, h->io_out, out_f * 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    const size_t ks = (size_t)h->dev.k_scale, kr = (size_t)h->dev.k_rotat, row_out = (size_t)h->dev.n_verts * 3;
+    for (int f0 = 0, k = 0; f0 < n_frames; f0 += HOST_CHUNK, k ^= 1) {
+        const int nf = std::min(HOST_CHUNK, n_frames - f0);
+        sdfa_handle::Workspace &w = h->ws[k];
+        if ((rc = ws_stream(w))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(w.stream));
+        if ((rc = grow(&w.io_in, &w.io_in_cap, (size_t)HOST_CHUNK * ks))) return rc;
+        if ((rc = grow(&w.io_in2, &w.io_in2_cap, (size_t)HOST_CHUNK * kr))) return rc;
+        if ((rc = grow(&w.io_out, &w.io_out_cap, (size_t)HOST_CHUNK * row_out))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(w.io_in, coeff_scale_host + (size_t)f0 * ks, (size_t)nf * ks * 4, cudaMemcpyHostToDevice, w.stream));
+        CUDA_TRY(cudaMemcpyAsync(w.io_in2, coeff_rotat_host + (size_t)f0 * kr, (size_t)nf * kr * 4, cudaMemcpyHostToDevice, w.stream));
+        if ((rc = decode_reconstruct_core(h, w, w.io_in, w.io_in2, nf, w.io_out, w.stream))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)f0 * row_out, w.io_out, (size_t)nf * row_out * 4, cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (auto &w : h->ws) if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
     return SDFA_OK;
 }
 
@@ -506,9 +537,10 @@ int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const 
         CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, dgrad_compact_dev, s));
         return SDFA_OK;
     }
-    if ((rc = grow(&h->ximg_s, &h->ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
-    if ((rc = grow(&h->ximg_r, &h->ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
-    CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, h->ximg_s, h->ximg_r, dgrad_compact_dev, s));
+    sdfa_handle::Workspace &w = h->ws[0];
+    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
+    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
+    CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, w.ximg_s, w.ximg_r, dgrad_compact_dev, s));
     return SDFA_OK;
 }
 
