@@ -112,13 +112,13 @@ int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, 
 int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
                           int n_frames, float *dgrad_dev, void *stream);
 
-/* decode only, compact layout: dgrad of the source triangles the reconstruction actually reads (the
- * ones some active equation block refers to), [n_frames, n_needed, 9].  This is what
- * sdfa_decode_reconstruct_* produces internally with the tcgen05 kernel.  sdfa_needed_tris copies the
- * sorted source-triangle indices (returns their count; tris may be NULL). */
+/* decode only, into the internal block-planar compact layout the assembly kernel consumes (what
+ * sdfa_decode_reconstruct_* produces with the tcgen05 kernel): [n_frames, stride] float32.
+ * sdfa_compact_layout returns `stride` and copies the map compact float -> source_triangle*9 + component
+ * (-1 = padding / nothing decoded there); map may be NULL. */
 int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
                             int n_frames, float *dgrad_compact_dev, void *stream);
-int sdfa_needed_tris(const sdfa_handle *h, int32_t *tris, int cap);
+int sdfa_compact_layout(const sdfa_handle *h, int32_t *map, int cap);
 
 /* ---- inverse path: meshes -> dgrad (getDeformationGradients, impl.hpp:144-213) ----------- */
 

@@ -35,7 +35,6 @@ struct sdfa_handle {
     std::vector<int32_t> eq_src_host;     // current equation -> source triangle map
     int n_src_tris = 0;
     bool has_pca = false, has_full_pca = false;
-    std::vector<int32_t> needed_tris;     // source triangles the active equations read (decode keeps these)
     // growable device scratch, two sets so that the *_host entry points can overlap the copies of one
     // chunk with the kernels of the next (each set is used on its own stream)
     struct Workspace {
@@ -91,27 +90,27 @@ static void default_eq_src(sdfa_handle *h) {
 }
 
 static int upload_eq_src(sdfa_handle *h) {
+    h->has_pca = false;                       // the compact basis is laid out per equation source: re-pack on change
     if (h->dev.device < 0) return SDFA_OK;
     CUDA_TRY(cudaSetDevice(h->dev.device));
     CUDA_TRY(cudaMemcpy(h->dev.eq_src, h->eq_src_host.data(), h->eq_src_host.size() * 4, cudaMemcpyHostToDevice));
-    // which source triangles are read at all, and the same map into the compact decoded layout
-    const HostPlan &p = h->host;
-    std::vector<int32_t> needed;
-    for (int k : p.active_eq) if (h->eq_src_host[k] >= 0) needed.push_back(h->eq_src_host[k]);
-    std::sort(needed.begin(), needed.end());
-    needed.erase(std::unique(needed.begin(), needed.end()), needed.end());
-    std::vector<int32_t> compact(p.n_eq);
-    for (int k = 0; k < p.n_eq; ++k) {
-        int s = h->eq_src_host[k];
-        if (s >= 0) {
-            auto it = std::lower_bound(needed.begin(), needed.end(), s);
-            compact[k] = (it != needed.end() && *it == s) ? (int32_t)(it - needed.begin()) : -1;
-        } else compact[k] = s;
-    }
-    CUDA_TRY(cudaMemcpy(h->dev.eq_src_compact, compact.data(), compact.size() * 4, cudaMemcpyHostToDevice));
-    if (needed != h->needed_tris) { h->needed_tris = needed; h->has_pca = false; }   // basis rows must be re-packed
-    h->dev.n_needed = (int)needed.size();
     return SDFA_OK;
+}
+
+// compact float -> (source triangle * 9 + component) of the block-planar decode layout, -1 where nothing is decoded
+static std::vector<int32_t> compact_map(const sdfa_handle *h) {
+    const AssemblyPlan &ap = h->host.asmplan;
+    std::vector<int32_t> map((size_t)ap.compact_stride, -1);
+    for (size_t b = 0; b < ap.blocks.size(); ++b) {
+        const int ne = ap.blocks[b].eq_end - ap.blocks[b].eq_begin;
+        for (int e = 0; e < ne; ++e) {
+            const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
+            if (src < 0) continue;
+            for (int j = 0; j < 9; ++j)
+                map[(size_t)ap.blk_coff[b] + (size_t)(j / 3) * ap.blk_plane[b] + e * 3 + j % 3] = src * 9 + j;
+        }
+    }
+    return map;
 }
 
 static int upload_base(sdfa_handle *h) {
@@ -188,7 +187,11 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             d.asm_max_rows = ap.max_rows_per_block;
             std::vector<int32_t> tmp(p.n_eq, 0);
             if ((r = upload_mut(h, tmp, &d.eq_src))) return r;
-            if ((r = upload_mut(h, tmp, &d.eq_src_compact))) return r;
+            if ((r = upload(h, ap.blk_coff, &d.asm_coff))) return r;
+            if ((r = upload(h, ap.blk_plane, &d.asm_plane))) return r;
+            d.compact_stride = ap.compact_stride;
+            d.asm_max_plane = 0;
+            for (int pl : ap.blk_plane) d.asm_max_plane = std::max(d.asm_max_plane, pl);
             if ((r = upload(h, p.prog.bytes, &d.prog))) return r;
             if ((r = upload(h, p.prog.stage_off, &d.stage_off))) return r;
             if ((r = upload(h, p.prog.io_desc, &d.io_desc))) return r;
@@ -315,12 +318,12 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
 }
 
 static int reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *dgrad_dev, long long stride,
-                            const int32_t *eq_src, int mode, int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
+                            bool staged, int mode, int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
     int rc;
     const size_t n_tiles = ((size_t)n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
     if ((rc = grow(&w.rhs, &w.rhs_cap, n_tiles * h->dev.n_free * SLOT_WORDS))) return rc;
     if ((rc = time_mark(h, 1, s))) return rc;
-    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, eq_src, n_frames, mode, w.rhs, s));
+    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, staged, n_frames, mode, w.rhs, s));
     if ((rc = time_mark(h, 2, s))) return rc;
     CUDA_TRY(launch_solve(h->dev, w.rhs, n_frames, s));
     if ((rc = time_mark(h, 3, s))) return rc;
@@ -335,7 +338,7 @@ int sdfa_reconstruct_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad
     if ((rc = need_device(h))) return rc;
     if (n_frames < 0 || (n_frames > 0 && (!dgrad_dev || !out_dev))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_dev: bad arguments");
     long long stride = dgrad_stride ? dgrad_stride : (long long)h->n_src_tris * 9;
-    return reconstruct_core(h, h->ws[0], dgrad_dev, stride, h->dev.eq_src, ASM_DGRAD, n_frames, out_dev, (cudaStream_t)stream, false);
+    return reconstruct_core(h, h->ws[0], dgrad_dev, stride, false, ASM_DGRAD, n_frames, out_dev, (cudaStream_t)stream, false);
 }
 
 // Frames per chunk of the host-buffer entry points: copies of chunk i overlap the kernels of chunk i+1.
@@ -359,7 +362,7 @@ int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames,
         if ((rc = grow(&w.io_in, &w.io_in_cap, (size_t)HOST_CHUNK * row_in))) return rc;
         if ((rc = grow(&w.io_out, &w.io_out_cap, (size_t)HOST_CHUNK * row_out))) return rc;
         CUDA_TRY(cudaMemcpyAsync(w.io_in, dgrad_host + (size_t)f0 * row_in, (size_t)nf * row_in * 4, cudaMemcpyHostToDevice, w.stream));
-        if ((rc = reconstruct_core(h, w, w.io_in, (long long)row_in, h->dev.eq_src, ASM_DGRAD, nf, w.io_out, w.stream, false))) return rc;
+        if ((rc = reconstruct_core(h, w, w.io_in, (long long)row_in, false, ASM_DGRAD, nf, w.io_out, w.stream, false))) return rc;
         CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)f0 * row_out, w.io_out, (size_t)nf * row_out * 4, cudaMemcpyDeviceToHost, w.stream));
     }
     for (auto &w : h->ws) if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
@@ -380,7 +383,7 @@ static int single_frame(sdfa_handle *h, const double *in, long long len, int mod
     if ((rc = grow(&w.io_in, &w.io_in_cap, (size_t)len))) return rc;
     if ((rc = grow(&w.io_out, &w.io_out_cap, (size_t)p.n_verts * 3))) return rc;
     CUDA_TRY(cudaMemcpyAsync(w.io_in, f32.data(), (size_t)len * 4, cudaMemcpyHostToDevice, 0));
-    if ((rc = reconstruct_core(h, w, w.io_in, len, h->dev.eq_src, mode, 1, w.io_out, 0, false))) return rc;
+    if ((rc = reconstruct_core(h, w, w.io_in, len, false, mode, 1, w.io_out, 0, false))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_host, w.io_out, (size_t)p.n_verts * 12, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
     return SDFA_OK;
@@ -423,43 +426,46 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
         return fail(SDFA_ERR_ARG, "sdfa_set_pca: bad arguments");
     DevicePlan &d = h->dev;
     const int nt = h->n_src_tris;
-    auto pack = [&](const float *W, const float *m, int per, int K, float **dw, float **dm, bool full) -> int {
-        const std::vector<int32_t> &need = h->needed_tris;
-        size_t ntri = full ? (size_t)nt : need.size();
-        std::vector<float> w(ntri * per * K), mm(ntri * per);
-        for (size_t t = 0; t < ntri; ++t) {
-            size_t src = full ? t : (size_t)need[t];
-            std::memcpy(&w[t * per * K], &W[src * per * K], sizeof(float) * per * K);
-            std::memcpy(&mm[t * per], &m[src * per], sizeof(float) * per);
-        }
+    auto pack_full = [&](const float *W, const float *m, int per, int K, float **dw, float **dm) -> int {
+        std::vector<float> w(W, W + (size_t)nt * per * K), mm(m, m + (size_t)nt * per);
         int r;
         if ((r = upload_mut(h, w, dw))) return r;
         return upload_mut(h, mm, dm);
     };
     d.k_scale = k_scale; d.k_rotat = k_rotat;
-    if ((rc = pack(compT_scale, means_scale, 6, k_scale, &d.w_scale, &d.m_scale, false))) return rc;
-    if ((rc = pack(compT_rotat, means_rotat, 3, k_rotat, &d.w_rotat, &d.m_rotat, false))) return rc;
-    if ((rc = pack(compT_scale, means_scale, 6, k_scale, &d.wfull_scale, &d.mfull_scale, true))) return rc;
-    if ((rc = pack(compT_rotat, means_rotat, 3, k_rotat, &d.wfull_rotat, &d.mfull_rotat, true))) return rc;
-    // tensor-core path: compact rows, split into TF32 hi/lo and laid out as shared-memory tile images
+    if ((rc = pack_full(compT_scale, means_scale, 6, k_scale, &d.wfull_scale, &d.mfull_scale))) return rc;
+    if ((rc = pack_full(compT_rotat, means_rotat, 3, k_rotat, &d.wfull_rotat, &d.mfull_rotat))) return rc;
+    // tensor-core path: one GEMM row per float of the block-planar compact layout (planes 0,1 from the
+    // scale basis, plane 2 from the rotation basis), split into TF32 hi/lo and stored as tile images
     {
-        const std::vector<int32_t> &need = h->needed_tris;
-        auto build = [&](const float *W, const float *m, int per, int col0, int K, float **dw, float **db, int32_t **doff, int *mt) -> int {
-            std::vector<float> w(need.size() * per * K), mm(need.size() * per), img, bias;
-            std::vector<int32_t> off;
-            for (size_t t = 0; t < need.size(); ++t) {
-                std::memcpy(&w[t * per * K], &W[(size_t)need[t] * per * K], sizeof(float) * per * K);
-                std::memcpy(&mm[t * per], &m[(size_t)need[t] * per], sizeof(float) * per);
-            }
-            tc_build_basis(w.data(), mm.data(), (int)need.size(), per, col0, K, img, bias, off);
+        const AssemblyPlan &ap = h->host.asmplan;
+        std::vector<int32_t> src_s, off_s, src_r, off_r;
+        for (size_t b = 0; b < ap.blocks.size(); ++b) {
+            const int ne = ap.blocks[b].eq_end - ap.blocks[b].eq_begin;
+            for (int pl = 0; pl < 3; ++pl)
+                for (int e = 0; e < ne; ++e) {
+                    const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
+                    if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
+                    for (int j = 0; j < 3; ++j) {
+                        const int32_t off = ap.blk_coff[b] + pl * ap.blk_plane[b] + e * 3 + j;
+                        if (pl < 2) { src_s.push_back(src < 0 ? -1 : src * 6 + pl * 3 + j); off_s.push_back(off); }
+                        else { src_r.push_back(src < 0 ? -1 : src * 3 + j); off_r.push_back(off); }
+                    }
+                }
+        }
+        auto build = [&](const float *W, const float *m, int K, const std::vector<int32_t> &src, const std::vector<int32_t> &off,
+                         float **dw, float **db, int32_t **doff, int *mt) -> int {
+            std::vector<float> img, bias;
+            std::vector<int32_t> o;
+            tc_build_basis(W, m, K, src, off, img, bias, o);
             *mt = (int)(bias.size() / 128);
             int r;
             if ((r = upload_mut(h, img, dw))) return r;
             if ((r = upload_mut(h, bias, db))) return r;
-            return upload_mut(h, off, doff);
+            return upload_mut(h, o, doff);
         };
-        if ((rc = build(compT_scale, means_scale, 6, 0, k_scale, &d.tc_w_scale, &d.tc_b_scale, &d.tc_o_scale, &d.tc_mt_scale))) return rc;
-        if ((rc = build(compT_rotat, means_rotat, 3, 6, k_rotat, &d.tc_w_rotat, &d.tc_b_rotat, &d.tc_o_rotat, &d.tc_mt_rotat))) return rc;
+        if ((rc = build(compT_scale, means_scale, k_scale, src_s, off_s, &d.tc_w_scale, &d.tc_b_scale, &d.tc_o_scale, &d.tc_mt_scale))) return rc;
+        if ((rc = build(compT_rotat, means_rotat, k_rotat, src_r, off_r, &d.tc_w_rotat, &d.tc_b_rotat, &d.tc_o_rotat, &d.tc_mt_rotat))) return rc;
     }
     h->has_pca = h->has_full_pca = true;
     return SDFA_OK;
@@ -468,17 +474,13 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
 static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *cs_dev, const float *cr_dev,
                                    int n_frames, float *out_dev, cudaStream_t s) {
     int rc;
-    const long long stride = (long long)h->dev.n_needed * 9;
+    const long long stride = h->dev.compact_stride;
     if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, (size_t)n_frames * stride))) return rc;
     if ((rc = time_mark(h, 0, s))) return rc;
-    if (std::getenv("SDFA_DECODE_SIMT")) {           // debugging aid: the fp32 CUDA-core decode kernel
-        CUDA_TRY(launch_decode(h->dev, cs_dev, cr_dev, n_frames, false, w.dgrad_c, s));
-    } else {
-        if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
-        if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
-        CUDA_TRY(launch_decode_tc(h->dev, cs_dev, cr_dev, n_frames, w.ximg_s, w.ximg_r, w.dgrad_c, s));
-    }
-    return reconstruct_core(h, w, w.dgrad_c, stride, h->dev.eq_src_compact, ASM_DGRAD, n_frames, out_dev, s, true);
+    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
+    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
+    CUDA_TRY(launch_decode_tc(h->dev, cs_dev, cr_dev, n_frames, w.ximg_s, w.ximg_r, w.dgrad_c, s));
+    return reconstruct_core(h, w, w.dgrad_c, stride, true, ASM_DGRAD, n_frames, out_dev, s, true);
 }
 
 int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
@@ -521,7 +523,7 @@ int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const fl
     if ((rc = need_device(h))) return rc;
     if (!h->has_full_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_dgrad_dev: call sdfa_set_pca first");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
-    CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, true, dgrad_dev, (cudaStream_t)stream));
+    CUDA_TRY(launch_decode_full(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, dgrad_dev, (cudaStream_t)stream));
     return SDFA_OK;
 }
 
@@ -533,10 +535,6 @@ int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const 
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_compact_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
     if (n_frames == 0) return SDFA_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (std::getenv("SDFA_DECODE_SIMT")) {
-        CUDA_TRY(launch_decode(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, false, dgrad_compact_dev, s));
-        return SDFA_OK;
-    }
     sdfa_handle::Workspace &w = h->ws[0];
     if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
     if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
@@ -544,11 +542,11 @@ int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const 
     return SDFA_OK;
 }
 
-int sdfa_needed_tris(const sdfa_handle *h, int32_t *tris, int cap) {
+int sdfa_compact_layout(const sdfa_handle *h, int32_t *map, int cap) {
     if (!h) return -1;
-    const int n = (int)h->needed_tris.size();
-    if (tris) std::memcpy(tris, h->needed_tris.data(), sizeof(int32_t) * (size_t)std::min(n, cap));
-    return n;
+    const std::vector<int32_t> m = compact_map(h);
+    if (map) std::memcpy(map, m.data(), sizeof(int32_t) * (size_t)std::min((int)m.size(), cap));
+    return (int)m.size();
 }
 
 int sdfa_get_deform_grad_host(const float *, const float *, int, const uint32_t *, int, double, int, int, double *) {

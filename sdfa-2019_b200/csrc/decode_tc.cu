@@ -259,20 +259,21 @@ size_t tc_ximg_floats(int n_frames, int K) {
     return (size_t)((n_frames + TC_BN - 1) / TC_BN) * tc_kblocks(K) * 2 * TC_BN * TC_BK;
 }
 
-// Host: pre-split, pre-tiled basis images + per-row bias and output offset.  `rows` = n_tri * per_tri basis
-// rows of a [rows, K] row-major basis; output row r = (tri, s) lands at tri*9 + col0 + s.
-void tc_build_basis(const float *W, const float *mean, int n_tri, int per_tri, int col0, int K,
-                    std::vector<float> &img, std::vector<float> &bias, std::vector<int32_t> &off) {
-    const int rows = n_tri * per_tri, m_tiles = (rows + TC_BM - 1) / TC_BM, kbs = tc_kblocks(K);
+// Host: pre-split, pre-tiled basis images + per-row bias and output offset.
+void tc_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src,
+                    const std::vector<int32_t> &rows_off, std::vector<float> &img, std::vector<float> &bias,
+                    std::vector<int32_t> &off) {
+    const int rows = (int)rows_src.size(), m_tiles = (rows + TC_BM - 1) / TC_BM, kbs = tc_kblocks(K);
     img.assign((size_t)m_tiles * kbs * 2 * TC_BM * TC_BK, 0.f);
     bias.assign((size_t)m_tiles * TC_BM, 0.f);
     off.assign((size_t)m_tiles * TC_BM, -1);
     for (int r = 0; r < rows; ++r) {
-        const int m = r / TC_BM, rl = r % TC_BM;
-        bias[r] = mean[r];
-        off[r] = (r / per_tri) * 9 + col0 + r % per_tri;
+        const int m = r / TC_BM, rl = r % TC_BM, src = rows_src[r];
+        off[r] = rows_off[r];
+        if (src < 0) continue;
+        bias[r] = mean[src];
         for (int k = 0; k < K; ++k) {
-            const float v = W[(size_t)r * K + k], hi = tf32_hi(v);
+            const float v = W[(size_t)src * K + k], hi = tf32_hi(v);
             float *tile = &img[((size_t)m * kbs + k / TC_BK) * (2 * TC_BM * TC_BK)];
             tile[swz(rl, k % TC_BK)] = hi;
             tile[TC_BM * TC_BK + swz(rl, k % TC_BK)] = v - hi;
@@ -291,7 +292,7 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const long long stride = (long long)d.n_needed * 9;
+    const long long stride = d.compact_stride;
     for (int g = 0; g < 2; ++g) {
         const float *x = g == 0 ? coeff_scale : coeff_rotat;
         const int K = g == 0 ? d.k_scale : d.k_rotat, kbs = tc_kblocks(K);

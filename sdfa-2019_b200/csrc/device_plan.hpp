@@ -20,7 +20,8 @@ struct DevicePlan {
     const int32_t  *asm_row_ptr = nullptr;
     const uint16_t *asm_inc = nullptr;
     int32_t        *eq_src = nullptr;       // equation block -> source triangle (>=0), -1 identity, -2 zero block
-    int32_t        *eq_src_compact = nullptr; // same, into the compact decoded dgrad
+    const int32_t  *asm_coff = nullptr, *asm_plane = nullptr;   // block-planar compact dgrad layout
+    int compact_stride = 0, asm_max_plane = 0;
     // ---- solve (K3)
     const uint8_t  *prog = nullptr;         // 16-byte aligned stage stream
     const uint32_t *stage_off = nullptr;
@@ -32,9 +33,7 @@ struct DevicePlan {
     float          *xbase_hi = nullptr, *xbase_lo = nullptr;   // [n_free*3] permuted order
     float          *cnst_pos = nullptr;     // [n_cnsts*3]
     // ---- decode (K1)
-    int k_scale = 0, k_rotat = 0, n_needed = 0;   // n_needed = source triangles some active equation reads
-    float *w_scale = nullptr, *m_scale = nullptr;  // compact basis rows [n_needed*6, k_scale], means
-    float *w_rotat = nullptr, *m_rotat = nullptr;  // [n_needed*3, k_rotat]
+    int k_scale = 0, k_rotat = 0;
     float *wfull_scale = nullptr, *mfull_scale = nullptr, *wfull_rotat = nullptr, *mfull_rotat = nullptr;
     // tensor-core decode (decode_tc.cu): pre-split, pre-tiled basis images, bias and output offsets per row
     float *tc_w_scale = nullptr, *tc_w_rotat = nullptr, *tc_b_scale = nullptr, *tc_b_rotat = nullptr;
@@ -45,12 +44,13 @@ struct DevicePlan {
 enum AssemblyMode { ASM_DGRAD = 0, ASM_MATRIX = 1 };
 
 // All launchers are asynchronous on `stream` and return the cudaError_t of the launch.
-cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, const int32_t *eq_src,
+// staged = dgrad is the block-planar compact buffer (decode output); else any [frame][tri][9] layout
+cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream);
 cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream);
 cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream);
-cudaError_t launch_decode(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
-                          bool full_layout, float *dgrad_out, cudaStream_t stream);
+cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
+                               float *dgrad_out, cudaStream_t stream);
 cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, const uint32_t *tris, int n_tris,
                                double eps, int as_matrix, double *out, cudaStream_t stream);
 // decode_tc.cu
@@ -61,7 +61,10 @@ size_t solve_smem_bytes(int n_slots);
 void count_launch();
 long long launch_counter();
 
-void tc_build_basis(const float *W, const float *mean, int n_tri, int per_tri, int col0, int K,
-                    std::vector<float> &img, std::vector<float> &bias, std::vector<int32_t> &off);
+// rows_src[r] = row of the [*, K] basis W that GEMM row r reproduces (or -1: zero row), rows_off[r] = where
+// its output goes inside a frame's compact row
+void tc_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src,
+                    const std::vector<int32_t> &rows_off, std::vector<float> &img, std::vector<float> &bias,
+                    std::vector<int32_t> &off);
 
 }  // namespace sdfa

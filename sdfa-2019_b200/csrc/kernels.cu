@@ -19,6 +19,40 @@ static std::atomic<long long> g_launches{0};
 long long launch_counter() { return g_launches.load(); }
 void count_launch() { g_launches++; }
 
+// ---- mbarrier / TMA bulk-copy helpers (shared by K2 and K3) -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
 // =============================================================================================
 // K2: per-equation transform + A^T (T^T - I) assembly.
 //
@@ -40,10 +74,11 @@ struct AsmParams {
     const int32_t *row_perm, *row_ptr;
     const uint16_t *inc;
     const int32_t *eq_src;
+    const int32_t *blk_coff, *blk_plane;    // block-planar compact layout (staged variant)
     const float *dgrad;
     long long frame_stride;
     float *rhs;
-    int n_frames, n_free, mode, max_eq;
+    int n_frames, n_free, mode, max_eq, max_plane, max_rows;
 };
 
 __device__ __forceinline__ void corner_vec(const float *d, float a, float b, const float *u, float *g) {
@@ -67,10 +102,17 @@ __device__ __forceinline__ void corner_vec(const float *d, float a, float b, con
 constexpr int ASM_THREADS = 128;
 constexpr int TPAD = 33;          // transpose-buffer row stride (odd: conflict free both ways)
 
+// STAGED: the input is the decode kernel's block-planar compact buffer; the block's span of a frame is one
+// contiguous run, fetched two frames ahead by a TMA bulk copy into a double-buffered stage (mbarrier
+// completion), and read back conflict-free (three planes of stride-3 triples).
+// !STAGED: any [frame][triangle][9] layout (the reference's dgrad tensor): gathered with scalar loads.
+template <bool STAGED>
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
-    extern __shared__ float sh[];
-    float *g_sh = sh;                               // [max_eq][9]
-    float *t_sh = sh + P.max_eq * 9;                // [rows*3][33]
+    extern __shared__ __align__(128) float sh[];
+    float *stage = sh;                                              // [2][3*max_plane] (STAGED only)
+    float *g_sh = sh + (STAGED ? 6 * P.max_plane : 0);              // [max_eq][9]
+    float *t_sh = g_sh + P.max_eq * 9;                              // [rows*3][33]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(t_sh + ((P.max_rows * 3 * TPAD + 3) & ~3));
     const int4 blk = P.blocks[blockIdx.x];
     const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
     const int tile = blockIdx.y;
@@ -92,8 +134,29 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
             for (int j = 0; j < 6; ++j) u_k[k][j] = __ldg(P.eq_u + (blk.x + e) * 6 + j);
         }
     }
+    int plane = 0;
+    uint32_t span_bytes = 0;
+    const float *span0 = nullptr;
+    if (STAGED) {
+        plane = P.blk_plane[blockIdx.x];
+        span_bytes = 3u * (uint32_t)plane * 4u;
+        span0 = P.dgrad + (long long)frame0 * P.frame_stride + P.blk_coff[blockIdx.x];
+        if (threadIdx.x == 0) {
+            mbar_init(smem_u32(&bars[0]), 1);
+            mbar_init(smem_u32(&bars[1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_async_smem();
+            for (int f = 0; f < 2 && f < nvalid; ++f) {
+                mbar_arrive_expect_tx(smem_u32(&bars[f]), span_bytes);
+                tma_bulk_g2s(smem_u32(stage + f * 3 * P.max_plane), span0 + (long long)f * P.frame_stride, span_bytes, smem_u32(&bars[f]));
+            }
+        }
+        __syncthreads();
+    }
     for (int f = 0; f < nvalid; ++f) {
         const float *row = P.dgrad + (long long)(frame0 + f) * P.frame_stride;
+        const float *st = stage + (f & 1) * 3 * P.max_plane;
+        if (STAGED) mbar_wait(smem_u32(&bars[f & 1]), (uint32_t)(f >> 1) & 1u);
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int e = threadIdx.x + k * ASM_THREADS;
@@ -103,8 +166,13 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
             float g2[3], g3[3];
             if (src >= 0) {
                 float d[9];
+                if (STAGED) {
 #pragma unroll
-                for (int j = 0; j < 9; ++j) d[j] = __ldg(row + (long long)src * 9 + j);
+                    for (int j = 0; j < 9; ++j) d[j] = st[(j / 3) * plane + e * 3 + (j % 3)];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) d[j] = __ldg(row + (long long)src * 9 + j);
+                }
                 if (P.mode == ASM_DGRAD) {
                     const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
                     float a = 0.f, b = 0.f;
@@ -143,6 +211,12 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
             for (int c = 0; c < 3; ++c) { g[c] = -(g2[c] + g3[c]); g[3 + c] = g2[c]; g[6 + c] = g3[c]; }
         }
         __syncthreads();
+        if (STAGED && threadIdx.x == 0 && f + 2 < nvalid) {          // this stage is free again: prefetch frame f+2
+            fence_async_smem();
+            mbar_arrive_expect_tx(smem_u32(&bars[f & 1]), span_bytes);
+            tma_bulk_g2s(smem_u32(stage + (f & 1) * 3 * P.max_plane), span0 + (long long)(f + 2) * P.frame_stride, span_bytes,
+                         smem_u32(&bars[f & 1]));
+        }
         for (int r = threadIdx.x; r < n_rows; r += ASM_THREADS) {
             const int gr = blk.z + r;
             const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
@@ -166,23 +240,26 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     }
 }
 
-static size_t asm_smem_bytes(const DevicePlan &d) {
-    return ((size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * TPAD) * sizeof(float);
+static size_t asm_smem_bytes(const DevicePlan &d, bool staged) {
+    size_t fl = (size_t)d.asm_max_eq * 9 + (((size_t)d.asm_max_rows * 3 * TPAD + 3) & ~(size_t)3);
+    if (staged) fl += 6 * (size_t)d.asm_max_plane;
+    return fl * sizeof(float) + 16;
 }
 
-cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, const int32_t *eq_src,
+cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    AsmParams P{d.asm_blocks, d.asm_eq_id, d.asm_eq_u, d.asm_row_perm, d.asm_row_ptr, d.asm_inc, eq_src,
-                dgrad, frame_stride, rhs, n_frames, d.n_free, mode, d.asm_max_eq};
-    const size_t smem = asm_smem_bytes(d);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    AsmParams P{d.asm_blocks, d.asm_eq_id, d.asm_eq_u, d.asm_row_perm, d.asm_row_ptr, d.asm_inc, d.eq_src,
+                d.asm_coff, d.asm_plane, dgrad, frame_stride, rhs, n_frames, d.n_free, mode, d.asm_max_eq,
+                d.asm_max_plane, d.asm_max_rows};
+    const size_t smem = asm_smem_bytes(d, staged);
+    cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
     dim3 grid((unsigned)d.n_asm_blocks, (unsigned)n_tiles);
-    k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
+    if (staged) k_assemble<true><<<grid, ASM_THREADS, smem, stream>>>(P);
+    else k_assemble<false><<<grid, ASM_THREADS, smem, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
 }
@@ -211,37 +288,6 @@ struct SolveParams {
     int n_free, n_tiles;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 
 __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state_lane) {
@@ -500,7 +546,7 @@ cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frame
 }
 
 // =============================================================================================
-// K1 (first version, exact fp32 FMA on CUDA cores): dgrad[f][tri][0..5] = coeff_s[f] . Ws[tri*6+s] + ms,
+// Full-layout decode (exact fp32 FMA on CUDA cores; not on the hot path -- the path's K1 is decode_tc.cu): dgrad[f][tri][0..5] = coeff_s[f] . Ws[tri*6+s] + ms,
 // dgrad[f][tri][6..8] = coeff_r[f] . Wr[tri*3+r] + mr  -- F.linear x2 + the scale/rotation interleave.
 // 64 frames x 64 outputs per CTA, 4x4 per thread, K streamed through shared memory in chunks of 16.
 constexpr int DEC_TF = 64, DEC_TJ = 64, DEC_TK = 16;
@@ -547,20 +593,18 @@ __global__ void __launch_bounds__(256) k_decode(const float *__restrict__ coeff,
     }
 }
 
-cudaError_t launch_decode(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
-                          bool full_layout, float *dgrad_out, cudaStream_t stream) {
+cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
+                               float *dgrad_out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    const int ntri = full_layout ? d.n_tris : d.n_needed;
-    const float *ws = full_layout ? d.wfull_scale : d.w_scale, *ms = full_layout ? d.mfull_scale : d.m_scale;
-    const float *wr = full_layout ? d.wfull_rotat : d.w_rotat, *mr = full_layout ? d.mfull_rotat : d.m_rotat;
+    const int ntri = d.n_tris;
     const long long stride = (long long)ntri * 9;
     dim3 gs((unsigned)((ntri * 6 + DEC_TJ - 1) / DEC_TJ), (unsigned)((n_frames + DEC_TF - 1) / DEC_TF));
-    k_decode<<<gs, 256, 0, stream>>>(coeff_scale, d.k_scale, ws, ms, ntri * 6, 6, 0, n_frames, dgrad_out, stride);
+    k_decode<<<gs, 256, 0, stream>>>(coeff_scale, d.k_scale, d.wfull_scale, d.mfull_scale, ntri * 6, 6, 0, n_frames, dgrad_out, stride);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 gr((unsigned)((ntri * 3 + DEC_TJ - 1) / DEC_TJ), (unsigned)((n_frames + DEC_TF - 1) / DEC_TF));
-    k_decode<<<gr, 256, 0, stream>>>(coeff_rotat, d.k_rotat, wr, mr, ntri * 3, 3, 6, n_frames, dgrad_out, stride);
+    k_decode<<<gr, 256, 0, stream>>>(coeff_rotat, d.k_rotat, d.wfull_rotat, d.mfull_rotat, ntri * 3, 3, 6, n_frames, dgrad_out, stride);
     g_launches++;
     return cudaGetLastError();
 }

@@ -94,6 +94,11 @@ struct AssemblyPlan {
     std::vector<int32_t>  row_ptr;      // size rows + 1 per block, concatenated with global offsets
     std::vector<uint16_t> inc;          // incidence: local_eq * 3 + corner
     int max_eq_per_block = 0, max_rows_per_block = 0;
+    // Block-planar compact dgrad (what the decode kernel writes and the staged assembly reads with one TMA
+    // bulk copy per block and frame): block b owns floats [blk_coff[b], +3*blk_plane[b]) of a frame's compact
+    // row = three planes [eq][s00,s01,s02], [eq][s11,s12,s22], [eq][r01,r02,r12], each padded to 16 bytes.
+    std::vector<int32_t> blk_coff, blk_plane;
+    int compact_stride = 0;             // floats per frame
 };
 
 // ------------------------------------------------------------------------------------------

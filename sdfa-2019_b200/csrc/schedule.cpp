@@ -644,6 +644,12 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
         ap.max_rows_per_block = std::max(ap.max_rows_per_block, blk.row_end - blk.row_begin);
         ap.blocks.push_back(blk);
     }
+    for (auto &blk : ap.blocks) {
+        const int plane = (3 * (blk.eq_end - blk.eq_begin) + 3) / 4 * 4;
+        ap.blk_coff.push_back(ap.compact_stride);
+        ap.blk_plane.push_back(plane);
+        ap.compact_stride += 3 * plane;
+    }
 }
 
 }  // namespace sdfa

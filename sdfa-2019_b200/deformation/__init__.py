@@ -227,20 +227,20 @@ class Reconstructor:
                                         ptr(out.data_ptr()), ptr(s)))
         return out
 
-    def needed_tris(self):
-        """Sorted source triangles the reconstruction reads (the rows kept of the PCA basis)."""
-        n = lib.sdfa_needed_tris(self._h, None, 0)
+    def compact_layout(self):
+        """Map of the internal block-planar compact dgrad: entry i = source_triangle*9 + component, -1 = padding."""
+        n = lib.sdfa_compact_layout(self._h, None, 0)
         out = np.empty(n, dtype=np.int32)
-        lib.sdfa_needed_tris(self._h, ptr(out), n)
+        lib.sdfa_compact_layout(self._h, ptr(out), n)
         return out
 
     def decode_compact(self, coeff_scale, coeff_rotat, stream=None):
-        """Coefficients -> dgrad of needed_tris() only, [N, n_needed, 9] (torch.cuda; tcgen05 kernel)."""
+        """Coefficients -> compact dgrad [N, stride] as laid out by compact_layout() (torch.cuda; tcgen05 kernel)."""
         import torch
         a = coeff_scale.contiguous().reshape(-1, self.k_scale)
         b = coeff_rotat.contiguous().reshape(-1, self.k_rotat)
-        n_needed = lib.sdfa_needed_tris(self._h, None, 0)
-        out = torch.empty((a.shape[0], n_needed, 9), dtype=torch.float32, device=a.device)
+        stride = lib.sdfa_compact_layout(self._h, None, 0)
+        out = torch.zeros((a.shape[0], stride), dtype=torch.float32, device=a.device)
         s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
         check(lib.sdfa_decode_compact_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), a.shape[0],
                                           ptr(out.data_ptr()), ptr(s)))
