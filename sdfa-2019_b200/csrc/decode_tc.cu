@@ -33,7 +33,8 @@ constexpr int TC_BK = 32;           // floats per K-block = one 128-byte swizzle
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB: one operand half (hi or lo)
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // W_hi, W_lo, X_hi, X_lo
-constexpr int TC_THREADS = 192;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each drains half of the columns
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue warps
 constexpr int TC_TMEM_COLS = 256;   // two 128-column fp32 accumulators
 
 // float index of element (row r, k) inside a [rows x 32] K-major SWIZZLE_128B tile image:
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
         const int lane_grp = warp & 3;                              // TMEM lanes 32*lane_grp .. +31 belong to this warp
+        const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (frames) it drains
         uint32_t tc = 0;
         for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
             const int m = tile % P.m_tiles, n = tile / P.m_tiles;
@@ -208,18 +210,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
             const float b = P.bias[row];
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BN + col_half * (TC_BN / 2);
 #pragma unroll 1
-            for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+            for (int chunk = 0; chunk < TC_BN / 64; ++chunk) {
                 uint32_t v[32];
                 tmem_ld32(taddr + chunk * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int f0 = n * TC_BN + chunk * 32;
+                const int f0 = n * TC_BN + col_half * (TC_BN / 2) + chunk * 32;
                 if (off >= 0) {
                     float *dst = P.out + (long long)f0 * P.out_stride + off;
+                    if (f0 + 32 <= P.n_frames) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (f0 + c < P.n_frames) dst[(long long)c * P.out_stride] = __uint_as_float(v[c]) + b;
+                        for (int c = 0; c < 32; ++c) { *dst = __uint_as_float(v[c]) + b; dst += P.out_stride; }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) { if (f0 + c < P.n_frames) *dst = __uint_as_float(v[c]) + b; dst += P.out_stride; }
+                    }
                 }
             }
             tc_fence_before();

@@ -99,7 +99,7 @@ __device__ __forceinline__ void corner_vec(const float *d, float a, float b, con
     g[2] = t2 + a * p2 + b * q2;
 }
 
-constexpr int ASM_THREADS = 128;
+constexpr int ASM_THREADS = 256;
 constexpr int TPAD = 33;          // transpose-buffer row stride (odd: conflict free both ways)
 
 // STAGED: the input is the decode kernel's block-planar compact buffer; the block's span of a frame is one
