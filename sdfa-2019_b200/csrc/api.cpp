@@ -211,6 +211,10 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             if ((r = upload_mut(h, cz, &d.cnst_pos))) return r;
             if ((r = upload_base(h))) return r;
             if ((r = upload_eq_src(h))) return r;
+            if (std::getenv("SDFA_SOLVE_PROFILE")) {
+                std::vector<long long> zero((size_t)h->dev.sm_count * 4 * 8, 0);
+                if ((r = upload_mut(h, zero, &d.solve_prof))) return r;
+            }
             return SDFA_OK;
         };
         rc = up();
@@ -604,6 +608,11 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
         std::vector<int> b;
         for (auto &x : p.asmplan.blocks) { b.push_back(x.eq_begin); b.push_back(x.eq_end); b.push_back(x.row_begin); b.push_back(x.row_end); }
         return give(b, dst, cap);
+    }
+    if (w == "solve_prof") {
+        std::vector<long long> v((size_t)h->dev.sm_count * 4 * 8, 0);
+        if (h->dev.solve_prof) cudaMemcpy(v.data(), h->dev.solve_prof, v.size() * 8, cudaMemcpyDeviceToHost);
+        return give(v, dst, cap);
     }
     if (w == "stats") {
         std::vector<long long> s = {p.prog.n_slots, p.prog.n_phases_fwd, p.prog.n_steps_fwd, p.prog.n_steps_bwd,

@@ -28,6 +28,7 @@ struct DevicePlan {
     const IoDesc   *io_desc = nullptr;
     const IoPhase  *io_phase = nullptr;
     int n_stages = 0, n_slots = 0, n_phases_fwd = 0, n_phases_bwd = 0;
+    long long *solve_prof = nullptr;        // optional cycle counters [sm_count*4][8] (SDFA_SOLVE_PROFILE=1)
     // ---- output (K5)
     const int32_t  *vert_row = nullptr;     // vertex -> permuted row (>= 0) or -1 - constraint index
     float          *xbase_hi = nullptr, *xbase_lo = nullptr;   // [n_free*3] permuted order

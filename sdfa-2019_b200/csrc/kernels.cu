@@ -286,26 +286,45 @@ struct SolveParams {
     int n_stages, n_slots, n_phases_fwd, n_phases_bwd;
     float *scratch;                             // [n_tiles][n_free][3][32]: rhs in, x out (in place)
     int n_free, n_tiles;
+    long long *prof;                            // optional [grid][8] cycle counters of consumer warp 0 (NULL = off)
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 
+// One task on one warp (lane = frame).  Entry lists are padded by the host to whole batches (4 sources of
+// kind B, 4 packed pairs of kind A), and the next batch's entries are fetched while the current batch's
+// state values are in flight, so a batch costs one shared-memory round trip instead of two.
 __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state_lane) {
     const uint4 th = *reinterpret_cast<const uint4 *>(task);       // TaskHeader
     const int n = (int)(th.w & 0xFFFFFFu);
+    const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);
     if (th.w & TASK_GROUP) {
         // kind B: up to three target rows share the sources -> 9 FMAs per 3 shared-memory value loads
-        const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);
         float a[3][3] = {};
-#pragma unroll 4
-        for (int k = 0; k < n; ++k) {
-            const uint4 p = e[k];
-            const float *s = reinterpret_cast<const float *>(state_lane + p.x);
-            const float v0 = s[0], v1 = s[COORD_STRIDE], v2 = s[2 * COORD_STRIDE];
-            const float c0 = __uint_as_float(p.y), c1 = __uint_as_float(p.z), c2 = __uint_as_float(p.w);
-            a[0][0] = fmaf(c0, v0, a[0][0]); a[0][1] = fmaf(c0, v1, a[0][1]); a[0][2] = fmaf(c0, v2, a[0][2]);
-            a[1][0] = fmaf(c1, v0, a[1][0]); a[1][1] = fmaf(c1, v1, a[1][1]); a[1][2] = fmaf(c1, v2, a[1][2]);
-            a[2][0] = fmaf(c2, v0, a[2][0]); a[2][1] = fmaf(c2, v1, a[2][1]); a[2][2] = fmaf(c2, v2, a[2][2]);
+        uint4 p[4] = {e[0], e[1], e[2], e[3]};
+        for (int k = 0; k < n; k += 4) {
+            float v[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float *s = reinterpret_cast<const float *>(state_lane + p[j].x);
+                v[j][0] = s[0]; v[j][1] = s[COORD_STRIDE]; v[j][2] = s[2 * COORD_STRIDE];
+            }
+            uint4 q[4];
+            const int kn = (k + 4 < n) ? k + 4 : k;                 // last batch re-reads itself (harmless)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = e[kn + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float c0 = __uint_as_float(p[j].y), c1 = __uint_as_float(p[j].z), c2 = __uint_as_float(p[j].w);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    a[0][d] = fmaf(c0, v[j][d], a[0][d]);
+                    a[1][d] = fmaf(c1, v[j][d], a[1][d]);
+                    a[2][d] = fmaf(c2, v[j][d], a[2][d]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[j] = q[j];
         }
         const uint32_t tg[3] = {th.x, th.y, th.z};
 #pragma unroll
@@ -320,23 +339,38 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
         }
         return;
     }
-    const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);   // kind A: two entries per uint4
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < n; k += 2) {
-        const uint4 p = e[k >> 1];
-        const float c0 = __uint_as_float(p.x), c1 = __uint_as_float(p.z);
-        const float *s0 = reinterpret_cast<const float *>(state_lane + p.y);
-        const float *s1 = reinterpret_cast<const float *>(state_lane + p.w);
-        a0 = fmaf(c0, s0[0], a0); a1 = fmaf(c0, s0[COORD_STRIDE], a1); a2 = fmaf(c0, s0[2 * COORD_STRIDE], a2);
-        b0 = fmaf(c1, s1[0], b0); b1 = fmaf(c1, s1[COORD_STRIDE], b1); b2 = fmaf(c1, s1[2 * COORD_STRIDE], b2);
+    // kind A: one target row, two entries {coeff, src} per uint4, 4 uint4 (8 entries) per batch
+    float a[3] = {}, b[3] = {};
+    uint4 p[4] = {e[0], e[1], e[2], e[3]};
+    const int nq = n >> 1;                                          // number of uint4 pairs, multiple of 4
+    for (int k = 0; k < nq; k += 4) {
+        float v[4][2][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *s0 = reinterpret_cast<const float *>(state_lane + p[j].y);
+            const float *s1 = reinterpret_cast<const float *>(state_lane + p[j].w);
+            v[j][0][0] = s0[0]; v[j][0][1] = s0[COORD_STRIDE]; v[j][0][2] = s0[2 * COORD_STRIDE];
+            v[j][1][0] = s1[0]; v[j][1][1] = s1[COORD_STRIDE]; v[j][1][2] = s1[2 * COORD_STRIDE];
+        }
+        uint4 q[4];
+        const int kn = (k + 4 < nq) ? k + 4 : k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = e[kn + j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float c0 = __uint_as_float(p[j].x), c1 = __uint_as_float(p[j].z);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { a[d] = fmaf(c0, v[j][0][d], a[d]); b[d] = fmaf(c1, v[j][1][d], b[d]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = q[j];
     }
     float *t = reinterpret_cast<float *>(state_lane + th.x);
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     if (!(th.w & TASK_OVERWRITE)) { v0 = t[0]; v1 = t[COORD_STRIDE]; v2 = t[2 * COORD_STRIDE]; }
-    t[0] = v0 - (a0 + b0);
-    t[COORD_STRIDE] = v1 - (a1 + b1);
-    t[2 * COORD_STRIDE] = v2 - (a2 + b2);
+    t[0] = v0 - (a[0] + b[0]);
+    t[COORD_STRIDE] = v1 - (a[1] + b[1]);
+    t[2 * COORD_STRIDE] = v2 - (a[2] + b[2]);
 }
 
 // shared memory map: [ring RING*STAGE_BYTES][barriers 8*(2*RING+4)][pad to 128][state n_slots*384]
@@ -431,10 +465,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
     uint8_t *state_lane = state + lane * 4;
     uint32_t it = 0, g = 0;
     (void)n_phases;
+    const bool prof = P.prof != nullptr && cw == 0;
+    long long c_stage = 0, c_ld = 0, c_task = 0, c_bar = 0, c_t0 = prof ? clock64() : 0, c_a = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         for (int s = 0; s < P.n_stages; ++s, ++it) {
             const uint32_t slot = it % RING, phase = (it / RING) & 1u;
+            if (prof) c_a = clock64();
             mbar_wait(smem_u32(&bars[BAR_FULL + slot]), phase);
+            if (prof) c_stage += clock64() - c_a;
             const uint8_t *stage = ring + slot * STAGE_BYTES;
             const int n_ops = (int)reinterpret_cast<const uint32_t *>(stage)[0];
             uint32_t at = 16;
@@ -443,11 +481,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
                 const uint32_t type = hw.x & 0xFFFFu, flags = hw.x >> 16;
                 if (type == OP_ROWS) {
                     const uint32_t *table = reinterpret_cast<const uint32_t *>(stage + hw.z);
+                    if (prof) c_a = clock64();
                     for (uint32_t t = cw; t < hw.y; t += NCW) run_row_task(stage + table[t], state_lane);
+                    if (prof) { long long c_b = clock64(); c_task += c_b - c_a; c_a = c_b; }
                     at = hw.w;
                     if (flags & OPF_SYNC_AFTER) consumer_bar();
+                    if (prof) c_bar += clock64() - c_a;
                 } else if (type == OP_PHASE_BEGIN) {
+                    if (prof) c_a = clock64();
                     mbar_wait(smem_u32(&bars[BAR_LD + (g & 1u)]), (g >> 1) & 1u);
+                    if (prof) c_ld += clock64() - c_a;
                     at += 16;
                 } else {   // OP_PHASE_END: the level barrier before it has ordered all consumer writes
                     fence_async_smem();
@@ -460,6 +503,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars[BAR_EMPTY + slot]));
         }
+    }
+    if (prof && lane == 0) {
+        long long *o = P.prof + (long long)blockIdx.x * 8;
+        o[0] = clock64() - c_t0; o[1] = c_stage; o[2] = c_ld; o[3] = c_task; o[4] = c_bar;
     }
 }
 
@@ -484,7 +531,7 @@ cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cuda
     }
     const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
     SolveParams P{d.prog, d.stage_off, d.io_desc, d.io_phase, d.n_stages, d.n_slots, d.n_phases_fwd, d.n_phases_bwd,
-                  scratch, d.n_free, n_tiles};
+                  scratch, d.n_free, n_tiles, d.solve_prof};
     int grid = d.sm_count * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
     k_solve<<<grid, SOLVE_THREADS, smem, stream>>>(P);

@@ -170,7 +170,8 @@ void make_descs(std::vector<std::pair<int, int>> &rows_slots, std::vector<IoDesc
 // kind A: one target row, entries {coeff, src} packed two per 16 bytes.
 Blob blob_single(const Task &t) {
     Blob b;
-    const size_t n = t.entries.size(), ne = n + (n & 1);
+    // padded to a multiple of 8 entries (4 packed pairs) so the kernel's loop has no remainder iterations
+    const size_t n = t.entries.size(), ne = (n + 7) / 8 * 8;
     b.bytes.assign(sizeof(TaskHeader) + ne * sizeof(TaskEntry), 0);
     TaskHeader th{(uint32_t)t.target_slot * SLOT_BYTES, 0, 0, (uint32_t)ne | t.flags};
     std::memcpy(&b.bytes[0], &th, sizeof(th));
@@ -178,11 +179,11 @@ Blob blob_single(const Task &t) {
         TaskEntry e{t.entries[k].coeff, t.entries[k].src_byte_off * SLOT_BYTES};
         std::memcpy(&b.bytes[sizeof(TaskHeader) + k * sizeof(TaskEntry)], &e, sizeof(e));
     }
-    if (n & 1) {     // padding entry: coefficient 0 on the task's own first source (a live, finite slot)
+    for (size_t k = n; k < ne; ++k) {     // padding: coefficient 0 on the task's own first source (a live, finite slot)
         TaskEntry e{0.f, t.entries[0].src_byte_off * SLOT_BYTES};
-        std::memcpy(&b.bytes[sizeof(TaskHeader) + n * sizeof(TaskEntry)], &e, sizeof(e));
+        std::memcpy(&b.bytes[sizeof(TaskHeader) + k * sizeof(TaskEntry)], &e, sizeof(e));
     }
-    b.work = n;
+    b.work = ne;
     return b;
 }
 // kind B: up to three target rows that read (nearly) the same sources: one entry {src, c0, c1, c2} per
@@ -196,8 +197,9 @@ Blob blob_group(const std::vector<const Task *> &rows) {
             g.c[r] += e.coeff;
         }
     Blob b;
-    b.bytes.assign(sizeof(TaskHeader) + uni.size() * sizeof(GroupEntry), 0);
-    TaskHeader th{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)uni.size() | TASK_GROUP};
+    const size_t ne = (uni.size() + 3) / 4 * 4;        // padded to a multiple of 4 sources (zero coefficients)
+    b.bytes.assign(sizeof(TaskHeader) + ne * sizeof(GroupEntry), 0);
+    TaskHeader th{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)ne | TASK_GROUP};
     uint32_t *tg = &th.target_byte_off;
     for (size_t r = 0; r < rows.size(); ++r) {
         tg[r] = (uint32_t)rows[r]->target_slot * SLOT_BYTES;
@@ -206,7 +208,11 @@ Blob blob_group(const std::vector<const Task *> &rows) {
     std::memcpy(&b.bytes[0], &th, sizeof(th));
     size_t k = 0;
     for (auto &kv : uni) std::memcpy(&b.bytes[sizeof(TaskHeader) + (k++) * sizeof(GroupEntry)], &kv.second, sizeof(GroupEntry));
-    b.work = uni.size() * rows.size();
+    for (; k < ne; ++k) {
+        GroupEntry pad{uni.begin()->second.src_byte_off, {0.f, 0.f, 0.f}};
+        std::memcpy(&b.bytes[sizeof(TaskHeader) + k * sizeof(GroupEntry)], &pad, sizeof(pad));
+    }
+    b.work = ne * 3;
     return b;
 }
 

@@ -89,7 +89,7 @@ _DEBUG_DTYPES = {
     "l_val": np.float64, "m_colptr": np.int32, "m_rowidx": np.int32, "m_val": np.float64, "x_base": np.float64,
     "active_eq": np.int32, "tri_u": np.float64, "prog": np.uint8, "stage_off": np.uint32, "io_desc": np.uint32, "io_phase": np.uint32, "eq_src": np.int32,
     "asm_eq_id": np.int32, "asm_eq_u": np.float32, "asm_row_perm": np.int32, "asm_row_ptr": np.int32,
-    "asm_inc": np.uint16, "asm_blocks": np.int32, "stats": np.int64,
+    "asm_inc": np.uint16, "solve_prof": np.int64, "asm_blocks": np.int32, "stats": np.int64,
 }
 
 

@@ -131,6 +131,7 @@ def _parse_phases(rec):
                     n = int(nf & 0xFFFFFF)
                     assert off % 16 == 0
                     if nf & TASK_GROUP:                       # kind B: {src, c0, c1, c2} entries, up to 3 rows
+                        assert n % 4 == 0
                         ent = st[off + 16: off + 16 + 16 * n]
                         src = ent.view(np.uint32)[0::4]
                         assert (src % (4 * SLOT_WORDS) == 0).all()
@@ -144,7 +145,7 @@ def _parse_phases(rec):
                                           (src // 4 // SLOT_WORDS).astype(np.int64)))
                         continue
                     tgt = t0
-                    assert n % 2 == 0 and tgt % (4 * SLOT_WORDS) == 0
+                    assert n % 8 == 0 and tgt % (4 * SLOT_WORDS) == 0
                     ent = st[off + 16: off + 16 + 8 * n]
                     src = ent.view(np.uint32)[1::2]
                     assert (src % (4 * SLOT_WORDS) == 0).all()
