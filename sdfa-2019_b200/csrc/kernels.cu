@@ -301,20 +301,23 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
     if (th.w & TASK_GROUP) {
         // kind B: up to three target rows share the sources -> 9 FMAs per 3 shared-memory value loads
         float a[3][3] = {};
-        uint4 p[4] = {e[0], e[1], e[2], e[3]};
-        for (int k = 0; k < n; k += 4) {
-            float v[4][3];
+        constexpr int BB = TASK_BATCH_B;
+        uint4 p[BB];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < BB; ++j) p[j] = e[j];
+        for (int k = 0; k < n; k += BB) {
+            float v[BB][3];
+#pragma unroll
+            for (int j = 0; j < BB; ++j) {
                 const float *s = reinterpret_cast<const float *>(state_lane + p[j].x);
                 v[j][0] = s[0]; v[j][1] = s[COORD_STRIDE]; v[j][2] = s[2 * COORD_STRIDE];
             }
-            uint4 q[4];
-            const int kn = (k + 4 < n) ? k + 4 : k;                 // last batch re-reads itself (harmless)
+            uint4 q[BB];
+            const int kn = (k + BB < n) ? k + BB : k;               // last batch re-reads itself (harmless)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = e[kn + j];
+            for (int j = 0; j < BB; ++j) q[j] = e[kn + j];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < BB; ++j) {
                 const float c0 = __uint_as_float(p[j].y), c1 = __uint_as_float(p[j].z), c2 = __uint_as_float(p[j].w);
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
@@ -324,7 +327,7 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[j] = q[j];
+            for (int j = 0; j < BB; ++j) p[j] = q[j];
         }
         const uint32_t tg[3] = {th.x, th.y, th.z};
 #pragma unroll

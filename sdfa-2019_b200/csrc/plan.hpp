@@ -56,6 +56,7 @@ struct TaskHeader {
     uint32_t n_entries_flags;   // low 24 bits count, bit 24 = TASK_GROUP, bits 25.. = OVERWRITE per row
 };
 constexpr uint32_t TASK_GROUP = 1u << 24, TASK_OVERWRITE = 1u << 25;
+constexpr int TASK_BATCH_B = 4;      // kind-B entry lists are padded to a multiple of this many sources
 struct TaskEntry { float coeff; uint32_t src_byte_off; };
 struct GroupEntry { uint32_t src_byte_off; float c[3]; };
 

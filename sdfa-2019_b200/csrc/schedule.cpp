@@ -197,7 +197,7 @@ Blob blob_group(const std::vector<const Task *> &rows) {
             g.c[r] += e.coeff;
         }
     Blob b;
-    const size_t ne = (uni.size() + 3) / 4 * 4;        // padded to a multiple of 4 sources (zero coefficients)
+    const size_t ne = (uni.size() + TASK_BATCH_B - 1) / TASK_BATCH_B * TASK_BATCH_B;   // whole batches (zero coefficients)
     b.bytes.assign(sizeof(TaskHeader) + ne * sizeof(GroupEntry), 0);
     TaskHeader th{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)ne | TASK_GROUP};
     uint32_t *tg = &th.target_byte_off;
