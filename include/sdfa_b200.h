@@ -128,6 +128,12 @@ int sdfa_compact_layout(const sdfa_handle *h, int32_t *map, int cap);
 int sdfa_get_deform_grad_host(const float *verts_a, const float *verts_b, int n_verts, const uint32_t *tris,
                               int n_tris, double eps, int as_matrix, int device, double *out_host);
 
+/* Batched, device buffers: verts_a_dev [n_verts,3] (the template), verts_b_dev [n_frames,n_verts,3] float32,
+ * tris_dev [n_tris,3] uint32; out_dev [n_frames,n_tris,9] float32 -- the dtype datasets store
+ * (generate_dgrad, speech_anime/datasets/vocaset/preload.py:765-835).  Indices are not range-checked. */
+int sdfa_deform_grad_batch_dev(const float *verts_a_dev, const float *verts_b_dev, int n_verts, const uint32_t *tris_dev,
+                               int n_tris, int n_frames, double eps, int as_matrix, float *out_dev, void *stream);
+
 /* ---- measurement / introspection -------------------------------------------------------- */
 
 /* Kernel launches issued by this library since process start (for bench.py's gpu_launches). */

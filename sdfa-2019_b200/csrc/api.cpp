@@ -553,8 +553,40 @@ int sdfa_compact_layout(const sdfa_handle *h, int32_t *map, int cap) {
     return (int)m.size();
 }
 
-int sdfa_get_deform_grad_host(const float *, const float *, int, const uint32_t *, int, double, int, int, double *) {
-    return fail(SDFA_ERR_UNSUPPORTED, "sdfa_get_deform_grad_host: the inverse path (mesh -> dgrad) is not built yet");
+int sdfa_get_deform_grad_host(const float *verts_a, const float *verts_b, int n_verts, const uint32_t *tris, int n_tris,
+                              double eps, int as_matrix, int device, double *out_host) {
+    if (!verts_a || !verts_b || !tris || !out_host || n_verts <= 0 || n_tris <= 0)
+        return fail(SDFA_ERR_ARG, "sdfa_get_deform_grad_host: bad arguments");
+    for (int i = 0; i < n_tris * 3; ++i)
+        if (tris[i] >= (uint32_t)n_verts) return fail(SDFA_ERR_ARG, "sdfa_get_deform_grad_host: triangle index out of range");
+    if (device < 0) return fail(SDFA_ERR_CUDA, "sdfa_get_deform_grad_host: needs a CUDA device; this library has no CPU path");
+    CUDA_TRY(cudaSetDevice(device));
+    float *da = nullptr, *db = nullptr;
+    uint32_t *dt = nullptr;
+    double *dout = nullptr;
+    auto cleanup = [&]() { cudaFree(da); cudaFree(db); cudaFree(dt); cudaFree(dout); };
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&da, (size_t)n_verts * 12)) || (e = cudaMalloc((void **)&db, (size_t)n_verts * 12)) ||
+        (e = cudaMalloc((void **)&dt, (size_t)n_tris * 12)) || (e = cudaMalloc((void **)&dout, (size_t)n_tris * 72)) ||
+        (e = cudaMemcpy(da, verts_a, (size_t)n_verts * 12, cudaMemcpyHostToDevice)) ||
+        (e = cudaMemcpy(db, verts_b, (size_t)n_verts * 12, cudaMemcpyHostToDevice)) ||
+        (e = cudaMemcpy(dt, tris, (size_t)n_tris * 12, cudaMemcpyHostToDevice)) ||
+        (e = launch_deform_grad(da, db, 0, dt, n_tris, 1, eps, as_matrix, dout, true, 0)) ||
+        (e = cudaMemcpy(out_host, dout, (size_t)n_tris * 72, cudaMemcpyDeviceToHost))) {
+        cleanup();
+        return fail(SDFA_ERR_CUDA, std::string("sdfa_get_deform_grad_host: ") + cudaGetErrorString(e));
+    }
+    cleanup();
+    return SDFA_OK;
+}
+
+int sdfa_deform_grad_batch_dev(const float *verts_a_dev, const float *verts_b_dev, int n_verts, const uint32_t *tris_dev,
+                               int n_tris, int n_frames, double eps, int as_matrix, float *out_dev, void *stream) {
+    if (!verts_a_dev || !verts_b_dev || !tris_dev || !out_dev || n_verts <= 0 || n_tris <= 0 || n_frames < 0)
+        return fail(SDFA_ERR_ARG, "sdfa_deform_grad_batch_dev: bad arguments");
+    CUDA_TRY(launch_deform_grad(verts_a_dev, verts_b_dev, (long long)n_verts * 3, tris_dev, n_tris, n_frames, eps, as_matrix,
+                                out_dev, false, (cudaStream_t)stream));
+    return SDFA_OK;
 }
 
 long long sdfa_launch_count(void) { return launch_counter(); }

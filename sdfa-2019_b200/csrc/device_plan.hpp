@@ -52,8 +52,10 @@ cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cuda
 cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream);
 cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                                float *dgrad_out, cudaStream_t stream);
-cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, const uint32_t *tris, int n_tris,
-                               double eps, int as_matrix, double *out, cudaStream_t stream);
+// inverse.cu: verts_b holds n_frames meshes vb_stride floats apart; out is [n_frames, n_tris, 9] double or float
+cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, long long vb_stride, const uint32_t *tris,
+                               int n_tris, int n_frames, double eps, int as_matrix, void *out, bool out_f64,
+                               cudaStream_t stream);
 // decode_tc.cu
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);

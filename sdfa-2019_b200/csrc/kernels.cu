@@ -556,32 +556,58 @@ struct OutParams {
     int n_frames, n_free, n_verts;
 };
 
+// Only the free vertices' lines go through the transpose buffer; constrained vertices (3/4 of FLAME) are
+// frame independent and are written from a per-CTA constant table.
 __global__ void __launch_bounds__(256) k_output(OutParams P) {
-    __shared__ float t_sh[OUT_VC * 3 * TPAD];
+    __shared__ float t_sh[OUT_VC * 3 * TPAD];    // [free line][33]
+    __shared__ float cval[OUT_VC * 3];           // constrained values per output element
+    __shared__ short line_of[OUT_VC * 3];        // output element -> free line in t_sh, -1 if constrained
+    __shared__ int free_row[OUT_VC * 3];         // free line -> scratch word offset row*96 + c*32
+    __shared__ float free_hi[OUT_VC * 3], free_lo[OUT_VC * 3];
+    __shared__ int n_free_lines;
     const int v0 = blockIdx.x * OUT_VC;
     const int nv = min(OUT_VC, P.n_verts - v0);
+    const int ne = nv * 3;
     const int tile = blockIdx.y;
     const int frame0 = tile * FRAMES_PER_TILE;
     const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *src_tile = P.scratch + (long long)tile * P.n_free * SLOT_WORDS;
-    for (int line = warp; line < nv * 3; line += 8) {
-        const int vl = line / 3, c = line - 3 * vl;
-        const int row = __ldg(P.vert_row + v0 + vl);
-        float v;
-        if (row >= 0) {
-            const float x = src_tile[(long long)row * SLOT_WORDS + c * COORD_STRIDE + lane];
-            v = __ldg(P.xb_hi + row * 3 + c) + (__ldg(P.xb_lo + row * 3 + c) + x);
-        } else {
-            v = __ldg(P.cnst_pos + (-1 - row) * 3 + c);
+    if (warp == 0) {                             // compact the free lines of this vertex chunk (ballot scan)
+        int base = 0;
+        for (int e0 = 0; e0 < ne; e0 += 32) {
+            const int e = e0 + lane;
+            int row = -1;
+            if (e < ne) row = __ldg(P.vert_row + v0 + e / 3);
+            const unsigned m = __ballot_sync(0xffffffffu, e < ne && row >= 0);
+            if (e < ne) {
+                const int c = e % 3;
+                if (row >= 0) {
+                    const int i = base + __popc(m & ((1u << lane) - 1u));
+                    line_of[e] = (short)i;
+                    free_row[i] = row * SLOT_WORDS + c * COORD_STRIDE;
+                    free_hi[i] = __ldg(P.xb_hi + row * 3 + c);
+                    free_lo[i] = __ldg(P.xb_lo + row * 3 + c);
+                } else {
+                    line_of[e] = -1;
+                    cval[e] = __ldg(P.cnst_pos + (-1 - row) * 3 + c);
+                }
+            }
+            base += __popc(m);
         }
-        t_sh[line * TPAD + lane] = v;
+        if (lane == 0) n_free_lines = base;
     }
     __syncthreads();
-    const int ne = nv * 3;
+    const int nl = n_free_lines;
+    const float *src_tile = P.scratch + (long long)tile * P.n_free * SLOT_WORDS;
+    for (int i = warp; i < nl; i += 8)
+        t_sh[i * TPAD + lane] = free_hi[i] + (free_lo[i] + src_tile[free_row[i] + lane]);
+    __syncthreads();
     for (int f = warp; f < nvalid; f += 8) {
         float *dst = P.out + ((long long)(frame0 + f) * P.n_verts + v0) * 3;
-        for (int e = lane; e < ne; e += 32) dst[e] = t_sh[e * TPAD + f];
+        for (int e = lane; e < ne; e += 32) {
+            const int i = line_of[e];
+            dst[e] = i >= 0 ? t_sh[i * TPAD + f] : cval[e];
+        }
     }
 }
 

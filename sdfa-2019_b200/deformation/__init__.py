@@ -34,7 +34,7 @@ from . import _native
 from ._native import SdfaError, check, lib, ptr
 
 __all__ = ["set_target", "is_same", "get_mesh", "get_mesh_from_dg", "get_mesh_from_dm", "get_deform_grad",
-           "get_deform_mat", "get_mesh_batch", "set_pca", "decode_and_get_mesh", "Reconstructor", "SdfaError"]
+           "get_deform_mat", "get_deform_grad_batch", "get_mesh_batch", "set_pca", "decode_and_get_mesh", "Reconstructor", "SdfaError"]
 
 
 def _f32c(a, what):
@@ -323,6 +323,26 @@ def get_deform_grad(verts_a, verts_b, faces, eps=1e-6):
 def get_deform_mat(verts_a, verts_b, faces, eps=1e-6):
     """GetDeformMat (pybind.cpp:37-58)."""
     return _inverse(verts_a, verts_b, faces, eps, 1)
+
+
+def get_deform_grad_batch(verts_a, verts_b, faces, eps=1e-6, as_matrix=False):
+    """Many meshes against one template on the GPU: verts_a [n_verts,3], verts_b [N,n_verts,3] float32
+    (numpy or torch.cuda) -> float32 [N, 9*n_tris] (what generate_dgrad stores, preload.py:765-835)."""
+    import torch
+    dev = verts_b.device if _is_torch(verts_b) and verts_b.is_cuda else torch.device("cuda", _default_device())
+    A = torch.as_tensor(np.ascontiguousarray(verts_a, dtype=np.float32) if not _is_torch(verts_a) else verts_a,
+                        dtype=torch.float32, device=dev).reshape(-1, 3).contiguous()
+    B = torch.as_tensor(np.ascontiguousarray(verts_b, dtype=np.float32) if not _is_torch(verts_b) else verts_b,
+                        dtype=torch.float32, device=dev).reshape(-1, A.shape[0], 3).contiguous()
+    Fh = _u32c(faces.cpu().numpy() if _is_torch(faces) else faces).reshape(-1, 3)
+    if Fh.size and int(Fh.max()) >= A.shape[0]:
+        raise SdfaError(_native.ERR_ARG, "face index out of range")
+    Fd = torch.from_numpy(Fh.astype(np.int32)).to(dev)          # same bits as uint32
+    out = torch.empty((B.shape[0], len(Fh) * 9), dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    check(lib.sdfa_deform_grad_batch_dev(ptr(A.data_ptr()), ptr(B.data_ptr()), A.shape[0], ptr(Fd.data_ptr()), len(Fh),
+                                         B.shape[0], float(eps), 1 if as_matrix else 0, ptr(out.data_ptr()), ptr(s)))
+    return out
 
 
 def get_mesh_batch(deform_grads, vert_cnsts=None, out=None):

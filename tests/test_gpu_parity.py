@@ -204,3 +204,32 @@ def test_decode_and_reconstruct_config2(rec, chk, flame):
     # torch path == numpy path
     out_t = rec.decode_and_get_mesh(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda())
     assert np.array_equal(out_t.cpu().numpy(), out)
+
+
+def test_inverse_path_vs_golden_and_round_trip(flame, golden_flame, golden_small):
+    """mesh -> dgrad on the GPU (getDeformationGradients, impl.hpp:144-213) and the mesh -> dgrad -> mesh
+    round trip of SURVEY section 4 (KAT 2)."""
+    import torch
+    from tests.golden.make_fixtures import degenerate_case
+    V, F, border = W.grid_mesh()
+    Vb = golden_small["Vb"]
+    assert np.abs(D.get_deform_grad(V, Vb, F) - golden_small["deform_grad"]).max() < 1e-9
+    assert np.abs(D.get_deform_mat(verts_a=V, verts_b=Vb, faces=F, eps=1e-6) - golden_small["deform_mat"]).max() < 1e-9
+    Vd, Vbd, Fd = degenerate_case(V, Vb, F)
+    g = D.get_deform_grad(Vd, Vbd, Fd)
+    assert np.abs(g - golden_small["degen_deform_grad"]).max() < 1e-9 and np.all(g.reshape(-1, 9)[-1] == 0)
+    assert np.array_equal(D.get_deform_mat(Vd, Vbd, Fd).reshape(-1, 3, 3)[-1], np.eye(3))
+    # FLAME: integrable sets against the reference's own get_deform_grad output, then back to the mesh
+    Vf, Ff, nfv, nft, tol = flame["V"], flame["F"], flame["nfv"], flame["nft"], flame["tol"]
+    active = np.setdiff1d(np.arange(len(Ff)), nft)
+    fm = np.ones(len(Vf), dtype=bool); fm[nfv] = False
+    targets = np.stack([W.smooth_displacement(Vf, fm, a * 1e-3, seed=a) for a in (2, 10, 30)])
+    dg = D.get_deform_grad_batch(Vf, targets, Ff)
+    assert dg.shape == (3, len(Ff) * 9) and dg.dtype == torch.float32
+    for k, amp in enumerate((2, 10, 30)):
+        ga = golden_flame[f"integ{amp}_dgrad_active"]
+        got = dg[k].cpu().numpy().reshape(-1, 9)[active]
+        assert (np.abs(got - ga) <= 2e-6 * np.maximum(1.0, np.abs(ga))).all(), amp
+    rec = D.Reconstructor(Vf, Ff, cnsts=nfv, device=0)
+    back = rec.get_mesh_batch(dg).cpu().numpy()
+    assert np.abs(back - targets).max() <= tol
