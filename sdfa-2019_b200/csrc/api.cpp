@@ -148,8 +148,14 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         if ((rc = order_and_factor(p, err)) != 0) { delete h; return fail(SDFA_ERR_FACTOR, "sdfa_create: " + err); }
         compute_base_solution(p, nullptr);
         {
+            // frames per solve tile: 32 unless the resident rows of a large factor do not fit in the 227 KB of
+            // shared memory a CTA can have, then 16 or 8 (config 5: subdivided template)
             auto envi = [](const char *k, int d) { const char *v = std::getenv(k); return v ? std::atoi(v) : d; };
-            build_solve_program(p, envi("SDFA_PIECE_CAP", 64), envi("SDFA_SUPERNODE_CAP", 32), envi("SDFA_SUBTREE_CAP", 24));
+            const int want = envi("SDFA_FRAMES_PER_TILE", 32);
+            for (int f = want; f >= 8; f /= 2) {
+                build_solve_program(p, envi("SDFA_PIECE_CAP", 64), envi("SDFA_SUPERNODE_CAP", 32), envi("SDFA_SUBTREE_CAP", 24), f);
+                if (solve_smem_bytes(p.prog.n_slots, f) <= 227 * 1024) break;
+            }
         }
         build_assembly_plan(p, /*rows_per_block=*/128, ASM_MAX_EQ);
     } catch (const std::exception &e) {
@@ -168,7 +174,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             if (prop.major < 10)
                 return fail(SDFA_ERR_CUDA, "sdfa_create: device is not sm_100-class (kernels are built for sm_100a only)");
             h->dev.sm_count = prop.multiProcessorCount;
-            if (solve_smem_bytes(p.prog.n_slots) > (size_t)prop.sharedMemPerBlockOptin)
+            if (solve_smem_bytes(p.prog.n_slots, p.prog.frames_per_tile) > (size_t)prop.sharedMemPerBlockOptin)
                 return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: solve state (" + std::to_string(p.prog.n_slots) +
                                                       " rows) does not fit in shared memory");
             DevicePlan &d = h->dev;
@@ -200,6 +206,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             d.n_slots = p.prog.n_slots;
             d.n_phases_fwd = p.prog.n_phases_fwd;
             d.n_phases_bwd = p.prog.n_phases_bwd;
+            d.frames_per_tile = p.prog.frames_per_tile;
             std::vector<int32_t> vert_row(p.n_verts);
             for (int v = 0; v < p.n_verts; ++v)
                 vert_row[v] = p.vi_to_free[v] >= 0 ? p.iperm[p.vi_to_free[v]] : -1 - p.vi_to_cnst[v];
@@ -324,8 +331,9 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
 static int reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *dgrad_dev, long long stride,
                             bool staged, int mode, int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
     int rc;
-    const size_t n_tiles = ((size_t)n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
-    if ((rc = grow(&w.rhs, &w.rhs_cap, n_tiles * h->dev.n_free * SLOT_WORDS))) return rc;
+    const int F = h->host.prog.frames_per_tile;
+    const size_t n_tiles = ((size_t)n_frames + F - 1) / F;
+    if ((rc = grow(&w.rhs, &w.rhs_cap, n_tiles * h->dev.n_free * slot_words(F)))) return rc;
     if ((rc = time_mark(h, 1, s))) return rc;
     CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, staged, n_frames, mode, w.rhs, s));
     if ((rc = time_mark(h, 2, s))) return rc;
@@ -651,8 +659,8 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
                                     p.prog.n_entries, (long long)p.prog.stage_off.size() - 1,
                                     (long long)p.prog.bytes.size(), p.asmplan.max_eq_per_block,
                                     (long long)p.asmplan.eq_id.size(), (long long)p.asmplan.blocks.size(),
-                                    (long long)solve_smem_bytes(p.prog.n_slots), p.prog.n_supernodes,
-                                    (long long)p.prog.io_desc.size(), p.prog.n_entries_padded};
+                                    (long long)solve_smem_bytes(p.prog.n_slots, p.prog.frames_per_tile), p.prog.n_supernodes,
+                                    (long long)p.prog.io_desc.size(), p.prog.n_entries_padded, p.prog.frames_per_tile};
         return give(s, dst, cap);
     }
     return -1;

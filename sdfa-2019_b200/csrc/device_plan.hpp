@@ -27,7 +27,7 @@ struct DevicePlan {
     const uint32_t *stage_off = nullptr;
     const IoDesc   *io_desc = nullptr;
     const IoPhase  *io_phase = nullptr;
-    int n_stages = 0, n_slots = 0, n_phases_fwd = 0, n_phases_bwd = 0;
+    int n_stages = 0, n_slots = 0, n_phases_fwd = 0, n_phases_bwd = 0, frames_per_tile = 32;
     long long *solve_prof = nullptr;        // optional cycle counters [sm_count*4][8] (SDFA_SOLVE_PROFILE=1)
     // ---- output (K5)
     const int32_t  *vert_row = nullptr;     // vertex -> permuted row (>= 0) or -1 - constraint index
@@ -60,7 +60,7 @@ cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, long 
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);
 size_t tc_ximg_floats(int n_frames, int K);
-size_t solve_smem_bytes(int n_slots);
+size_t solve_smem_bytes(int n_slots, int frames_per_tile);
 void count_launch();
 long long launch_counter();
 

@@ -78,7 +78,7 @@ struct AsmParams {
     const float *dgrad;
     long long frame_stride;
     float *rhs;
-    int n_frames, n_free, mode, max_eq, max_plane, max_rows;
+    int n_frames, n_free, mode, max_eq, max_plane, max_rows, F;   // F = frames per solve tile
 };
 
 __device__ __forceinline__ void corner_vec(const float *d, float a, float b, const float *u, float *g) {
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     const int4 blk = P.blocks[blockIdx.x];
     const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
     const int tile = blockIdx.y;
-    const int frame0 = tile * FRAMES_PER_TILE;
-    const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
+    const int frame0 = tile * P.F;
+    const int nvalid = min(P.F, P.n_frames - frame0);
     // frame-invariant per-equation data stays in registers: thread t owns equations t, t+128, ...
     constexpr int KMAX = ASM_MAX_EQ / ASM_THREADS;
     int src_k[KMAX];
@@ -230,14 +230,15 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
         }
         __syncthreads();
     }
-    // transposed write-out: line (row, c) = 32 consecutive frames = 128 bytes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *dst_tile = P.rhs + (long long)tile * P.n_free * SLOT_WORDS;
-    for (int line = warp; line < n_rows * 3; line += ASM_THREADS / 32) {
-        const int r = line / 3, c = line - 3 * r;
-        const float v = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
-        dst_tile[(long long)P.row_perm[blk.z + r] * SLOT_WORDS + c * COORD_STRIDE + lane] = v;
-    }
+    // transposed write-out: line (row, c) = F consecutive frames
+    float *dst_tile = P.rhs + (long long)tile * P.n_free * 3 * P.F;
+    if (lane < P.F)
+        for (int line = warp; line < n_rows * 3; line += ASM_THREADS / 32) {
+            const int r = line / 3, c = line - 3 * r;
+            const float v = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
+            dst_tile[((long long)P.row_perm[blk.z + r] * 3 + c) * P.F + lane] = v;
+        }
 }
 
 static size_t asm_smem_bytes(const DevicePlan &d, bool staged) {
@@ -251,12 +252,12 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
     if (n_frames <= 0) return cudaSuccess;
     AsmParams P{d.asm_blocks, d.asm_eq_id, d.asm_eq_u, d.asm_row_perm, d.asm_row_ptr, d.asm_inc, d.eq_src,
                 d.asm_coff, d.asm_plane, dgrad, frame_stride, rhs, n_frames, d.n_free, mode, d.asm_max_eq,
-                d.asm_max_plane, d.asm_max_rows};
+                d.asm_max_plane, d.asm_max_rows, d.frames_per_tile};
     const size_t smem = asm_smem_bytes(d, staged);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
+    const int n_tiles = (n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
     dim3 grid((unsigned)d.n_asm_blocks, (unsigned)n_tiles);
     if (staged) k_assemble<true><<<grid, ASM_THREADS, smem, stream>>>(P);
     else k_assemble<false><<<grid, ASM_THREADS, smem, stream>>>(P);
@@ -294,6 +295,7 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 // One task on one warp (lane = frame).  Entry lists are padded by the host to whole batches (4 sources of
 // kind B, 4 packed pairs of kind A), and the next batch's entries are fetched while the current batch's
 // state values are in flight, so a batch costs one shared-memory round trip instead of two.
+template <int COORD_STRIDE>
 __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state_lane) {
     const uint4 th = *reinterpret_cast<const uint4 *>(task);       // TaskHeader
     const int n = (int)(th.w & 0xFFFFFFu);
@@ -380,7 +382,9 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
 constexpr int SOLVE_BAR_BYTES = 128;
 constexpr int BAR_FULL = 0, BAR_EMPTY = RING, BAR_LD = 2 * RING, BAR_DONE = 2 * RING + 2;
 
+template <int F>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
+    constexpr int SLOT_WORDS = 3 * F, SLOT_BYTES = 12 * F;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *ring = smem;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING * STAGE_BYTES);
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
     }
     // ---------------------------------------------------------------------- consumers
     const int cw = warp - 2;
-    uint8_t *state_lane = state + lane * 4;
+    uint8_t *state_lane = state + (lane % F) * 4;     // F < 32: the upper lanes mirror the lower ones
     uint32_t it = 0, g = 0;
     (void)n_phases;
     const bool prof = P.prof != nullptr && cw == 0;
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
                 if (type == OP_ROWS) {
                     const uint32_t *table = reinterpret_cast<const uint32_t *>(stage + hw.z);
                     if (prof) c_a = clock64();
-                    for (uint32_t t = cw; t < hw.y; t += NCW) run_row_task(stage + table[t], state_lane);
+                    for (uint32_t t = cw; t < hw.y; t += NCW) run_row_task<F>(stage + table[t], state_lane);
                     if (prof) { long long c_b = clock64(); c_task += c_b - c_a; c_a = c_b; }
                     at = hw.w;
                     if (flags & OPF_SYNC_AFTER) consumer_bar();
@@ -513,33 +517,43 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
     }
 }
 
-size_t solve_smem_bytes(int n_slots) {
-    return (size_t)RING * STAGE_BYTES + SOLVE_BAR_BYTES + (size_t)n_slots * SLOT_BYTES;
+size_t solve_smem_bytes(int n_slots, int frames_per_tile) {
+    return (size_t)RING * STAGE_BYTES + SOLVE_BAR_BYTES + (size_t)n_slots * slot_bytes(frames_per_tile);
 }
 
-cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
-    if (n_frames <= 0) return cudaSuccess;
-    const size_t smem = solve_smem_bytes(d.n_slots);
+template <int F>
+static cudaError_t launch_solve_f(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
+    const size_t smem = solve_smem_bytes(d.n_slots, F);
     static int configured_device = -1;
     static size_t configured_smem = 0;
     static int ctas_per_sm = 1;
     if (configured_device != d.device || configured_smem != smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_solve<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_solve, SOLVE_THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_solve<F>, SOLVE_THREADS, smem);
         if (e != cudaSuccess) return e;
         if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
         configured_device = d.device;
         configured_smem = smem;
     }
-    const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
+    const int n_tiles = (n_frames + F - 1) / F;
     SolveParams P{d.prog, d.stage_off, d.io_desc, d.io_phase, d.n_stages, d.n_slots, d.n_phases_fwd, d.n_phases_bwd,
                   scratch, d.n_free, n_tiles, d.solve_prof};
     int grid = d.sm_count * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    k_solve<<<grid, SOLVE_THREADS, smem, stream>>>(P);
+    k_solve<F><<<grid, SOLVE_THREADS, smem, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
+}
+
+cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    switch (d.frames_per_tile) {
+        case 32: return launch_solve_f<32>(d, scratch, n_frames, stream);
+        case 16: return launch_solve_f<16>(d, scratch, n_frames, stream);
+        case 8: return launch_solve_f<8>(d, scratch, n_frames, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 // =============================================================================================
@@ -553,7 +567,7 @@ struct OutParams {
     const int32_t *vert_row;                     // vertex -> permuted row, or -1-(constraint index)
     const float *xb_hi, *xb_lo, *cnst_pos;
     float *out;
-    int n_frames, n_free, n_verts;
+    int n_frames, n_free, n_verts, F;
 };
 
 // Only the free vertices' lines go through the transpose buffer; constrained vertices (3/4 of FLAME) are
@@ -569,8 +583,8 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
     const int nv = min(OUT_VC, P.n_verts - v0);
     const int ne = nv * 3;
     const int tile = blockIdx.y;
-    const int frame0 = tile * FRAMES_PER_TILE;
-    const int nvalid = min(FRAMES_PER_TILE, P.n_frames - frame0);
+    const int frame0 = tile * P.F;
+    const int nvalid = min(P.F, P.n_frames - frame0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {                             // compact the free lines of this vertex chunk (ballot scan)
         int base = 0;
@@ -584,7 +598,7 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
                 if (row >= 0) {
                     const int i = base + __popc(m & ((1u << lane) - 1u));
                     line_of[e] = (short)i;
-                    free_row[i] = row * SLOT_WORDS + c * COORD_STRIDE;
+                    free_row[i] = (row * 3 + c) * P.F;
                     free_hi[i] = __ldg(P.xb_hi + row * 3 + c);
                     free_lo[i] = __ldg(P.xb_lo + row * 3 + c);
                 } else {
@@ -598,9 +612,10 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
     }
     __syncthreads();
     const int nl = n_free_lines;
-    const float *src_tile = P.scratch + (long long)tile * P.n_free * SLOT_WORDS;
-    for (int i = warp; i < nl; i += 8)
-        t_sh[i * TPAD + lane] = free_hi[i] + (free_lo[i] + src_tile[free_row[i] + lane]);
+    const float *src_tile = P.scratch + (long long)tile * P.n_free * 3 * P.F;
+    if (lane < P.F)
+        for (int i = warp; i < nl; i += 8)
+            t_sh[i * TPAD + lane] = free_hi[i] + (free_lo[i] + src_tile[free_row[i] + lane]);
     __syncthreads();
     for (int f = warp; f < nvalid; f += 8) {
         float *dst = P.out + ((long long)(frame0 + f) * P.n_verts + v0) * 3;
@@ -613,8 +628,8 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
 
 cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    OutParams P{scratch, d.vert_row, d.xbase_hi, d.xbase_lo, d.cnst_pos, out, n_frames, d.n_free, d.n_verts};
-    const int n_tiles = (n_frames + FRAMES_PER_TILE - 1) / FRAMES_PER_TILE;
+    OutParams P{scratch, d.vert_row, d.xbase_hi, d.xbase_lo, d.cnst_pos, out, n_frames, d.n_free, d.n_verts, d.frames_per_tile};
+    const int n_tiles = (n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
     dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)n_tiles);
     k_output<<<grid, 256, 0, stream>>>(P);
     g_launches++;

@@ -11,14 +11,14 @@
 namespace sdfa {
 
 // ------------------------------------------------------------------------------------------
-// Geometry of the solve tile.  One CTA of the solve kernel owns FRAMES_PER_TILE frames (lane = frame).
-// A state "slot" holds one row of the permuted system for all those frames: [3 coords][32 frames] floats
-// = 384 bytes, which is also the layout of one row in the global scratch ("tile-major":
-// scratch[tile][row][coord][frame]), so rows move between global and shared memory with plain TMA bulk copies.
-constexpr int FRAMES_PER_TILE = 32;
-constexpr int COORD_STRIDE    = 32;
-constexpr int SLOT_WORDS      = 3 * COORD_STRIDE;     // 96
-constexpr int SLOT_BYTES      = SLOT_WORDS * 4;       // 384
+// Geometry of the solve tile.  One CTA of the solve kernel owns a tile of F frames (lane = frame),
+// F = 32 when the resident rows fit in shared memory, else 16 or 8 (large factors: config 5).
+// A state "slot" holds one row of the permuted system for those frames: [3 coords][F] floats, which is
+// also the layout of one row in the global scratch ("tile-major": scratch[tile][row][coord][frame]), so
+// rows move between global and shared memory with plain TMA bulk copies.
+constexpr int MAX_FRAMES_PER_TILE = 32;
+constexpr int slot_words(int f) { return 3 * f; }
+constexpr int slot_bytes(int f) { return 12 * f; }
 
 // ------------------------------------------------------------------------------------------
 // Solve program.  Two sweeps (forward L y = b, backward L^T x = y), each a sequence of PHASES; a phase
@@ -70,6 +70,7 @@ struct SolveProgram {
     std::vector<IoDesc>   io_desc;
     std::vector<IoPhase>  io_phase;     // forward phases then backward phases
     int n_phases_fwd = 0, n_phases_bwd = 0;
+    int frames_per_tile = 32;           // F
     int n_slots = 0;                    // state slots a CTA needs (peak over both sweeps)
     int n_steps_fwd = 0, n_steps_bwd = 0, n_supernodes = 0;
     long long n_entries = 0;            // useful multiply-adds per (frame, coordinate)
@@ -136,7 +137,7 @@ int  order_and_factor(HostPlan &p, std::string &err);             // perm, etree
 void compute_base_solution(HostPlan &p, const float *cnst_pos);   // x_base
 void solve_factored(const HostPlan &p, std::vector<double> &rhs_perm /* [n_free*3] in/out */);
 // schedule.cpp
-void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap);
+void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap, int frames_per_tile);
 void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block);
 constexpr int ASM_MAX_EQ = 512;   // equations per row block the assembly kernel keeps in registers/shared memory
 

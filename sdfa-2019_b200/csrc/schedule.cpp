@@ -168,7 +168,7 @@ void make_descs(std::vector<std::pair<int, int>> &rows_slots, std::vector<IoDesc
 
 // ---- serialisation of tasks (formats in plan.hpp) --------------------------------------------------
 // kind A: one target row, entries {coeff, src} packed two per 16 bytes.
-Blob blob_single(const Task &t) {
+Blob blob_single(const Task &t, int SLOT_BYTES) {
     Blob b;
     // padded to a multiple of 8 entries (4 packed pairs) so the kernel's loop has no remainder iterations
     const size_t n = t.entries.size(), ne = (n + 7) / 8 * 8;
@@ -188,7 +188,7 @@ Blob blob_single(const Task &t) {
 }
 // kind B: up to three target rows that read (nearly) the same sources: one entry {src, c0, c1, c2} per
 // source, so each source value is fetched from shared memory once for all rows of the group.
-Blob blob_group(const std::vector<const Task *> &rows) {
+Blob blob_group(const std::vector<const Task *> &rows, int SLOT_BYTES) {
     std::map<uint32_t, GroupEntry> uni;
     for (size_t r = 0; r < rows.size(); ++r)
         for (const TaskEntry &e : rows[r]->entries) {
@@ -219,7 +219,7 @@ Blob blob_group(const std::vector<const Task *> &rows) {
 // Groups the tasks of one level: neighbouring target rows (same block of the factor) whose source lists
 // nearly coincide share one kind-B task.  `pad_limit` bounds the zero padding the union may introduce.
 std::vector<Blob> group_level(std::vector<Task> &lv, const std::vector<int> &block_of_row, double pad_limit,
-                              long long &useful, long long &padded) {
+                              long long &useful, long long &padded, int SLOT_BYTES) {
     std::vector<Blob> out;
     std::stable_sort(lv.begin(), lv.end(), [&](const Task &a, const Task &b) { return a.target_row < b.target_row; });
     size_t i = 0;
@@ -240,8 +240,8 @@ std::vector<Blob> group_level(std::vector<Task> &lv, const std::vector<int> &blo
             ++j;
         }
         useful += (long long)sum;
-        if (grp.size() == 1) { out.push_back(blob_single(lv[i])); padded += (long long)sum; }
-        else { out.push_back(blob_group(grp)); padded += (long long)(uni.size() * 3); }
+        if (grp.size() == 1) { out.push_back(blob_single(lv[i], SLOT_BYTES)); padded += (long long)sum; }
+        else { out.push_back(blob_group(grp, SLOT_BYTES)); padded += (long long)(uni.size() * 3); }
         i = j;
     }
     return out;
@@ -363,10 +363,12 @@ struct PhaseData {
 };
 }  // namespace
 
-void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap) {
+void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap, int frames_per_tile) {
     const int n = p.n_free;
     SolveProgram &prog = p.prog;
     prog = SolveProgram();
+    prog.frames_per_tile = frames_per_tile;
+    const int SLOT_BYTES = slot_bytes(frames_per_tile);
     std::vector<Supernode> sn = find_supernodes(p, supernode_cap, subtree_cap);
     const int ns = (int)sn.size();
     prog.n_supernodes = ns;
@@ -554,7 +556,7 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subt
                 t.target_slot = resolve(t.target_slot);
                 for (auto &e : t.entries) e.src_byte_off = (uint32_t)resolve((int)e.src_byte_off);
             }
-            std::vector<Blob> blobs = group_level(lv, block_of_row, pad_limit, useful, padded);
+            std::vector<Blob> blobs = group_level(lv, block_of_row, pad_limit, useful, padded, SLOT_BYTES);
             em.rows(blobs, true);
         }
         em.marker(OP_PHASE_END);

@@ -7,8 +7,6 @@ op encoding) without a GPU.  It is NOT a fallback: nothing under ``sdfa-2019_b20
 """
 import numpy as np
 
-F, CS = 32, 32                      # FRAMES_PER_TILE, COORD_STRIDE (csrc/plan.hpp)
-SLOT_WORDS = 3 * CS
 OP_ROWS, OP_PHASE_BEGIN, OP_PHASE_END = 1, 2, 3
 TASK_GROUP, TASK_OVERWRITE = 1 << 24, 1 << 25
 f32 = np.float32
@@ -102,7 +100,13 @@ class _Hazards:
             self.w[s] = me
 
 
+def _geometry(rec):
+    f = int(rec.debug("stats")[14])            # frames per tile (32, or 16/8 for large factors)
+    return f, 3 * f
+
+
 def _parse_phases(rec):
+    F, SLOT_WORDS = _geometry(rec)
     """Splits the stage stream into phases: list of levels, each a list of (target_slot, overwrite, coeff[], src_slot[])."""
     prog, stage_off = rec.debug("prog"), rec.debug("stage_off")
     phases, cur, level = [], None, []
@@ -165,6 +169,7 @@ def solve(rec, rhs, cnst_pos=None):
     real-time order of TMA loads, levels and stores (loads of phase q+2 are issued right after the stores of
     phase q), with NaN-poisoned shared memory and a slot-level race check inside every level."""
     stats = rec.debug("stats")
+    F, SLOT_WORDS = _geometry(rec)
     n_slots = int(stats[0])
     io_desc = rec.debug("io_desc").reshape(-1, 4)
     io_phase = rec.debug("io_phase").reshape(-1, 4)

@@ -233,3 +233,24 @@ def test_inverse_path_vs_golden_and_round_trip(flame, golden_flame, golden_small
     rec = D.Reconstructor(Vf, Ff, cnsts=nfv, device=0)
     back = rec.get_mesh_batch(dg).cpu().numpy()
     assert np.abs(back - targets).max() <= tol
+
+
+def test_config5_subdivided_template():
+    """Config 5: FLAME subdivided twice (79 936 v / 159 616 f, 20 653 unknowns, nnz(L) ~ 7.8e5): the factor's
+    resident rows only fit in shared memory with 16 frames per tile.  Parity on the same 1e-6 x bbox bar."""
+    V, F, c = W.flame_sub2()
+    assert V.shape == (79936, 3) and F.shape == (159616, 3) and len(c) == 59283
+    tol = 1e-6 * W.bbox_diag(V)
+    r = D.Reconstructor(V, F, cnsts=c, device=0)
+    assert r.n_free == 20653 and int(r.debug("stats")[14]) in (8, 16)
+    o = TriangleDeformationOracle()
+    assert o.set_target(V, F, cnsts=c)
+    dg = W.iid_dgrad(37, len(F), sigma=0.01, seed=5)
+    out = r.get_mesh_batch(dg)
+    for i in (0, 15, 16, 36):
+        ref = o.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[c])
+        assert np.abs(out[i] - ref).max() <= tol, i
+        assert np.array_equal(out[i][c], V[c])
+    # KAT: zero dgrad gives back the template
+    z = r.get_mesh_batch(np.zeros((1, len(F) * 9), dtype=np.float32))
+    assert np.abs(z[0] - V).max() <= 1e-8

@@ -164,3 +164,18 @@ def test_emulated_tile_boundaries():
     o = TriangleDeformationOracle(); o.set_target(V, F, cnsts=border)
     ref = o.get_mesh(dg[17].astype(np.float64), vert_cnsts=V[border])
     assert np.abs(out[17] - ref).max() < 1e-6 * W.bbox_diag(V)
+
+
+def test_emulated_config5_picks_smaller_tiles():
+    """The subdivided template (config 5) does not fit 32 frames per tile; the plan must fall back to 16 or 8
+    and still be right (one frame through the interpreter)."""
+    V, F, c = W.flame_sub2()
+    r = D.Reconstructor(V, F, cnsts=c, device=-1)
+    stats = r.debug("stats")
+    assert r.n_free == 20653 and stats[14] in (8, 16) and stats[10] <= 227 * 1024
+    o = TriangleDeformationOracle()
+    assert o.set_target(V, F, cnsts=c)
+    dg = W.iid_dgrad(1, len(F), sigma=0.01, seed=5)
+    out, _ = E.solve(r, E.assemble(r, dg))
+    ref = o.get_mesh(dg[0].astype(np.float64), vert_cnsts=V[c])
+    assert np.abs(out[0] - ref).max() <= 0.2e-6 * W.bbox_diag(V)
