@@ -153,7 +153,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             auto envi = [](const char *k, int d) { const char *v = std::getenv(k); return v ? std::atoi(v) : d; };
             const int want = envi("SDFA_FRAMES_PER_TILE", 32);
             for (int f = want; f >= 8; f /= 2) {
-                build_solve_program(p, envi("SDFA_PIECE_CAP", 64), envi("SDFA_SUPERNODE_CAP", 32), envi("SDFA_SUBTREE_CAP", 24), f);
+                build_solve_program(p, envi("SDFA_PIECE_CAP", 64), envi("SDFA_SUPERNODE_CAP", 32), envi("SDFA_SUBTREE_CAP", 16), f);
                 if (solve_smem_bytes(p.prog.n_slots, f) <= 227 * 1024) break;
             }
         }

@@ -538,7 +538,7 @@ void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subt
     std::vector<int> block_of_row(n);
     for (int b = 0; b < ns; ++b) for (int c = sn[b].c0; c < sn[b].c1; ++c) block_of_row[c] = b;
     const char *pl = std::getenv("SDFA_GROUP_PAD");
-    const double pad_limit = pl ? std::atof(pl) : 1.25;
+    const double pad_limit = pl ? std::atof(pl) : 1.5;
     long long useful = 0, padded = 0;
     for (auto &ph : phases) {
         for (auto &rs : ph.loads) rs.second = resolve(rs.second);
