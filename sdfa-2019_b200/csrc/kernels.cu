@@ -105,13 +105,14 @@ constexpr int TPAD = 33;          // transpose-buffer row stride (odd: conflict 
 // STAGED: the input is the decode kernel's block-planar compact buffer; the block's span of a frame is one
 // contiguous run, fetched two frames ahead by a TMA bulk copy into a double-buffered stage (mbarrier
 // completion), and read back conflict-free (three planes of stride-3 triples).
-// !STAGED: any [frame][triangle][9] layout (the reference's dgrad tensor): gathered with scalar loads.
+// !STAGED: any [frame][triangle][9] layout (the reference's dgrad tensor): every thread gathers its
+// equations' nine values with 4-byte cp.async copies into the same double-buffered stage, two frames ahead.
 template <bool STAGED>
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     extern __shared__ __align__(128) float sh[];
-    float *stage = sh;                                              // [2][3*max_plane] (STAGED only)
-    float *g_sh = sh + (STAGED ? 6 * P.max_plane : 0);              // [max_eq][9]
-    float *t_sh = g_sh + P.max_eq * 9;                              // [rows*3][33]
+    float *stage = sh;                                              // [2][3*max_plane]: the frame's dgrad, block-planar
+    float *g_sh0 = sh + 6 * P.max_plane;                            // [2][max_eq][9]: corner vectors, double buffered
+    float *t_sh = g_sh0 + 2 * P.max_eq * 9;                         // [rows*3][33]
     uint64_t *bars = reinterpret_cast<uint64_t *>(t_sh + ((P.max_rows * 3 * TPAD + 3) & ~3));
     const int4 blk = P.blocks[blockIdx.x];
     const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
@@ -134,11 +135,26 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
             for (int j = 0; j < 6; ++j) u_k[k][j] = __ldg(P.eq_u + (blk.x + e) * 6 + j);
         }
     }
-    int plane = 0;
+    const int plane = P.blk_plane[blockIdx.x];
     uint32_t span_bytes = 0;
     const float *span0 = nullptr;
+    // !STAGED: asynchronous gather of frame `ft` into stage `si` (one commit group per frame and thread)
+    auto gather = [&](int ft, int si) {
+        const float *row = P.dgrad + (long long)(frame0 + ft) * P.frame_stride;
+        float *dst = stage + si * 3 * P.max_plane;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int e = threadIdx.x + k * ASM_THREADS;
+            if (e >= n_eq || src_k[k] < 0) continue;
+            const float *src = row + (long long)src_k[k] * 9;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (j / 3) * plane + e * 3 + (j % 3))),
+                             "l"(src + j) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if (STAGED) {
-        plane = P.blk_plane[blockIdx.x];
         span_bytes = 3u * (uint32_t)plane * 4u;
         span0 = P.dgrad + (long long)frame0 * P.frame_stride + P.blk_coff[blockIdx.x];
         if (threadIdx.x == 0) {
@@ -152,27 +168,30 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
             }
         }
         __syncthreads();
+    } else {
+        gather(0, 0);
+        if (nvalid > 1) gather(1, 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // frame 0 has landed (this thread's part)
+        __syncthreads();
     }
-    for (int f = 0; f < nvalid; ++f) {
-        const float *row = P.dgrad + (long long)(frame0 + f) * P.frame_stride;
+    // Software pipeline over the tile's frames with ONE block barrier per frame: iteration f computes the
+    // corner vectors of frame f into g_sh[f&1] and sums the rows of frame f-1 out of g_sh[(f-1)&1].
+    for (int f = 0; f <= nvalid; ++f) {
         const float *st = stage + (f & 1) * 3 * P.max_plane;
-        if (STAGED) mbar_wait(smem_u32(&bars[f & 1]), (uint32_t)(f >> 1) & 1u);
+        float *g_sh = g_sh0 + (f & 1) * P.max_eq * 9;
+        if (STAGED && f < nvalid) mbar_wait(smem_u32(&bars[f & 1]), (uint32_t)(f >> 1) & 1u);
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int e = threadIdx.x + k * ASM_THREADS;
-            if (e >= n_eq) break;
+            if (e >= n_eq || f >= nvalid) break;
             const int src = src_k[k];
             const float *u0 = &u_k[k][0], *u1 = &u_k[k][3];
             float g2[3], g3[3];
             if (src >= 0) {
                 float d[9];
-                if (STAGED) {
 #pragma unroll
-                    for (int j = 0; j < 9; ++j) d[j] = st[(j / 3) * plane + e * 3 + (j % 3)];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) d[j] = __ldg(row + (long long)src * 9 + j);
-                }
+                for (int j = 0; j < 9; ++j) d[j] = st[(j / 3) * plane + e * 3 + (j % 3)];
                 if (P.mode == ASM_DGRAD) {
                     const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
                     float a = 0.f, b = 0.f;
@@ -210,25 +229,30 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) { g[c] = -(g2[c] + g3[c]); g[3 + c] = g2[c]; g[6 + c] = g3[c]; }
         }
+        if (f >= 1) {
+            const float *gp = g_sh0 + ((f - 1) & 1) * P.max_eq * 9;
+            // rows are dealt from the top thread ids down: the low threads carry the extra equations above
+            for (int r = ASM_THREADS - 1 - threadIdx.x; r < n_rows; r += ASM_THREADS) {
+                const int gr = blk.z + r;
+                const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+                for (int q = q0; q < q1; ++q) {
+                    const float *g = gp + 3 * (int)P.inc[q];
+                    s0 += g[0]; s1 += g[1]; s2 += g[2];
+                }
+                float *t = t_sh + (3 * r) * TPAD + (f - 1);
+                t[0] = s0; t[TPAD] = s1; t[2 * TPAD] = s2;
+            }
+        }
+        if (!STAGED) asm volatile("cp.async.wait_group 0;" ::: "memory");   // frame f+1 has landed (this thread's part)
         __syncthreads();
-        if (STAGED && threadIdx.x == 0 && f + 2 < nvalid) {          // this stage is free again: prefetch frame f+2
+        if (!STAGED && f + 2 < nvalid) gather(f + 2, f & 1);         // stage f&1 has been consumed
+        if (STAGED && threadIdx.x == 0 && f + 2 < nvalid) {          // stage f&1 has been consumed: prefetch frame f+2
             fence_async_smem();
             mbar_arrive_expect_tx(smem_u32(&bars[f & 1]), span_bytes);
             tma_bulk_g2s(smem_u32(stage + (f & 1) * 3 * P.max_plane), span0 + (long long)(f + 2) * P.frame_stride, span_bytes,
                          smem_u32(&bars[f & 1]));
         }
-        for (int r = threadIdx.x; r < n_rows; r += ASM_THREADS) {
-            const int gr = blk.z + r;
-            const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-            for (int q = q0; q < q1; ++q) {
-                const float *g = g_sh + 3 * (int)P.inc[q];
-                s0 += g[0]; s1 += g[1]; s2 += g[2];
-            }
-            float *t = t_sh + (3 * r) * TPAD + f;
-            t[0] = s0; t[TPAD] = s1; t[2 * TPAD] = s2;
-        }
-        __syncthreads();
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // transposed write-out: line (row, c) = F consecutive frames
@@ -242,8 +266,9 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
 }
 
 static size_t asm_smem_bytes(const DevicePlan &d, bool staged) {
-    size_t fl = (size_t)d.asm_max_eq * 9 + (((size_t)d.asm_max_rows * 3 * TPAD + 3) & ~(size_t)3);
-    if (staged) fl += 6 * (size_t)d.asm_max_plane;
+    size_t fl = 2 * (size_t)d.asm_max_eq * 9 + (((size_t)d.asm_max_rows * 3 * TPAD + 3) & ~(size_t)3);
+    fl += 6 * (size_t)d.asm_max_plane;
+    (void)staged;
     return fl * sizeof(float) + 16;
 }
 
