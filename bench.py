@@ -7,7 +7,7 @@
 Workload (config.workload): configs[1] of BASELINE.json -- PCA-coefficient decode + reconstruction of
 240-frame sentences (4 s at 60 fps) on the FLAME template with the default mask (5023 v / 9976 tris, 3762
 constrained vertices, 2601 active triangles), random PCA basis (K = 85 scale + 180 rotation).  One step =
-one batch of S sentences per GPU (default 64 -> 15 360 frames), i.e. the three kernels of the path:
+one batch of S sentences per GPU (default 296 -> 71 040 frames), i.e. the three kernels of the path:
 K1 decode -> K2 assembly -> K3 solve (+ constrained-vertex fill).  Frames are sharded over ranks with no
 data-path collective ("weak": per-GPU batch fixed).
 
@@ -38,6 +38,18 @@ BYTES_PATH = 36 * N_ACTIVE + 12 * N_VERTS          # 153 912 B/frame, SURVEY 8(d
 BYTES_SOLVE = 2 * 12 * N_FREE                      # 30 264 B/frame: rhs in + solution out
 BYTES_ASSEMBLY = 36 * N_ACTIVE + 12 * N_FREE       # dgrad of the active triangles in + rhs out
 DECODE_FLOP = 2 * (N_ACTIVE * 6 * 85 + N_ACTIVE * 3 * 180)   # 5 462 100 useful FLOP/frame
+
+
+def ncu_traffic(kernel, n_frames):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json holds
+    bytes per frame measured at 15 360 frames per launch), scaled to this launch; None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as fp:
+            per_frame = json.load(fp)["dram_bytes_per_frame"][kernel]
+        return per_frame * n_frames
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -173,7 +185,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sentences", type=int, default=64, help="240-frame sentences per step per GPU")
+    ap.add_argument("--sentences", type=int, default=296,
+                    help="240-frame sentences per step per GPU (296 -> 71 040 frames = 2220 solve tiles = 15 per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -275,9 +288,10 @@ def main():
     else:
         b = BYTES_SOLVE if dom == "solve_ms" else BYTES_ASSEMBLY
         ach = b * n / (stage[dom] * 1e-3) / 1e9
-        roof = {"kernel": "k_solve (K3)" if dom == "solve_ms" else "k_assemble (K2)", "bound": "hbm", "achieved": ach,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                "algorithmic_bytes_per_frame": b}
+        kname = "k_solve" if dom == "solve_ms" else "k_assemble"
+        roof = {"kernel": kname + (" (K3)" if dom == "solve_ms" else " (K2)"), "bound": "hbm", "achieved": ach,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(kname, n),
+                "algorithmic_bytes_per_frame": b, "algorithmic_bytes_per_launch": b * n}
     roof["peak_source"] = peak_src
     path_gbs = BYTES_PATH * n / (ms_dgrad * 1e-3) / 1e9
     result = {
