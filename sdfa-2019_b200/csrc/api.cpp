@@ -116,11 +116,15 @@ static std::vector<int32_t> compact_map(const sdfa_handle *h) {
 static int upload_base(sdfa_handle *h) {
     if (h->dev.device < 0) return SDFA_OK;
     const HostPlan &p = h->host;
+    // x_base is kept in the Cholesky order (row iperm[f]); the kernels index it by scratch row
     std::vector<float> hi(p.x_base.size()), lo(p.x_base.size());
-    for (size_t i = 0; i < hi.size(); ++i) {
-        hi[i] = (float)p.x_base[i];
-        lo[i] = (float)(p.x_base[i] - (double)hi[i]);
-    }
+    for (int f = 0; f < p.n_free; ++f)
+        for (int c = 0; c < 3; ++c) {
+            const double x = p.x_base[(size_t)p.iperm[f] * 3 + c];
+            const size_t i = (size_t)p.scratch_row[f] * 3 + c;
+            hi[i] = (float)x;
+            lo[i] = (float)(x - (double)hi[i]);
+        }
     CUDA_TRY(cudaSetDevice(h->dev.device));
     CUDA_TRY(cudaMemcpy(h->dev.xbase_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->dev.xbase_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
@@ -157,6 +161,22 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
                 if (solve_smem_bytes(p.prog.n_slots, f) <= 227 * 1024) break;
             }
         }
+        {
+            // solver: the tensor-core plan when the template fits it, else the SIMT sweeps (SDFA_SOLVER=simt|tensor forces)
+            const char *sv = std::getenv("SDFA_SOLVER");
+            const std::string solver = sv ? sv : "auto";
+            if (solver != "simt") {
+                const char *lm = std::getenv("SDFA_TS_LEAF");
+                build_tensor_plan(p, lm ? std::atoi(lm) : 64);
+            } else p.tplan.why_not = "SDFA_SOLVER=simt";
+            if (solver == "tensor" && !p.tplan.valid) {
+                std::string why = p.tplan.why_not;
+                delete h;
+                return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: SDFA_SOLVER=tensor but the template does not fit: " + why);
+            }
+            p.use_tensor = p.tplan.valid;
+            p.scratch_row = p.use_tensor ? p.tplan.row_of_free : p.iperm;
+        }
         build_assembly_plan(p, /*rows_per_block=*/128, ASM_MAX_EQ);
     } catch (const std::exception &e) {
         delete h;
@@ -174,7 +194,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             if (prop.major < 10)
                 return fail(SDFA_ERR_CUDA, "sdfa_create: device is not sm_100-class (kernels are built for sm_100a only)");
             h->dev.sm_count = prop.multiProcessorCount;
-            if (solve_smem_bytes(p.prog.n_slots, p.prog.frames_per_tile) > (size_t)prop.sharedMemPerBlockOptin)
+            if (!p.use_tensor && solve_smem_bytes(p.prog.n_slots, p.prog.frames_per_tile) > (size_t)prop.sharedMemPerBlockOptin)
                 return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: solve state (" + std::to_string(p.prog.n_slots) +
                                                       " rows) does not fit in shared memory");
             DevicePlan &d = h->dev;
@@ -207,9 +227,33 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             d.n_phases_fwd = p.prog.n_phases_fwd;
             d.n_phases_bwd = p.prog.n_phases_bwd;
             d.frames_per_tile = p.prog.frames_per_tile;
+            d.layout.sub = 1;
+            d.layout.tile_stride = (long long)p.n_free * slot_words(d.frames_per_tile);
+            d.layout.row_stride = 3 * d.frames_per_tile;
+            d.layout.c_stride = d.frames_per_tile;
+            d.use_tensor = p.use_tensor;
+            if (p.use_tensor) {
+                const TensorPlan &tp = p.tplan;
+                if (solve_tc_smem_bytes((int)tp.mma.size(), (int)tp.epi.size()) > (size_t)prop.sharedMemPerBlockOptin)
+                    return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: tensor solve program does not fit in shared memory");
+                if ((r = upload(h, tp.mma, &d.ts_mma))) return r;
+                if ((r = upload(h, tp.epi, &d.ts_epi))) return r;
+                if ((r = upload(h, tp.matrix, &d.ts_matrix))) return r;
+                if ((r = upload(h, tp.chunk_off, &d.ts_chunk_off))) return r;
+                d.ts_n_mma = (int)tp.mma.size();
+                d.ts_n_epi = (int)tp.epi.size();
+                d.ts_n_chunks = (int)tp.chunk_off.size() - 1;
+                d.ts_n_mma_events = tp.n_mma_events;
+                d.ts_n_epi_events = tp.n_epi_events;
+                d.frames_per_tile = 32;                          // K2 / K5 tile; four of them share a 128-column solve tile
+                d.layout.sub = TS_COLS / 32;
+                d.layout.tile_stride = 3LL * p.n_free * TS_COLS;
+                d.layout.row_stride = TS_COLS;
+                d.layout.c_stride = p.n_free * TS_COLS;
+            }
             std::vector<int32_t> vert_row(p.n_verts);
             for (int v = 0; v < p.n_verts; ++v)
-                vert_row[v] = p.vi_to_free[v] >= 0 ? p.iperm[p.vi_to_free[v]] : -1 - p.vi_to_cnst[v];
+                vert_row[v] = p.vi_to_free[v] >= 0 ? p.scratch_row[p.vi_to_free[v]] : -1 - p.vi_to_cnst[v];
             if ((r = upload(h, vert_row, &d.vert_row))) return r;
             std::vector<float> z((size_t)p.n_free * 3, 0.f);
             if ((r = upload_mut(h, z, &d.xbase_hi))) return r;
@@ -331,13 +375,19 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
 static int reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *dgrad_dev, long long stride,
                             bool staged, int mode, int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
     int rc;
-    const int F = h->host.prog.frames_per_tile;
-    const size_t n_tiles = ((size_t)n_frames + F - 1) / F;
-    if ((rc = grow(&w.rhs, &w.rhs_cap, n_tiles * h->dev.n_free * slot_words(F)))) return rc;
+    {
+        const size_t need = scratch_floats(h->dev, n_frames);
+        if (w.rhs_cap < need) {
+            if ((rc = grow(&w.rhs, &w.rhs_cap, need))) return rc;
+            // columns of a partially filled tensor tile that no frame owns are solved too: keep them finite
+            CUDA_TRY(cudaMemsetAsync(w.rhs, 0, need * sizeof(float), s));
+        }
+    }
     if ((rc = time_mark(h, 1, s))) return rc;
     CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, staged, n_frames, mode, w.rhs, s));
     if ((rc = time_mark(h, 2, s))) return rc;
-    CUDA_TRY(launch_solve(h->dev, w.rhs, n_frames, s));
+    if (h->dev.use_tensor) CUDA_TRY(launch_solve_tc(h->dev, w.rhs, n_frames, s));
+    else CUDA_TRY(launch_solve(h->dev, w.rhs, n_frames, s));
     if ((rc = time_mark(h, 3, s))) return rc;
     CUDA_TRY(launch_output(h->dev, w.rhs, n_frames, out_dev, s));
     if ((rc = time_mark(h, 4, s))) return rc;
@@ -644,6 +694,19 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
     if (w == "asm_row_perm") return give(p.asmplan.row_perm, dst, cap);
     if (w == "asm_row_ptr") return give(p.asmplan.row_ptr, dst, cap);
     if (w == "asm_inc") return give(p.asmplan.inc, dst, cap);
+    if (w == "scratch_row") return give(p.scratch_row, dst, cap);
+    if (w == "ts_mma") return give(p.tplan.mma, dst, cap);
+    if (w == "ts_epi") return give(p.tplan.epi, dst, cap);
+    if (w == "ts_matrix") return give(p.tplan.matrix, dst, cap);
+    if (w == "ts_chunk_off") return give(p.tplan.chunk_off, dst, cap);
+    if (w == "ts_why_not") { std::vector<char> v(p.tplan.why_not.begin(), p.tplan.why_not.end()); return give(v, dst, cap); }
+    if (w == "ts_stats") {
+        std::vector<long long> v = {p.use_tensor ? 1 : 0, p.tplan.valid ? 1 : 0, (long long)p.tplan.mma.size(), (long long)p.tplan.epi.size(),
+                                    (long long)p.tplan.chunk_off.size() - 1, (long long)p.tplan.matrix.size(), p.tplan.n_mma_events,
+                                    p.tplan.n_epi_events, p.tplan.n_nodes, p.tplan.n_leaves, p.tplan.nk_products, p.tplan.tmem_fwd,
+                                    p.tplan.tmem_bwd, (long long)solve_tc_smem_bytes((int)p.tplan.mma.size(), (int)p.tplan.epi.size())};
+        return give(v, dst, cap);
+    }
     if (w == "asm_blocks") {
         std::vector<int> b;
         for (auto &x : p.asmplan.blocks) { b.push_back(x.eq_begin); b.push_back(x.eq_end); b.push_back(x.row_begin); b.push_back(x.row_end); }

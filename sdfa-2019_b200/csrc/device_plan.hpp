@@ -7,6 +7,16 @@
 
 namespace sdfa {
 
+// Where element (32-frame tile t, row, coordinate c, lane) of the solve scratch lives:
+//   (t / sub) * tile_stride + (t % sub) * 32 + row * row_stride + c * c_stride + lane
+// SIMT solve: sub = 1, rows of [3][F] floats ("tile-major"); tensor solve: sub = 4, one [n_free][128] matrix per
+// (128-frame tile, coordinate).
+struct ScratchLayout {
+    int sub = 1;
+    long long tile_stride = 0;
+    int row_stride = 0, c_stride = 0;
+};
+
 struct DevicePlan {
     int device = -1;
     int n_verts = 0, n_tris = 0, n_cnsts = 0, n_free = 0, n_eq = 0;
@@ -29,6 +39,14 @@ struct DevicePlan {
     const IoPhase  *io_phase = nullptr;
     int n_stages = 0, n_slots = 0, n_phases_fwd = 0, n_phases_bwd = 0, frames_per_tile = 32;
     long long *solve_prof = nullptr;        // optional cycle counters [sm_count*4][8] (SDFA_SOLVE_PROFILE=1)
+    // ---- tensor-core solve (K3T, solve_tc.cu); used instead of K3 when use_tensor
+    bool use_tensor = false;
+    ScratchLayout layout;
+    const MmaOp    *ts_mma = nullptr;
+    const EpiOp    *ts_epi = nullptr;
+    const uint8_t  *ts_matrix = nullptr;
+    const uint32_t *ts_chunk_off = nullptr;
+    int ts_n_mma = 0, ts_n_epi = 0, ts_n_chunks = 0, ts_n_mma_events = 0, ts_n_epi_events = 0;
     // ---- output (K5)
     const int32_t  *vert_row = nullptr;     // vertex -> permuted row (>= 0) or -1 - constraint index
     float          *xbase_hi = nullptr, *xbase_lo = nullptr;   // [n_free*3] permuted order
@@ -49,6 +67,9 @@ enum AssemblyMode { ASM_DGRAD = 0, ASM_MATRIX = 1 };
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream);
 cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream);
+cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream);
+size_t solve_tc_smem_bytes(int n_mma, int n_epi);
+size_t scratch_floats(const DevicePlan &d, int n_frames);
 cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream);
 cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                                float *dgrad_out, cudaStream_t stream);

@@ -79,6 +79,7 @@ struct AsmParams {
     long long frame_stride;
     float *rhs;
     int n_frames, n_free, mode, max_eq, max_plane, max_rows, F;   // F = frames per solve tile
+    ScratchLayout L;
 };
 
 __device__ __forceinline__ void corner_vec(const float *d, float a, float b, const float *u, float *g) {
@@ -256,12 +257,12 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // transposed write-out: line (row, c) = F consecutive frames
-    float *dst_tile = P.rhs + (long long)tile * P.n_free * 3 * P.F;
+    float *dst_tile = P.rhs + (long long)(tile / P.L.sub) * P.L.tile_stride + (tile % P.L.sub) * 32;
     if (lane < P.F)
         for (int line = warp; line < n_rows * 3; line += ASM_THREADS / 32) {
             const int r = line / 3, c = line - 3 * r;
             const float v = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
-            dst_tile[((long long)P.row_perm[blk.z + r] * 3 + c) * P.F + lane] = v;
+            dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride + lane] = v;
         }
 }
 
@@ -277,7 +278,7 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
     if (n_frames <= 0) return cudaSuccess;
     AsmParams P{d.asm_blocks, d.asm_eq_id, d.asm_eq_u, d.asm_row_perm, d.asm_row_ptr, d.asm_inc, d.eq_src,
                 d.asm_coff, d.asm_plane, dgrad, frame_stride, rhs, n_frames, d.n_free, mode, d.asm_max_eq,
-                d.asm_max_plane, d.asm_max_rows, d.frames_per_tile};
+                d.asm_max_plane, d.asm_max_rows, d.frames_per_tile, d.layout};
     const size_t smem = asm_smem_bytes(d, staged);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -542,6 +543,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
     }
 }
 
+size_t scratch_floats(const DevicePlan &d, int n_frames) {
+    const size_t n_tiles = ((size_t)n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
+    return (n_tiles + d.layout.sub - 1) / d.layout.sub * (size_t)d.layout.tile_stride;
+}
+
 size_t solve_smem_bytes(int n_slots, int frames_per_tile) {
     return (size_t)RING * STAGE_BYTES + SOLVE_BAR_BYTES + (size_t)n_slots * slot_bytes(frames_per_tile);
 }
@@ -593,6 +599,7 @@ struct OutParams {
     const float *xb_hi, *xb_lo, *cnst_pos;
     float *out;
     int n_frames, n_free, n_verts, F;
+    ScratchLayout L;
 };
 
 // Only the free vertices' lines go through the transpose buffer; constrained vertices (3/4 of FLAME) are
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
                 if (row >= 0) {
                     const int i = base + __popc(m & ((1u << lane) - 1u));
                     line_of[e] = (short)i;
-                    free_row[i] = (row * 3 + c) * P.F;
+                    free_row[i] = row * P.L.row_stride + c * P.L.c_stride;
                     free_hi[i] = __ldg(P.xb_hi + row * 3 + c);
                     free_lo[i] = __ldg(P.xb_lo + row * 3 + c);
                 } else {
@@ -637,7 +644,7 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
     }
     __syncthreads();
     const int nl = n_free_lines;
-    const float *src_tile = P.scratch + (long long)tile * P.n_free * 3 * P.F;
+    const float *src_tile = P.scratch + (long long)(tile / P.L.sub) * P.L.tile_stride + (tile % P.L.sub) * 32;
     if (lane < P.F)
         for (int i = warp; i < nl; i += 8)
             t_sh[i * TPAD + lane] = free_hi[i] + (free_lo[i] + src_tile[free_row[i] + lane]);
@@ -653,7 +660,7 @@ __global__ void __launch_bounds__(256) k_output(OutParams P) {
 
 cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    OutParams P{scratch, d.vert_row, d.xbase_hi, d.xbase_lo, d.cnst_pos, out, n_frames, d.n_free, d.n_verts, d.frames_per_tile};
+    OutParams P{scratch, d.vert_row, d.xbase_hi, d.xbase_lo, d.cnst_pos, out, n_frames, d.n_free, d.n_verts, d.frames_per_tile, d.layout};
     const int n_tiles = (n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
     dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)n_tiles);
     k_output<<<grid, 256, 0, stream>>>(P);

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include "tplan.hpp"
+
 namespace sdfa {
 
 // ------------------------------------------------------------------------------------------
@@ -129,6 +131,11 @@ struct HostPlan {
     std::vector<float>  cnst_pos;       // [n_cnsts*3] currently active constraint positions
     SolveProgram prog;
     AssemblyPlan asmplan;
+    // tensor-core solve (tplan.hpp); when use_tensor is set the scratch rows follow its nested-dissection
+    // order instead of the Cholesky permutation
+    TensorPlan tplan;
+    bool use_tensor = false;
+    std::vector<int> scratch_row;       // free column -> row of the solve scratch (= iperm, or tplan.row_of_free)
 };
 
 // analysis.cpp

@@ -639,7 +639,7 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
             for (int d = 0; d < 6; ++d) ap.eq_u.push_back((float)u[d]);
         }
         for (int f : rows) {
-            ap.row_perm.push_back(p.iperm[f]);
+            ap.row_perm.push_back(p.scratch_row[f]);
             for (auto &kc : inc[f]) {
                 int local = (int)(std::lower_bound(eqs.begin(), eqs.end(), kc.first) - eqs.begin());
                 ap.inc.push_back((uint16_t)(local * 3 + kc.second));

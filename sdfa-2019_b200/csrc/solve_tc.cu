@@ -1,0 +1,285 @@
+// solve_tc.cu -- K3T: the batched solve (A^T A + reg I) X = RHS on the 5th-generation tensor cores.
+//
+// Replaces `solver_.solve(...)` of the reference's per-frame path (deformation/cpp/src/deform_triangle_impl.hpp:286-292,
+// Eigen::SparseLU) for templates whose plan fits (tplan.hpp): nested-dissection block Cholesky whose blocks are
+// explicit small dense matrices, executed as tcgen05.mma kind::tf32 products
+//      D[128 columns, N] (+)= A[128 columns, K] * Bt[N, K]
+// with the right-hand-side columns (frame x coordinate) on the M dimension = the 128 lanes of tensor memory:
+// A (the source rows, split into TF32 hi / lo) and D (accumulators) both live in tensor memory, so a result
+// is turned into the next product's operand by one tcgen05.ld / split / tcgen05.st round trip of the epilogue
+// warps and never goes through shared memory; Bt (the fixed matrices, pre-split hi / lo, K-major
+// SWIZZLE_128B tile images) streams L2 -> shared-memory ring with cp.async.bulk.  3xTF32: every K-step issues
+// A_hi B_hi + A_lo B_hi + A_hi B_lo into the fp32 accumulator.
+//
+// One persistent CTA per SM loops over 128-column tiles of scratch[tile][row][128]; warp roles:
+//   warp 0   streamer : matrix chunks -> ring (mbarrier full / empty)
+//   warp 1   issuer   : one thread walks the MmaOp stream
+//   warps 2-5 epilogue: thread = column = tensor-memory lane, walks the EpiOp stream
+// The two streams synchronise through single-use-per-tile mbarrier events chosen by the planner.
+#include "device_plan.hpp"
+
+namespace sdfa {
+
+namespace {
+
+constexpr int TS_RING = 4;
+constexpr int TS_THREADS = 32 * 6;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (same encoding as decode_tc.cu)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, K = 8 (A: lane = row, 8 consecutive 32-bit columns)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+struct TsParams {
+    const MmaOp *mma;
+    const EpiOp *epi;
+    const uint8_t *matrix;
+    const uint32_t *chunk_off;
+    int n_mma, n_epi, n_chunks, n_mma_events, n_epi_events;
+    float *scratch;            // [n_tiles][n_rows][128]
+    int n_rows, n_tiles;
+};
+
+// instruction descriptor: D fp32, A / B tf32, both K-major, M = 128; N is filled in per op
+constexpr uint32_t TS_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
+constexpr int TS_MAX_CHUNKS8 = TS_MAX_NODE / 8;
+
+__global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B images: 1024-byte aligned
+    uint8_t *ring = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TS_RING * TS_STAGE_BYTES);
+    uint64_t *bar_full = bars, *bar_empty = bars + TS_RING, *bar_mma = bars + 2 * TS_RING, *bar_epi = bar_mma + TS_MAX_EVENTS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_epi + TS_MAX_EVENTS);
+    MmaOp *mma_sm = reinterpret_cast<MmaOp *>(tmem_slot + 4);
+    EpiOp *epi_sm = reinterpret_cast<EpiOp *>(mma_sm + P.n_mma);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < P.n_mma * 8; i += TS_THREADS)
+        reinterpret_cast<uint32_t *>(mma_sm)[i] = reinterpret_cast<const uint32_t *>(P.mma)[i];
+    for (int i = threadIdx.x; i < P.n_epi * 8; i += TS_THREADS)
+        reinterpret_cast<uint32_t *>(epi_sm)[i] = reinterpret_cast<const uint32_t *>(P.epi)[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_RING; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 1); }
+        for (int e = 0; e < P.n_mma_events; ++e) mbar_init(smem_u32(bar_mma + e), 1);     // tcgen05.commit
+        for (int e = 0; e < P.n_epi_events; ++e) mbar_init(smem_u32(bar_epi + e), 4);     // one arrive per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TS_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ streamer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+                for (int c = 0; c < P.n_chunks; ++c, ++it) {
+                    const uint32_t s = it % TS_RING, ph = (it / TS_RING) & 1u;
+                    mbar_wait(smem_u32(bar_empty + s), ph ^ 1u);
+                    const uint32_t off = P.chunk_off[c], bytes = P.chunk_off[c + 1] - off;
+                    mbar_arrive_expect_tx(smem_u32(bar_full + s), bytes);
+                    tma_bulk_g2s(smem_u32(ring + s * TS_STAGE_BYTES), P.matrix + off, bytes, smem_u32(bar_full + s));
+                }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t par = tcount & 1u;
+                uint32_t stage = 0, slot = 0;
+                for (int m = 0; m < P.n_mma; ++m) {
+                    const MmaOp op = mma_sm[m];
+                    if (op.wait_epi >= 0) {
+                        mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
+                        tc_fence_after();
+                    }
+                    if (op.flags & MMA_CHUNK_FIRST) {
+                        slot = it % TS_RING;
+                        mbar_wait(smem_u32(bar_full + slot), (it / TS_RING) & 1u);
+                        tc_fence_after();
+                        stage = smem_u32(ring + slot * TS_STAGE_BYTES);
+                    }
+                    const uint32_t idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
+                    const uint32_t d = tmem_base + op.d_col, a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
+                    const uint32_t kb_bytes = (uint32_t)op.n * 128u;
+                    uint32_t acc = (op.flags & MMA_ACCUMULATE) ? 1u : 0u;
+                    for (uint32_t j = 0; j < op.k8; ++j) {
+                        const uint32_t off = (j >> 2) * kb_bytes + (j & 3u) * 32u;
+                        const uint64_t b_hi = umma_desc(stage + op.b_hi_off + off), b_lo = umma_desc(stage + op.b_lo_off + off);
+                        umma_tf32_ts(d, a_hi + 8 * j, b_hi, idesc, acc);
+                        umma_tf32_ts(d, a_lo + 8 * j, b_hi, idesc, 1u);
+                        umma_tf32_ts(d, a_hi + 8 * j, b_lo, idesc, 1u);
+                        acc = 1u;
+                    }
+                    if (op.flags & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
+                    if (op.commit_mma >= 0) tc_commit(smem_u32(bar_mma + op.commit_mma));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = column
+        const int lane_grp = warp & 3;                               // tensor-memory lanes 32*lane_grp.. belong to this warp
+        const int col = lane_grp * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t par = tcount & 1u;
+            float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS + col;
+#pragma unroll 1
+            for (int e = 0; e < P.n_epi; ++e) {
+                const EpiOp op = epi_sm[e];
+                const int nch = op.n_chunks, nv = op.n_valid;
+                float g[TS_MAX_CHUNKS8][8];
+                if (op.flags & EPI_ADD_GLOBAL) {                     // issue the global loads before waiting
+                    const float *src = sc + (size_t)op.row_in * TS_COLS;
+#pragma unroll
+                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) g[c][i] = (c < nch && c * 8 + i < nv) ? src[(size_t)(c * 8 + i) * TS_COLS] : 0.f;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) g[c][i] = 0.f;
+                }
+                if (op.wait_mma >= 0) {
+                    mbar_wait(smem_u32(bar_mma + op.wait_mma), par);
+                    tc_fence_after();
+                }
+                if (op.flags & EPI_FROM_TMEM) {
+#pragma unroll
+                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+                        if (c < nch) {
+                            uint32_t v[8];
+                            tmem_ld8(tlane + op.src_col + 8 * c, v);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) g[c][i] = (c * 8 + i < nv) ? g[c][i] + __uint_as_float(v[i]) : 0.f;
+                        }
+                }
+                if (op.flags & EPI_STORE_GLOBAL) {
+                    float *dst = sc + (size_t)op.row_out * TS_COLS;
+#pragma unroll
+                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (c < nch && c * 8 + i < nv) dst[(size_t)(c * 8 + i) * TS_COLS] = g[c][i];
+                }
+                if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT)) {
+                    const bool split = (op.flags & EPI_ST_SPLIT) != 0;
+#pragma unroll
+                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+                        if (c < nch) {
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t u = __float_as_uint(g[c][i]);
+                                hi[i] = split ? (u & 0xFFFFE000u) : u;
+                                lo[i] = __float_as_uint(g[c][i] - __uint_as_float(hi[i])) & 0xFFFFE000u;
+                            }
+                            tmem_st8(tlane + op.hi_col + 8 * c, hi);
+                            if (split) tmem_st8(tlane + op.lo_col + 8 * c, lo);
+                        }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                if (op.signal_epi >= 0) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(bar_epi + op.signal_epi));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace
+
+size_t solve_tc_smem_bytes(int n_mma, int n_epi) {
+    return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)(2 * TS_RING + 2 * TS_MAX_EVENTS) * 8 + 16 +
+           (size_t)n_mma * sizeof(MmaOp) + (size_t)n_epi * sizeof(EpiOp);
+}
+
+cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    const size_t smem = solve_tc_smem_bytes(d.ts_n_mma, d.ts_n_epi);
+    static int configured_device = -1;
+    static size_t configured_smem = 0;
+    if (configured_device != d.device || configured_smem != smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured_device = d.device;
+        configured_smem = smem;
+    }
+    const int n_tiles = 3 * ((n_frames + TS_COLS - 1) / TS_COLS);
+    TsParams P{d.ts_mma, d.ts_epi, d.ts_matrix, d.ts_chunk_off, d.ts_n_mma, d.ts_n_epi, d.ts_n_chunks,
+               d.ts_n_mma_events, d.ts_n_epi_events, scratch, d.n_free, n_tiles};
+    int grid = d.sm_count;
+    if (grid > n_tiles) grid = n_tiles;
+    k_solve_tc<<<grid, TS_THREADS, smem, stream>>>(P);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace sdfa

@@ -1,0 +1,498 @@
+// tplan.cpp -- host planner of the tensor-core solve (see tplan.hpp for the scheme and the formats).
+//
+// Replaces, together with solve_tc.cu, the per-frame `solver_.solve(...)` of the reference
+// (deformation/cpp/src/deform_triangle_impl.hpp:286-292; Eigen::SparseLU set up at :122-139) for templates
+// whose system fits: the factorisation below is a block Cholesky over a nested-dissection tree, computed
+// once in fp64, whose blocks are folded into explicit products so that the GPU only multiplies.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <numeric>
+
+namespace sdfa {
+
+namespace {
+
+inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+inline float rn_tf32(float x) {          // round to nearest-even TF32 (10 explicit mantissa bits), low 13 bits zero
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u = (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+struct Coupling {
+    int anc;                      // ancestor node index
+    int r0, r1;                   // coupled local rows of the ancestor lie in [r0, r1)
+    std::vector<double> G;        // |anc| x |J| row-major: F_aJ F_JJ^-1 (zero rows where not coupled)
+};
+
+struct TNode {
+    std::vector<int> rows;        // free columns of this node, in scratch order
+    int parent = -1;
+    std::vector<int> children;
+    std::vector<int> anc;         // ancestors, nearest first
+    int row0 = 0;                 // first scratch row
+    int acc_off = 0, xs_off = 0;  // tensor-memory stack offsets (forward accumulators / backward solutions)
+    std::vector<double> P;        // |J| x |J|: F_JJ^-1
+    std::vector<Coupling> coup;
+};
+
+struct Builder {
+    HostPlan &p;
+    TensorPlan &t;
+    int n;
+    std::vector<std::vector<int>> adj;
+    std::vector<TNode> nodes;
+    int leaf_max;
+    std::string err;
+
+    Builder(HostPlan &hp, int lm) : p(hp), t(hp.tplan), n(hp.n_free), leaf_max(lm) {}
+
+    const float *pos(int f) const { return &p.verts[(size_t)p.free_to_vi[f] * 3]; }
+
+    static int widest_axis(const std::vector<int> &idx, const std::function<const float *(int)> &pos) {
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int f : idx)
+            for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], pos(f)[d]); hi[d] = std::max(hi[d], pos(f)[d]); }
+        int ax = 0;
+        for (int d = 1; d < 3; ++d) if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+        return ax;
+    }
+
+    // geometric nested dissection: split at the median of the widest axis, the separator is the smaller of
+    // the two one-sided boundaries of the cut
+    int bisect(std::vector<int> idx, int parent) {
+        const int me = (int)nodes.size();
+        nodes.emplace_back();
+        nodes[me].parent = parent;
+        auto P = [this](int f) { return pos(f); };
+        if ((int)idx.size() <= leaf_max) {
+            nodes[me].rows = idx;
+            return me;
+        }
+        const int ax = widest_axis(idx, P);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return pos(a)[ax] < pos(b)[ax]; });
+        const int half = (int)idx.size() / 2;
+        std::vector<int> side(n, -1);                       // -1 outside, 0 / 1 the two sides
+        for (int i = 0; i < (int)idx.size(); ++i) side[idx[i]] = i < half ? 0 : 1;
+        std::vector<int> bnd[2];
+        for (int f : idx)
+            for (int g : adj[f])
+                if (side[g] >= 0 && side[g] != side[f]) { bnd[side[f]].push_back(f); break; }
+        const std::vector<int> &sep = bnd[0].size() <= bnd[1].size() ? bnd[0] : bnd[1];
+        std::vector<char> in_sep(n, 0);
+        for (int f : sep) in_sep[f] = 1;
+        std::vector<int> part[2], s(sep);
+        for (int f : idx) if (!in_sep[f]) part[side[f]].push_back(f);
+        if (part[0].empty() || part[1].empty()) {           // degenerate cut: keep as one block if it fits
+            nodes[me].rows = idx;
+            if ((int)idx.size() > TS_MAX_NODE) err = "cannot split a block of " + std::to_string(idx.size()) + " rows";
+            return me;
+        }
+        if (!s.empty()) {                                   // order the separator along its own widest axis
+            const int sax = widest_axis(s, P);
+            std::stable_sort(s.begin(), s.end(), [&](int a, int b) { return pos(a)[sax] < pos(b)[sax]; });
+        }
+        nodes[me].rows = s;
+        for (int k = 0; k < 2; ++k) {
+            const int c = bisect(part[k], me);
+            nodes[me].children.push_back(c);
+        }
+        return me;
+    }
+
+    void postorder(int v, std::vector<int> &out) {
+        for (int c : nodes[v].children) postorder(c, out);
+        out.push_back(v);
+    }
+
+    // in-place inverse of a symmetric positive definite k x k matrix through its Cholesky factor;
+    // returns false when a pivot is not safely positive
+    static bool spd_inverse(std::vector<double> &a, int k, double pivot_floor) {
+        std::vector<double> l((size_t)k * k, 0.0);
+        for (int j = 0; j < k; ++j) {
+            double d = a[(size_t)j * k + j];
+            for (int q = 0; q < j; ++q) d -= l[(size_t)j * k + q] * l[(size_t)j * k + q];
+            if (!(d > pivot_floor)) return false;
+            const double ljj = std::sqrt(d);
+            l[(size_t)j * k + j] = ljj;
+            for (int i = j + 1; i < k; ++i) {
+                double s = a[(size_t)i * k + j];
+                for (int q = 0; q < j; ++q) s -= l[(size_t)i * k + q] * l[(size_t)j * k + q];
+                l[(size_t)i * k + j] = s / ljj;
+            }
+        }
+        // W = L^-1 (lower), then A^-1 = W^T W
+        std::vector<double> w((size_t)k * k, 0.0);
+        for (int c = 0; c < k; ++c) {
+            w[(size_t)c * k + c] = 1.0 / l[(size_t)c * k + c];
+            for (int i = c + 1; i < k; ++i) {
+                double s = 0.0;
+                for (int q = c; q < i; ++q) s -= l[(size_t)i * k + q] * w[(size_t)q * k + c];
+                w[(size_t)i * k + c] = s / l[(size_t)i * k + i];
+            }
+        }
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double s = 0.0;
+                for (int q = i; q < k; ++q) s += w[(size_t)q * k + i] * w[(size_t)q * k + j];
+                a[(size_t)i * k + j] = a[(size_t)j * k + i] = s;
+            }
+        return true;
+    }
+
+    bool factor(const std::vector<int> &post) {
+        std::vector<double> F((size_t)n * n, 0.0);
+        double max_diag = 0.0;
+        for (int c = 0; c < n; ++c)
+            for (int q = p.m_colptr[c]; q < p.m_colptr[c + 1]; ++q) {
+                const int r = p.m_rowidx[q];
+                F[(size_t)r * n + c] = F[(size_t)c * n + r] = p.m_val[q];
+                if (r == c) max_diag = std::max(max_diag, p.m_val[q]);
+            }
+        const double floor = 1e-9 * max_diag;               // the SIMT path pins such pivots (unconstrained templates)
+        for (int v : post) {
+            TNode &nd = nodes[v];
+            const int k = (int)nd.rows.size();
+            if (k == 0) continue;
+            nd.P.assign((size_t)k * k, 0.0);
+            for (int i = 0; i < k; ++i)
+                for (int j = 0; j < k; ++j) nd.P[(size_t)i * k + j] = F[(size_t)nd.rows[i] * n + nd.rows[j]];
+            if (!spd_inverse(nd.P, k, floor)) { err = "pivot below 1e-9 x max diagonal (singular / unconstrained system)"; return false; }
+            std::vector<int> brow;                           // coupled ancestor rows (free columns)
+            std::vector<double> gb, fb;                      // G and F restricted to them, |B| x k
+            for (int a : nd.anc) {
+                const TNode &an = nodes[a];
+                const int m = (int)an.rows.size();
+                Coupling c;
+                c.anc = a; c.r0 = m; c.r1 = 0;
+                std::vector<double> faj((size_t)m * k);
+                for (int i = 0; i < m; ++i) {
+                    bool nz = false;
+                    for (int j = 0; j < k; ++j) {
+                        const double x = F[(size_t)an.rows[i] * n + nd.rows[j]];
+                        faj[(size_t)i * k + j] = x;
+                        nz |= (x != 0.0);
+                    }
+                    if (nz) { c.r0 = std::min(c.r0, i); c.r1 = std::max(c.r1, i + 1); }
+                }
+                if (c.r1 <= c.r0) continue;
+                c.G.assign((size_t)m * k, 0.0);
+                for (int i = c.r0; i < c.r1; ++i) {
+                    bool nz = false;
+                    for (int j = 0; j < k; ++j) nz |= (faj[(size_t)i * k + j] != 0.0);
+                    if (!nz) continue;
+                    for (int j = 0; j < k; ++j) {
+                        double s = 0.0;
+                        for (int q = 0; q < k; ++q) s += faj[(size_t)i * k + q] * nd.P[(size_t)q * k + j];
+                        c.G[(size_t)i * k + j] = s;
+                    }
+                    brow.push_back(an.rows[i]);
+                    gb.insert(gb.end(), c.G.begin() + (size_t)i * k, c.G.begin() + (size_t)(i + 1) * k);
+                    fb.insert(fb.end(), faj.begin() + (size_t)i * k, faj.begin() + (size_t)(i + 1) * k);
+                }
+                nd.coup.push_back(std::move(c));
+            }
+            const int nb = (int)brow.size();                 // Schur update F_BB -= G_B F_BJ^T
+            for (int i = 0; i < nb; ++i)
+                for (int j = 0; j < nb; ++j) {
+                    double s = 0.0;
+                    for (int q = 0; q < k; ++q) s += gb[(size_t)i * k + q] * fb[(size_t)j * k + q];
+                    F[(size_t)brow[i] * n + brow[j]] -= s;
+                }
+        }
+        return true;
+    }
+
+    // ---------------------------------------------------------------- program emission
+    std::vector<int> epi_wait_op, mma_wait_op;              // op index in the other stream, -1 none
+    std::vector<char> epi_signals, mma_commits;
+    int last_epi_write[TS_TMEM_COLS], last_epi_read[TS_TMEM_COLS], last_mma_write[TS_TMEM_COLS], last_mma_read[TS_TMEM_COLS];
+    uint32_t chunk_fill = 0;
+
+    struct Range { int c0, c1; };
+
+    void add_epi(EpiOp op, std::vector<Range> reads, std::vector<Range> writes) {
+        int need = -1;
+        const int e = (int)t.epi.size();
+        for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) need = std::max(need, last_mma_write[c]);
+        for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) need = std::max(need, std::max(last_mma_write[c], last_mma_read[c]));
+        for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) last_epi_read[c] = e;
+        for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) last_epi_write[c] = e;
+        if (need >= 0) mma_commits[need] = 1;
+        epi_wait_op.push_back(need);
+        epi_signals.push_back(0);
+        op.wait_mma = op.signal_epi = -1;
+        t.epi.push_back(op);
+    }
+
+    // Bt(nn, kk) = element of the [N x K] tile (row nn of the product's output, kk of its source)
+    void add_mma(MmaOp op, const std::function<double(int, int)> &bt) {
+        const int m = (int)t.mma.size();
+        const int K = op.k8 * 8, N = op.n;
+        int need = -1;
+        for (int c = 0; c < K; ++c) need = std::max(need, std::max(last_epi_write[op.a_hi_col + c], last_epi_write[op.a_lo_col + c]));
+        for (int c = 0; c < N; ++c) need = std::max(need, std::max(last_epi_write[op.d_col + c], last_epi_read[op.d_col + c]));
+        for (int c = 0; c < K; ++c) last_mma_read[op.a_hi_col + c] = last_mma_read[op.a_lo_col + c] = m;
+        for (int c = 0; c < N; ++c) last_mma_write[op.d_col + c] = m;
+        if (need >= 0) epi_signals[need] = 1;
+        mma_wait_op.push_back(need);
+        mma_commits.push_back(0);
+        // tile images: K-blocks of 32, each an [N x 32] K-major SWIZZLE_128B image; hi then lo
+        const int kb = (K + 31) / 32;
+        const uint32_t half = (uint32_t)kb * N * 128, bytes = 2 * half;
+        if (t.chunk_off.empty()) { t.chunk_off.push_back(0); chunk_fill = 0; op.flags |= MMA_CHUNK_FIRST; }
+        else if (chunk_fill + bytes > (uint32_t)TS_STAGE_BYTES) {
+            t.mma.back().flags |= MMA_CHUNK_LAST;
+            t.chunk_off.push_back((uint32_t)t.matrix.size());
+            chunk_fill = 0;
+            op.flags |= MMA_CHUNK_FIRST;
+        }
+        op.b_hi_off = chunk_fill;
+        op.b_lo_off = chunk_fill + half;
+        chunk_fill += bytes;
+        const size_t base = t.matrix.size();
+        t.matrix.resize(base + bytes, 0);
+        float *hi = reinterpret_cast<float *>(t.matrix.data() + base), *lo = reinterpret_cast<float *>(t.matrix.data() + base + half);
+        for (int nn = 0; nn < N; ++nn)
+            for (int kk = 0; kk < K; ++kk) {
+                const double v = bt(nn, kk);
+                if (v == 0.0) continue;
+                const float h = rn_tf32((float)v), l = rn_tf32((float)(v - (double)h));
+                const int at = (kk / 32) * (N * 32) + ts_swz(nn, kk % 32);
+                hi[at] = h;
+                lo[at] = l;
+            }
+        op.wait_epi = op.commit_mma = -1;
+        t.mma.push_back(op);
+        t.nk_products += (long long)N * K;
+    }
+
+    bool emit(const std::vector<int> &post) {
+        std::fill(last_epi_write, last_epi_write + TS_TMEM_COLS, -1);
+        std::fill(last_epi_read, last_epi_read + TS_TMEM_COLS, -1);
+        std::fill(last_mma_write, last_mma_write + TS_TMEM_COLS, -1);
+        std::fill(last_mma_read, last_mma_read + TS_TMEM_COLS, -1);
+        std::vector<int> steps;
+        int kmax = 0, nmax = 0, acc_cols = 0, xs_cols = 0;
+        for (int v : post) {
+            const int k = (int)nodes[v].rows.size();
+            if (k == 0) continue;
+            steps.push_back(v);
+            kmax = std::max(kmax, pad_to(k, 8));
+            nmax = std::max(nmax, pad_to(k, 16));
+            if (!nodes[v].children.empty()) {
+                acc_cols = std::max(acc_cols, nodes[v].acc_off + pad_to(k, 16));
+                xs_cols = std::max(xs_cols, nodes[v].xs_off + pad_to(k, 8));
+            }
+        }
+        // ---- tensor-memory maps
+        const int s0 = acc_cols;
+        int n_slots = 2;
+        if (s0 + n_slots * 2 * kmax + nmax > TS_TMEM_COLS) n_slots = 1;
+        const int du = pad_to(s0 + n_slots * 2 * kmax, 16);
+        t.tmem_fwd = du + nmax;
+        if (t.tmem_fwd > TS_TMEM_COLS) { err = "forward sweep needs " + std::to_string(t.tmem_fwd) + " tensor-memory columns"; return false; }
+        const int dx0 = pad_to(2 * xs_cols, 16);
+        const int ring = std::min(3, (TS_TMEM_COLS - dx0) / std::max(nmax, 1));
+        if (ring < 1) { err = "backward sweep needs " + std::to_string(dx0 + nmax) + " tensor-memory columns"; return false; }
+        t.tmem_bwd = dx0 + ring * nmax;
+        auto slot_hi = [&](int k) { return s0 + k * 2 * kmax; };
+        auto slot_lo = [&](int k) { return s0 + k * 2 * kmax + kmax; };
+
+        // ---- forward sweep
+        std::vector<char> inited(nodes.size(), 0);
+        auto emit_prep = [&](int i) {
+            const TNode &nd = nodes[steps[i]];
+            for (auto it = nd.anc.rbegin(); it != nd.anc.rend(); ++it) {
+                const TNode &an = nodes[*it];
+                if (inited[*it] || an.rows.empty()) continue;
+                inited[*it] = 1;
+                EpiOp op{};
+                op.flags = EPI_ADD_GLOBAL | EPI_ST_RAW;
+                op.n_chunks = (uint16_t)(pad_to((int)an.rows.size(), 16) / 8);
+                op.n_valid = (uint16_t)an.rows.size();
+                op.hi_col = (uint16_t)an.acc_off;
+                op.row_in = (uint32_t)an.row0;
+                add_epi(op, {}, {{an.acc_off, an.acc_off + op.n_chunks * 8}});
+            }
+            const int k = (int)nd.rows.size(), k8 = pad_to(k, 8), sl = i % n_slots;
+            EpiOp op{};
+            op.n_chunks = (uint16_t)(k8 / 8);
+            op.n_valid = (uint16_t)k;
+            op.hi_col = (uint16_t)slot_hi(sl);
+            op.lo_col = (uint16_t)slot_lo(sl);
+            std::vector<Range> rd;
+            if (nd.children.empty()) {
+                op.flags = EPI_ADD_GLOBAL | EPI_ST_SPLIT;
+                op.row_in = (uint32_t)nd.row0;
+            } else {
+                op.flags = EPI_FROM_TMEM | EPI_ST_SPLIT;
+                op.src_col = (uint16_t)nd.acc_off;
+                rd.push_back({nd.acc_off, nd.acc_off + k8});
+            }
+            add_epi(op, rd, {{slot_hi(sl), slot_hi(sl) + k8}, {slot_lo(sl), slot_lo(sl) + k8}});
+        };
+        const int ns = (int)steps.size();
+        if (ns == 0) { err = "empty system"; return false; }
+        emit_prep(0);
+        for (int i = 0; i < ns; ++i) {
+            const TNode &nd = nodes[steps[i]];
+            const int k = (int)nd.rows.size(), k8 = pad_to(k, 8), sl = i % n_slots;
+            for (const Coupling &c : nd.coup) {
+                const TNode &an = nodes[c.anc];
+                const int m = (int)an.rows.size();
+                const int w0 = c.r0 / 16 * 16, w1 = pad_to(c.r1, 16);
+                MmaOp op{};
+                op.d_col = (uint16_t)(an.acc_off + w0);
+                op.a_hi_col = (uint16_t)slot_hi(sl);
+                op.a_lo_col = (uint16_t)slot_lo(sl);
+                op.n = (uint16_t)(w1 - w0);
+                op.k8 = (uint16_t)(k8 / 8);
+                op.flags = MMA_ACCUMULATE;
+                add_mma(op, [&](int nn, int kk) { return (w0 + nn < m && kk < k) ? -c.G[(size_t)(w0 + nn) * k + kk] : 0.0; });
+            }
+            {
+                MmaOp op{};
+                op.d_col = (uint16_t)du;
+                op.a_hi_col = (uint16_t)slot_hi(sl);
+                op.a_lo_col = (uint16_t)slot_lo(sl);
+                op.n = (uint16_t)pad_to(k, 16);
+                op.k8 = (uint16_t)(k8 / 8);
+                add_mma(op, [&](int nn, int kk) { return (nn < k && kk < k) ? nd.P[(size_t)nn * k + kk] : 0.0; });
+            }
+            if (i + 1 < ns) emit_prep(i + 1);
+            EpiOp op{};
+            op.flags = EPI_FROM_TMEM | EPI_STORE_GLOBAL;
+            op.n_chunks = (uint16_t)(k8 / 8);
+            op.n_valid = (uint16_t)k;
+            op.src_col = (uint16_t)du;
+            op.row_out = (uint32_t)nd.row0;
+            add_epi(op, {{du, du + k8}}, {});
+        }
+        // ---- backward sweep (reverse post-order: every node after its ancestors)
+        int ri = 0;
+        for (int i = ns - 1; i >= 0; --i) {
+            const TNode &nd = nodes[steps[i]];
+            const int k = (int)nd.rows.size(), k8 = pad_to(k, 8);
+            const int dx = dx0 + (ri % ring) * nmax;
+            bool first = true;
+            for (const Coupling &c : nd.coup) {
+                const TNode &an = nodes[c.anc];
+                const int m = (int)an.rows.size();
+                const int k0 = c.r0 / 8 * 8, k1 = pad_to(c.r1, 8);
+                MmaOp op{};
+                op.d_col = (uint16_t)dx;
+                op.a_hi_col = (uint16_t)(an.xs_off + k0);
+                op.a_lo_col = (uint16_t)(xs_cols + an.xs_off + k0);
+                op.n = (uint16_t)pad_to(k, 16);
+                op.k8 = (uint16_t)((k1 - k0) / 8);
+                op.flags = first ? 0 : MMA_ACCUMULATE;
+                first = false;
+                add_mma(op, [&](int nn, int kk) { return (nn < k && k0 + kk < m) ? -c.G[(size_t)(k0 + kk) * k + nn] : 0.0; });
+            }
+            EpiOp op{};
+            op.flags = EPI_ADD_GLOBAL | EPI_STORE_GLOBAL;
+            op.n_chunks = (uint16_t)(k8 / 8);
+            op.n_valid = (uint16_t)k;
+            op.row_in = op.row_out = (uint32_t)nd.row0;
+            std::vector<Range> rd, wr;
+            if (!first) {
+                op.flags |= EPI_FROM_TMEM;
+                op.src_col = (uint16_t)dx;
+                rd.push_back({dx, dx + k8});
+                ++ri;
+            }
+            if (!nd.children.empty()) {
+                op.flags |= EPI_ST_SPLIT;
+                op.hi_col = (uint16_t)nd.xs_off;
+                op.lo_col = (uint16_t)(xs_cols + nd.xs_off);
+                wr.push_back({nd.xs_off, nd.xs_off + k8});
+                wr.push_back({xs_cols + nd.xs_off, xs_cols + nd.xs_off + k8});
+            }
+            add_epi(op, rd, wr);
+        }
+        if (!t.mma.empty()) t.mma.back().flags |= MMA_CHUNK_LAST;
+        t.chunk_off.push_back((uint32_t)t.matrix.size());
+        // the tile boundary is a full synchronisation: the last EPI op must wait for the last MMA op
+        if (!t.mma.empty()) {
+            const int last = (int)t.mma.size() - 1;
+            if (epi_wait_op.back() < last) {
+                // only possible if the final node had no couplings; wait for everything anyway
+                epi_wait_op.back() = last;
+                mma_commits[last] = 1;
+            }
+        }
+        // ---- events
+        std::vector<int> mma_evt(t.mma.size(), -1), epi_evt(t.epi.size(), -1);
+        for (size_t m = 0; m < t.mma.size(); ++m) if (mma_commits[m]) mma_evt[m] = t.n_mma_events++;
+        for (size_t e = 0; e < t.epi.size(); ++e) if (epi_signals[e]) epi_evt[e] = t.n_epi_events++;
+        if (t.n_mma_events > TS_MAX_EVENTS || t.n_epi_events > TS_MAX_EVENTS) { err = "too many synchronisation events"; return false; }
+        for (size_t m = 0; m < t.mma.size(); ++m) {
+            t.mma[m].commit_mma = (int16_t)mma_evt[m];
+            t.mma[m].wait_epi = (int16_t)(mma_wait_op[m] >= 0 ? epi_evt[mma_wait_op[m]] : -1);
+        }
+        for (size_t e = 0; e < t.epi.size(); ++e) {
+            t.epi[e].signal_epi = (int16_t)epi_evt[e];
+            t.epi[e].wait_mma = (int16_t)(epi_wait_op[e] >= 0 ? mma_evt[epi_wait_op[e]] : -1);
+        }
+        return true;
+    }
+
+    bool run() {
+        if (n > 2560) { err = "more than 2560 unknowns (dense block elimination not attempted)"; return false; }
+        adj.assign(n, {});
+        for (int c = 0; c < n; ++c)
+            for (int q = p.m_colptr[c]; q < p.m_colptr[c + 1]; ++q) {
+                const int r = p.m_rowidx[q];
+                if (r != c) { adj[r].push_back(c); adj[c].push_back(r); }
+            }
+        std::vector<int> all(n);
+        std::iota(all.begin(), all.end(), 0);
+        const int root = bisect(all, -1);
+        if (!err.empty()) return false;
+        std::vector<int> post;
+        postorder(root, post);
+        int row = 0;
+        t.row_of_free.assign(n, -1);
+        t.free_of_row.assign(n, -1);
+        for (int v : post) {
+            TNode &nd = nodes[v];
+            if ((int)nd.rows.size() > TS_MAX_NODE) { err = "tree node of " + std::to_string(nd.rows.size()) + " rows"; return false; }
+            nd.row0 = row;
+            for (int f : nd.rows) { t.row_of_free[f] = row; t.free_of_row[row] = f; ++row; }
+            for (int a = nd.parent; a >= 0; a = nodes[a].parent) nd.anc.push_back(a);
+            for (int a : nd.anc) {
+                nd.acc_off += pad_to((int)nodes[a].rows.size(), 16);
+                nd.xs_off += pad_to((int)nodes[a].rows.size(), 8);
+            }
+            t.n_leaves += nd.children.empty();
+        }
+        t.n_nodes = (int)nodes.size();
+        if (!factor(post)) return false;
+        return emit(post);
+    }
+};
+
+}  // namespace
+
+void build_tensor_plan(HostPlan &p, int leaf_max) {
+    p.tplan = TensorPlan();
+    leaf_max = std::max(8, std::min(leaf_max, TS_MAX_NODE));
+    Builder b(p, leaf_max);
+    if (b.run()) p.tplan.valid = true;
+    else {
+        std::string why = b.err;
+        p.tplan = TensorPlan();
+        p.tplan.why_not = why;
+    }
+}
+
+}  // namespace sdfa

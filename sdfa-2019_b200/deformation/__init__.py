@@ -27,6 +27,7 @@ viewer/video.py:220-277 should call instead of one frame at a time):
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -68,7 +69,9 @@ class Reconstructor:
     ``device=-1`` keeps everything on the host for plan inspection; compute calls then raise.
     """
 
-    def __init__(self, verts, faces, cnsts=(), corrs=(), reg=1e-10, device=None):
+    def __init__(self, verts, faces, cnsts=(), corrs=(), reg=1e-10, device=None, solver=None):
+        """``solver``: None = tensor-core solve when the template fits it, else the SIMT sweeps;
+        "simt" / "tensor" force one (same as the SDFA_SOLVER environment variable)."""
         V = _f32c(verts, "verts")
         F = _u32c(faces)
         c = _u32c(cnsts).reshape(-1)
@@ -83,8 +86,18 @@ class Reconstructor:
         self.device = _default_device() if device is None else int(device)
         self._h = ctypes.c_void_p()
         self._verts, self._faces, self._cnsts = V, F, c
-        check(lib.sdfa_create(ctypes.byref(self._h), ptr(V), len(V), ptr(F), len(F), ptr(c) if c.size else None,
-                              len(c), ptr(cc) if cc.size else None, float(reg), self.device))
+        prev = os.environ.get("SDFA_SOLVER")
+        if solver is not None:
+            os.environ["SDFA_SOLVER"] = solver
+        try:
+            check(lib.sdfa_create(ctypes.byref(self._h), ptr(V), len(V), ptr(F), len(F), ptr(c) if c.size else None,
+                                  len(c), ptr(cc) if cc.size else None, float(reg), self.device))
+        finally:
+            if solver is not None:
+                if prev is None:
+                    os.environ.pop("SDFA_SOLVER", None)
+                else:
+                    os.environ["SDFA_SOLVER"] = prev
         nf, ne, na, nnz = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
         check(lib.sdfa_info(self._h, None, None, None, ctypes.byref(nf), ctypes.byref(ne), ctypes.byref(na),
                             ctypes.byref(nnz)))

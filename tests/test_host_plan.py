@@ -13,6 +13,7 @@ import deformation as D
 from deformation import _native, workloads as W
 from oracle.dgrad_oracle import TriangleDeformationOracle
 from tests import plan_emulator as E
+from tests import tplan_emulator as T
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
@@ -51,6 +52,12 @@ def test_argument_errors_raise(flame):
 
 @pytest.fixture(scope="module")
 def flame_rec(flame):
+    """SIMT solve plan (the sweeps of kernel K3); the tensor-core plan has its own fixture below."""
+    return D.Reconstructor(flame["V"], flame["F"], cnsts=flame["nfv"], device=-1, solver="simt")
+
+
+@pytest.fixture(scope="module")
+def flame_rec_tensor(flame):
     return D.Reconstructor(flame["V"], flame["F"], cnsts=flame["nfv"], device=-1)
 
 
@@ -118,7 +125,7 @@ def test_emulated_small_mesh_modes(golden_small):
     V, F, border = W.grid_mesh()
     dg = W.iid_dgrad(4, len(F), sigma=0.05, seed=7)
     tol = 1e-6 * W.bbox_diag(V)
-    r = D.Reconstructor(V, F, cnsts=border, device=-1)
+    r = D.Reconstructor(V, F, cnsts=border, device=-1, solver="simt")
     out, _ = E.solve(r, E.assemble(r, dg))
     assert np.abs(out - golden_small["cnst_verts"]).max() < tol
     # raw matrices
@@ -131,12 +138,12 @@ def test_emulated_small_mesh_modes(golden_small):
     out, _ = E.solve(r, E.assemble(r, dg[:1]), cnst_pos=Cm)
     assert np.abs(out[0] - golden_small["moved_cnst_verts"]).max() < tol
     # single constraint
-    r1 = D.Reconstructor(V, F, cnsts=[5], device=-1)
+    r1 = D.Reconstructor(V, F, cnsts=[5], device=-1, solver="simt")
     out, _ = E.solve(r1, E.assemble(r1, dg[1:2]))
     assert np.abs(out[0] - golden_small["one_cnst_verts"]).max() < 5 * tol    # cond ~1e8: fp32 sweeps
     # correspondences
     cc, cf = golden_small["corr_count"], golden_small["corr_faces"]
-    rc = D.Reconstructor(V, F, cnsts=border, corrs=cc, device=-1)
+    rc = D.Reconstructor(V, F, cnsts=border, corrs=cc, device=-1, solver="simt")
     rc.set_correspondences(cc, cf, n_src_tris=11)
     src = W.iid_dgrad(1, 11, sigma=0.05, seed=9)
     out, _ = E.solve(rc, E.assemble(rc, src))
@@ -156,7 +163,7 @@ def test_emulated_unconstrained_is_pinned(golden_small):
 def test_emulated_tile_boundaries():
     """33 frames = one full tile + a 1-frame tile; every frame must equal its single-frame result."""
     V, F, border = W.grid_mesh()
-    r = D.Reconstructor(V, F, cnsts=border, device=-1)
+    r = D.Reconstructor(V, F, cnsts=border, device=-1, solver="simt")
     dg = W.iid_dgrad(33, len(F), sigma=0.05, seed=3)
     out, _ = E.solve(r, E.assemble(r, dg))
     one, _ = E.solve(r, E.assemble(r, dg[32:33]))
@@ -179,3 +186,82 @@ def test_emulated_config5_picks_smaller_tiles():
     out, _ = E.solve(r, E.assemble(r, dg))
     ref = o.get_mesh(dg[0].astype(np.float64), vert_cnsts=V[c])
     assert np.abs(out[0] - ref).max() <= 0.2e-6 * W.bbox_diag(V)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core solve plan (csrc/tplan.cpp -> kernel K3T): interpreted by tests/tplan_emulator.py
+
+def test_tensor_plan_budget(flame_rec_tensor):
+    st = flame_rec_tensor.debug("ts_stats")
+    used, valid, n_mma, n_epi, n_chunks, nbytes, ev_m, ev_e, n_nodes, n_leaves, nk, t_f, t_b, smem = [int(x) for x in st]
+    assert used == 1 and valid == 1
+    assert t_f <= 512 and t_b <= 512 and ev_m <= 256 and ev_e <= 256 and smem <= 227 * 1024
+    assert nk <= 300_000                      # N*K summed over the products of one 128-column tile
+    rows = flame_rec_tensor.debug("scratch_row")
+    assert sorted(rows) == list(range(flame_rec_tensor.n_free))
+    mma = flame_rec_tensor.debug("ts_mma").view(T.MMA_DT)
+    assert (mma["n"] % 16 == 0).all() and (mma["n"] <= 64).all() and (mma["k8"] >= 1).all() and (mma["k8"] <= 8).all()
+    assert (mma["d_col"] % 16 == 0).all() and (mma["a_hi_col"] % 8 == 0).all() and (mma["a_lo_col"] % 8 == 0).all()
+    assert (mma["b_hi_off"] % 1024 == 0).all() and (mma["b_lo_off"] % 1024 == 0).all()
+
+
+def test_tensor_emulated_flame_frames_match_oracle(flame_rec_tensor, flame, golden_flame):
+    V, F, nfv = flame["V"], flame["F"], flame["nfv"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    dg = W.iid_dgrad(2, len(F), sigma=0.01, seed=0)
+    rhs = E.assemble(flame_rec_tensor, dg)
+    first = None
+    for seed in (0, 1, 2, 3):                 # different interleavings of the two instruction streams
+        out = T.solve(flame_rec_tensor, rhs, seed=seed)
+        assert not np.isnan(out).any()
+        for i in range(2):
+            assert np.abs(out[i][free] - golden_flame["iid_free_verts"][i]).max() < 0.1 * flame["tol"]
+            assert np.array_equal(out[i][nfv], V[nfv])
+        if first is None:
+            first = out
+        assert np.array_equal(out, first)     # the result does not depend on the interleaving
+
+
+def test_tensor_emulated_large_deformation(flame_rec_tensor, flame, golden_flame):
+    V, F, nfv, nft = flame["V"], flame["F"], flame["nfv"], flame["nft"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    active = np.setdiff1d(np.arange(len(F)), nft)
+    full = np.zeros((1, len(F), 9), dtype=np.float32)
+    full[0, active] = golden_flame["integ30_dgrad_active"]
+    out = T.solve(flame_rec_tensor, E.assemble(flame_rec_tensor, full.reshape(1, -1)))
+    assert np.abs(out[0][free] - golden_flame["integ30_free_verts"]).max() < 0.25 * flame["tol"]
+
+
+def test_tensor_emulated_small_mesh_modes(golden_small):
+    V, F, border = W.grid_mesh()
+    dg = W.iid_dgrad(4, len(F), sigma=0.05, seed=7)
+    tol = 1e-6 * W.bbox_diag(V)
+    for leaf in ("64", "8"):                  # one leaf, and a real tree on the 35 unknowns
+        os.environ["SDFA_TS_LEAF"] = leaf
+        try:
+            r = D.Reconstructor(V, F, cnsts=border, device=-1, solver="tensor")
+        finally:
+            del os.environ["SDFA_TS_LEAF"]
+        out = T.solve(r, E.assemble(r, dg))
+        assert np.abs(out - golden_small["cnst_verts"]).max() < tol
+        Cm = (V[border] + np.float32(0.001)).astype(np.float32)
+        r.set_constraint_positions(Cm)
+        out = T.solve(r, E.assemble(r, dg[:1]), cnst_pos=Cm)
+        assert np.abs(out[0] - golden_small["moved_cnst_verts"]).max() < tol
+    cc, cf = golden_small["corr_count"], golden_small["corr_faces"]
+    rc = D.Reconstructor(V, F, cnsts=border, corrs=cc, device=-1, solver="tensor")
+    rc.set_correspondences(cc, cf, n_src_tris=11)
+    src = W.iid_dgrad(1, 11, sigma=0.05, seed=9)
+    out = T.solve(rc, E.assemble(rc, src))
+    assert np.abs(out[0] - golden_small["corr_verts"]).max() < tol
+
+
+def test_tensor_plan_declines_what_it_cannot_do():
+    V, F, _ = W.grid_mesh()
+    r = D.Reconstructor(V, F, device=-1)                          # unconstrained: singular system, pinned pivots
+    assert r.debug("ts_stats")[0] == 0 and b"pivot" in bytes(r.debug("ts_why_not"))
+    with pytest.raises(D.SdfaError):
+        D.Reconstructor(V, F, device=-1, solver="tensor")
+    V, F, c = W.flame_sub2()
+    r = D.Reconstructor(V, F, cnsts=c, device=-1)                 # config 5: 20 653 unknowns -> SIMT sweeps
+    assert r.debug("ts_stats")[0] == 0 and b"unknowns" in bytes(r.debug("ts_why_not"))
