@@ -12,9 +12,10 @@
 // A_hi B_hi + A_lo B_hi + A_hi B_lo into the fp32 accumulator.
 //
 // One persistent CTA per SM loops over 128-column tiles of scratch[tile][row][128]; warp roles:
-//   warp 0   streamer : matrix chunks -> ring (mbarrier full / empty)
-//   warp 1   issuer   : one thread walks the MmaOp stream
-//   warps 2-5 epilogue: thread = column = tensor-memory lane, walks the EpiOp stream
+//   warp 0   streamer  : matrix chunks -> ring (mbarrier full / empty)
+//   warp 1   issuer    : one thread walks the MmaOp stream
+//   warp 2   row loader: the scratch rows the EpiOp stream will add, TMA bulk copies into a second ring, ops ahead
+//   warps 3-6 epilogue : thread = column = tensor-memory lane, walks the EpiOp stream
 // The two streams synchronise through single-use-per-tile mbarrier events chosen by the planner.
 #include "device_plan.hpp"
 
@@ -22,8 +23,10 @@ namespace sdfa {
 
 namespace {
 
-constexpr int TS_RING = 4;
-constexpr int TS_THREADS = 32 * 6;
+constexpr int TS_RING = 3;                     // matrix ring stages (32 KB each)
+constexpr int TS_ROWRING = 3;                  // scratch-row ring stages (<= 64 rows x 128 columns each)
+constexpr int TS_ROWSTAGE_BYTES = TS_MAX_NODE * TS_COLS * 4;
+constexpr int TS_THREADS = 32 * 7;             // streamer, issuer, row loader, 4 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -86,6 +89,7 @@ struct TsParams {
     int n_mma, n_epi, n_chunks, n_mma_events, n_epi_events;
     float *scratch;            // [n_tiles][n_rows][128]
     int n_rows, n_tiles;
+    long long *prof;           // optional timeline of CTA 0's second tile: 3 clocks per EPI op, then 3 per MMA op
 };
 
 // instruction descriptor: D fp32, A / B tf32, both K-major, M = 128; N is filled in per op
@@ -96,8 +100,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B images: 1024-byte aligned
     uint8_t *ring = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TS_RING * TS_STAGE_BYTES);
-    uint64_t *bar_full = bars, *bar_empty = bars + TS_RING, *bar_mma = bars + 2 * TS_RING, *bar_epi = bar_mma + TS_MAX_EVENTS;
+    float *rowring = reinterpret_cast<float *>(smem + TS_RING * TS_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TS_RING * TS_STAGE_BYTES + TS_ROWRING * TS_ROWSTAGE_BYTES);
+    uint64_t *bar_full = bars, *bar_empty = bars + TS_RING, *bar_rfull = bars + 2 * TS_RING, *bar_rempty = bar_rfull + TS_ROWRING;
+    uint64_t *bar_fwd = bar_rempty + TS_ROWRING, *bar_mma = bar_fwd + 1, *bar_epi = bar_mma + TS_MAX_EVENTS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_epi + TS_MAX_EVENTS);
     MmaOp *mma_sm = reinterpret_cast<MmaOp *>(tmem_slot + 4);
     EpiOp *epi_sm = reinterpret_cast<EpiOp *>(mma_sm + P.n_mma);
@@ -109,6 +115,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
         reinterpret_cast<uint32_t *>(epi_sm)[i] = reinterpret_cast<const uint32_t *>(P.epi)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < TS_RING; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 1); }
+        for (int s = 0; s < TS_ROWRING; ++s) { mbar_init(smem_u32(bar_rfull + s), 1); mbar_init(smem_u32(bar_rempty + s), 4); }
+        mbar_init(smem_u32(bar_fwd), 4);
         for (int e = 0; e < P.n_mma_events; ++e) mbar_init(smem_u32(bar_mma + e), 1);     // tcgen05.commit
         for (int e = 0; e < P.n_epi_events; ++e) mbar_init(smem_u32(bar_epi + e), 4);     // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,10 +130,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
 
     if (warp == 0) {
         // ------------------------------------------------------------------ streamer
-        if (lane == 0) {
+        if (leader) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
                 for (int c = 0; c < P.n_chunks; ++c, ++it) {
@@ -138,13 +148,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (leader) {
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t par = tcount & 1u;
                 uint32_t stage = 0, slot = 0;
+                const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1;
                 for (int m = 0; m < P.n_mma; ++m) {
                     const MmaOp op = mma_sm[m];
+                    if (prof) P.prof[3 * (P.n_epi + m)] = clock64();
                     if (op.wait_epi >= 0) {
                         mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
                         tc_fence_after();
@@ -155,6 +167,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                         tc_fence_after();
                         stage = smem_u32(ring + slot * TS_STAGE_BYTES);
                     }
+                    if (prof) P.prof[3 * (P.n_epi + m) + 1] = clock64();
                     const uint32_t idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
                     const uint32_t d = tmem_base + op.d_col, a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
                     const uint32_t kb_bytes = (uint32_t)op.n * 128u;
@@ -169,6 +182,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     }
                     if (op.flags & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
                     if (op.commit_mma >= 0) tc_commit(smem_u32(bar_mma + op.commit_mma));
+                    if (prof) P.prof[3 * (P.n_epi + m) + 2] = clock64();
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ row loader
+        if (leader) {
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
+                const float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS;
+                for (int e = 0; e < P.n_epi; ++e) {
+                    const EpiOp op = epi_sm[e];
+                    if (!(op.flags & EPI_ADD_GLOBAL)) continue;
+                    // rows stored earlier in this tile (the forward sweep's u) are only read by the backward sweep:
+                    // wait until the epilogue has made them visible to the async proxy
+                    if (op.flags & EPI_AFTER_STORES) mbar_wait(smem_u32(bar_fwd), tcount & 1u);
+                    const uint32_t s = it % TS_ROWRING, ph = (it / TS_ROWRING) & 1u;
+                    mbar_wait(smem_u32(bar_rempty + s), ph ^ 1u);
+                    const uint32_t bytes = (uint32_t)op.n_valid * TS_COLS * 4u;
+                    mbar_arrive_expect_tx(smem_u32(bar_rfull + s), bytes);
+                    tma_bulk_g2s(smem_u32(rowring + (size_t)s * (TS_ROWSTAGE_BYTES / 4)), sc + (size_t)op.row_in * TS_COLS, bytes,
+                                 smem_u32(bar_rfull + s));
+                    ++it;
                 }
             }
         }
@@ -177,21 +213,28 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
         const int lane_grp = warp & 3;                               // tensor-memory lanes 32*lane_grp.. belong to this warp
         const int col = lane_grp * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        uint32_t tcount = 0;
+        uint32_t tcount = 0, lit = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t par = tcount & 1u;
             float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS + col;
+            const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1 && threadIdx.x == 96;
 #pragma unroll 1
             for (int e = 0; e < P.n_epi; ++e) {
                 const EpiOp op = epi_sm[e];
+                if (prof) P.prof[3 * e] = clock64();
                 const int nch = op.n_chunks, nv = op.n_valid;
                 float g[TS_MAX_CHUNKS8][8];
-                if (op.flags & EPI_ADD_GLOBAL) {                     // issue the global loads before waiting
-                    const float *src = sc + (size_t)op.row_in * TS_COLS;
+                if (op.flags & EPI_ADD_GLOBAL) {                     // the rows are (being) staged in the row ring
+                    const uint32_t s = lit % TS_ROWRING;
+                    mbar_wait(smem_u32(bar_rfull + s), (lit / TS_ROWRING) & 1u);
+                    const float *src = rowring + (size_t)s * (TS_ROWSTAGE_BYTES / 4) + col;
 #pragma unroll
                     for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) g[c][i] = (c < nch && c * 8 + i < nv) ? src[(size_t)(c * 8 + i) * TS_COLS] : 0.f;
+                        for (int i = 0; i < 8; ++i) g[c][i] = (c * 8 + i < nv) ? src[(c * 8 + i) * TS_COLS] : 0.f;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(bar_rempty + s));
+                    ++lit;
                 } else {
 #pragma unroll
                     for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
@@ -202,16 +245,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     mbar_wait(smem_u32(bar_mma + op.wait_mma), par);
                     tc_fence_after();
                 }
+                if (prof) P.prof[3 * e + 1] = clock64();
                 if (op.flags & EPI_FROM_TMEM) {
+                    uint32_t v[TS_MAX_CHUNKS8][8];
 #pragma unroll
                     for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
-                        if (c < nch) {
-                            uint32_t v[8];
-                            tmem_ld8(tlane + op.src_col + 8 * c, v);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (c < nch) tmem_ld8(tlane + op.src_col + 8 * c, v[c]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) g[c][i] = (c * 8 + i < nv) ? g[c][i] + __uint_as_float(v[i]) : 0.f;
-                        }
+                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (c < nch) g[c][i] = (c * 8 + i < nv) ? g[c][i] + __uint_as_float(v[c][i]) : 0.f;
                 }
                 if (op.flags & EPI_STORE_GLOBAL) {
                     float *dst = sc + (size_t)op.row_out * TS_COLS;
@@ -219,7 +264,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (c < nch && c * 8 + i < nv) dst[(size_t)(c * 8 + i) * TS_COLS] = g[c][i];
+                            if (c * 8 + i < nv) __stcg(dst + (size_t)(c * 8 + i) * TS_COLS, g[c][i]);
+                    if (op.flags & EPI_LAST_FWD_STORE) {             // hand the forward sweep's rows to the row loader
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(bar_fwd));
+                    }
                 }
                 if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT)) {
                     const bool split = (op.flags & EPI_ST_SPLIT) != 0;
@@ -243,6 +293,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(bar_epi + op.signal_epi));
                 }
+                if (prof) P.prof[3 * e + 2] = clock64();
             }
         }
     }
@@ -257,7 +308,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
 }  // namespace
 
 size_t solve_tc_smem_bytes(int n_mma, int n_epi) {
-    return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)(2 * TS_RING + 2 * TS_MAX_EVENTS) * 8 + 16 +
+    return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)TS_ROWRING * TS_ROWSTAGE_BYTES +
+           (size_t)(2 * TS_RING + 2 * TS_ROWRING + 1 + 2 * TS_MAX_EVENTS) * 8 + 16 +
            (size_t)n_mma * sizeof(MmaOp) + (size_t)n_epi * sizeof(EpiOp);
 }
 
@@ -274,7 +326,7 @@ cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, c
     }
     const int n_tiles = 3 * ((n_frames + TS_COLS - 1) / TS_COLS);
     TsParams P{d.ts_mma, d.ts_epi, d.ts_matrix, d.ts_chunk_off, d.ts_n_mma, d.ts_n_epi, d.ts_n_chunks,
-               d.ts_n_mma_events, d.ts_n_epi_events, scratch, d.n_free, n_tiles};
+               d.ts_n_mma_events, d.ts_n_epi_events, scratch, d.n_free, n_tiles, d.solve_prof};
     int grid = d.sm_count;
     if (grid > n_tiles) grid = n_tiles;
     k_solve_tc<<<grid, TS_THREADS, smem, stream>>>(P);

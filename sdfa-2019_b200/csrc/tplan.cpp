@@ -375,6 +375,7 @@ struct Builder {
             op.n_valid = (uint16_t)k;
             op.src_col = (uint16_t)du;
             op.row_out = (uint32_t)nd.row0;
+            if (i == ns - 1) op.flags |= EPI_LAST_FWD_STORE;
             add_epi(op, {{du, du + k8}}, {});
         }
         // ---- backward sweep (reverse post-order: every node after its ancestors)
@@ -399,7 +400,7 @@ struct Builder {
                 add_mma(op, [&](int nn, int kk) { return (nn < k && k0 + kk < m) ? -c.G[(size_t)(k0 + kk) * k + nn] : 0.0; });
             }
             EpiOp op{};
-            op.flags = EPI_ADD_GLOBAL | EPI_STORE_GLOBAL;
+            op.flags = EPI_ADD_GLOBAL | EPI_STORE_GLOBAL | (i == ns - 1 ? EPI_AFTER_STORES : 0);
             op.n_chunks = (uint16_t)(k8 / 8);
             op.n_valid = (uint16_t)k;
             op.row_in = op.row_out = (uint32_t)nd.row0;

@@ -41,6 +41,8 @@ enum EpiFlags : uint16_t {
     EPI_STORE_GLOBAL = 4,     // scratch[row_out + i] = v
     EPI_ST_RAW       = 8,     // tmem[hi_col + i] = v
     EPI_ST_SPLIT     = 16,    // tmem[hi_col + i] = tf32(v), tmem[lo_col + i] = tf32(v - tf32(v))
+    EPI_LAST_FWD_STORE = 32,  // the forward sweep's last store: after it the rows it wrote may be bulk-loaded
+    EPI_AFTER_STORES = 64,    // the first op that adds rows stored earlier in the tile (start of the backward sweep)
 };
 
 struct EpiOp {                // 32 bytes
