@@ -263,7 +263,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             if ((r = upload_base(h))) return r;
             if ((r = upload_eq_src(h))) return r;
             if (std::getenv("SDFA_SOLVE_PROFILE")) {
-                std::vector<long long> zero(std::max((size_t)h->dev.sm_count * 4 * 8, 3 * (p.tplan.mma.size() + p.tplan.epi.size())), 0);
+                std::vector<long long> zero(std::max((size_t)h->dev.sm_count * 4 * 8, (3 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
                 if ((r = upload_mut(h, zero, &d.solve_prof))) return r;
             }
             return SDFA_OK;
@@ -713,7 +713,7 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
         return give(b, dst, cap);
     }
     if (w == "solve_prof") {
-        std::vector<long long> v(std::max((size_t)h->dev.sm_count * 4 * 8, 3 * (p.tplan.mma.size() + p.tplan.epi.size())), 0);
+        std::vector<long long> v(std::max((size_t)h->dev.sm_count * 4 * 8, (3 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
         if (h->dev.solve_prof) cudaMemcpy(v.data(), h->dev.solve_prof, v.size() * 8, cudaMemcpyDeviceToHost);
         return give(v, dst, cap);
     }

@@ -15,7 +15,9 @@
 //   warp 0   streamer  : matrix chunks -> ring (mbarrier full / empty)
 //   warp 1   issuer    : one thread walks the MmaOp stream
 //   warp 2   row loader: the scratch rows the EpiOp stream will add, TMA bulk copies into a second ring, ops ahead
-//   warps 3-6 epilogue : thread = column = tensor-memory lane, walks the EpiOp stream
+//   warp 3   row storer: bulk-stores the rows an op has written into its ring stage, then frees the stage
+//   warps 4-11 epilogue: thread = column = tensor-memory lane (two warps per lane quarter split an op's chunks),
+//                        walks the EpiOp stream
 // The two streams synchronise through single-use-per-tile mbarrier events chosen by the planner.
 #include "device_plan.hpp"
 
@@ -26,7 +28,8 @@ namespace {
 constexpr int TS_RING = 3;                     // matrix ring stages (32 KB each)
 constexpr int TS_ROWRING = 3;                  // scratch-row ring stages (<= 64 rows x 128 columns each)
 constexpr int TS_ROWSTAGE_BYTES = TS_MAX_NODE * TS_COLS * 4;
-constexpr int TS_THREADS = 32 * 7;             // streamer, issuer, row loader, 4 epilogue warps
+constexpr int TS_EPI_WARPS = 8;                // two warps per tensor-memory lane quarter, each takes every other 8-column chunk
+constexpr int TS_THREADS = 32 * (4 + TS_EPI_WARPS);   // streamer, issuer, row loader, row storer, epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -103,7 +106,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     float *rowring = reinterpret_cast<float *>(smem + TS_RING * TS_STAGE_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TS_RING * TS_STAGE_BYTES + TS_ROWRING * TS_ROWSTAGE_BYTES);
     uint64_t *bar_full = bars, *bar_empty = bars + TS_RING, *bar_rfull = bars + 2 * TS_RING, *bar_rempty = bar_rfull + TS_ROWRING;
-    uint64_t *bar_fwd = bar_rempty + TS_ROWRING, *bar_mma = bar_fwd + 1, *bar_epi = bar_mma + TS_MAX_EVENTS;
+    uint64_t *bar_sdone = bar_rempty + TS_ROWRING;
+    uint64_t *bar_fwd = bar_sdone + TS_ROWRING, *bar_mma = bar_fwd + 1, *bar_epi = bar_mma + TS_MAX_EVENTS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_epi + TS_MAX_EVENTS);
     MmaOp *mma_sm = reinterpret_cast<MmaOp *>(tmem_slot + 4);
     EpiOp *epi_sm = reinterpret_cast<EpiOp *>(mma_sm + P.n_mma);
@@ -115,10 +119,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
         reinterpret_cast<uint32_t *>(epi_sm)[i] = reinterpret_cast<const uint32_t *>(P.epi)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < TS_RING; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 1); }
-        for (int s = 0; s < TS_ROWRING; ++s) { mbar_init(smem_u32(bar_rfull + s), 1); mbar_init(smem_u32(bar_rempty + s), 4); }
-        mbar_init(smem_u32(bar_fwd), 4);
+        for (int s = 0; s < TS_ROWRING; ++s) {
+            mbar_init(smem_u32(bar_rfull + s), 1);
+            mbar_init(smem_u32(bar_rempty + s), TS_EPI_WARPS);   // the epilogue warps, or the storer on their behalf
+            mbar_init(smem_u32(bar_sdone + s), TS_EPI_WARPS);
+        }
+        mbar_init(smem_u32(bar_fwd), 1);
         for (int e = 0; e < P.n_mma_events; ++e) mbar_init(smem_u32(bar_mma + e), 1);     // tcgen05.commit
-        for (int e = 0; e < P.n_epi_events; ++e) mbar_init(smem_u32(bar_epi + e), 4);     // one arrive per epilogue warp
+        for (int e = 0; e < P.n_epi_events; ++e) mbar_init(smem_u32(bar_epi + e), TS_EPI_WARPS);     // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -154,9 +162,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                 const uint32_t par = tcount & 1u;
                 uint32_t stage = 0, slot = 0;
                 const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1;
+                MmaOp nxt = mma_sm[0];
                 for (int m = 0; m < P.n_mma; ++m) {
-                    const MmaOp op = mma_sm[m];
-                    if (prof) P.prof[3 * (P.n_epi + m)] = clock64();
+                    const MmaOp op = nxt;
+                    nxt = mma_sm[m + 1 < P.n_mma ? m + 1 : m];
+                    if (prof) P.prof[6 * P.n_epi + 3 * m] = clock64();
                     if (op.wait_epi >= 0) {
                         mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
                         tc_fence_after();
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                         tc_fence_after();
                         stage = smem_u32(ring + slot * TS_STAGE_BYTES);
                     }
-                    if (prof) P.prof[3 * (P.n_epi + m) + 1] = clock64();
+                    if (prof) P.prof[6 * P.n_epi + 3 * m + 1] = clock64();
                     const uint32_t idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
                     const uint32_t d = tmem_base + op.d_col, a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
                     const uint32_t kb_bytes = (uint32_t)op.n * 128u;
@@ -182,100 +192,149 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     }
                     if (op.flags & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
                     if (op.commit_mma >= 0) tc_commit(smem_u32(bar_mma + op.commit_mma));
-                    if (prof) P.prof[3 * (P.n_epi + m) + 2] = clock64();
+                    if (prof) P.prof[6 * P.n_epi + 3 * m + 2] = clock64();
                 }
             }
         }
     } else if (warp == 2) {
         // ------------------------------------------------------------------ row loader
+        // every op that adds or stores scratch rows owns the next stage of the row ring
         if (leader) {
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
                 const float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS;
                 for (int e = 0; e < P.n_epi; ++e) {
                     const EpiOp op = epi_sm[e];
-                    if (!(op.flags & EPI_ADD_GLOBAL)) continue;
+                    if (!(op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL))) continue;
                     // rows stored earlier in this tile (the forward sweep's u) are only read by the backward sweep:
-                    // wait until the epilogue has made them visible to the async proxy
+                    // wait until the storer has seen those bulk stores complete
                     if (op.flags & EPI_AFTER_STORES) mbar_wait(smem_u32(bar_fwd), tcount & 1u);
                     const uint32_t s = it % TS_ROWRING, ph = (it / TS_ROWRING) & 1u;
                     mbar_wait(smem_u32(bar_rempty + s), ph ^ 1u);
-                    const uint32_t bytes = (uint32_t)op.n_valid * TS_COLS * 4u;
-                    mbar_arrive_expect_tx(smem_u32(bar_rfull + s), bytes);
-                    tma_bulk_g2s(smem_u32(rowring + (size_t)s * (TS_ROWSTAGE_BYTES / 4)), sc + (size_t)op.row_in * TS_COLS, bytes,
-                                 smem_u32(bar_rfull + s));
+                    if (op.flags & EPI_ADD_GLOBAL) {
+                        const uint32_t bytes = (uint32_t)op.n_valid * TS_COLS * 4u;
+                        mbar_arrive_expect_tx(smem_u32(bar_rfull + s), bytes);
+                        tma_bulk_g2s(smem_u32(rowring + (size_t)s * (TS_ROWSTAGE_BYTES / 4)), sc + (size_t)op.row_in * TS_COLS, bytes,
+                                     smem_u32(bar_rfull + s));
+                    } else mbar_arrive(smem_u32(bar_rfull + s));
                     ++it;
                 }
             }
         }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ row storer
+        if (leader) {
+            uint32_t it = 0, tcount = 0, sdone_par = 0;              // bit s: parity of stage s's next "written" phase
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
+                float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS;
+                for (int e = 0; e < P.n_epi; ++e) {
+                    const EpiOp op = epi_sm[e];
+                    if (!(op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL))) continue;
+                    const uint32_t s = it % TS_ROWRING;
+                    ++it;
+                    if (!(op.flags & EPI_STORE_GLOBAL)) continue;   // the epilogue frees such stages itself
+                    mbar_wait(smem_u32(bar_sdone + s), (sdone_par >> s) & 1u);   // all warps have written their columns (and fenced)
+                    sdone_par ^= 1u << s;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(sc + (size_t)op.row_out * TS_COLS), "r"(smem_u32(rowring + (size_t)s * (TS_ROWSTAGE_BYTES / 4))),
+                                   "r"((uint32_t)op.n_valid * TS_COLS * 4u) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (op.flags & EPI_LAST_FWD_STORE) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the forward sweep's rows are in memory
+                        mbar_arrive(smem_u32(bar_fwd));
+                    } else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_rempty + s)), "r"((uint32_t)TS_EPI_WARPS) : "memory");
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
     } else {
         // ------------------------------------------------------------------ epilogue: thread = column
         const int lane_grp = warp & 3;                               // tensor-memory lanes 32*lane_grp.. belong to this warp
+        const int half = (warp - 4) >> 2;                            // this warp takes chunks half, half + 2, ...
         const int col = lane_grp * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        constexpr int NC = TS_MAX_CHUNKS8 / 2;
         uint32_t tcount = 0, lit = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t par = tcount & 1u;
-            float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS + col;
-            const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1 && threadIdx.x == 96;
+            const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1 && threadIdx.x == 128;
+            EpiOp nxt = epi_sm[0];
 #pragma unroll 1
             for (int e = 0; e < P.n_epi; ++e) {
-                const EpiOp op = epi_sm[e];
-                if (prof) P.prof[3 * e] = clock64();
+                const EpiOp op = nxt;
+                nxt = epi_sm[e + 1 < P.n_epi ? e + 1 : e];
+                if (prof) P.prof[6 * e] = clock64();
                 const int nch = op.n_chunks, nv = op.n_valid;
-                float g[TS_MAX_CHUNKS8][8];
-                if (op.flags & EPI_ADD_GLOBAL) {                     // the rows are (being) staged in the row ring
-                    const uint32_t s = lit % TS_ROWRING;
-                    mbar_wait(smem_u32(bar_rfull + s), (lit / TS_ROWRING) & 1u);
-                    const float *src = rowring + (size_t)s * (TS_ROWSTAGE_BYTES / 4) + col;
-#pragma unroll
-                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) g[c][i] = (c * 8 + i < nv) ? src[(c * 8 + i) * TS_COLS] : 0.f;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(bar_rempty + s));
+                float g[NC][8];                                      // chunk 2 * c + half
+                const bool ring_op = (op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL)) != 0;
+                const uint32_t rs = lit % TS_ROWRING;
+                float *stage_col = rowring + (size_t)rs * (TS_ROWSTAGE_BYTES / 4) + col;
+                if (ring_op) {
+                    mbar_wait(smem_u32(bar_rfull + rs), (lit / TS_ROWRING) & 1u);
                     ++lit;
+                }
+                if (op.flags & EPI_ADD_GLOBAL) {                     // the rows are staged in the row ring
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = (2 * c + half) * 8 + i;
+                            g[c][i] = r < nv ? stage_col[r * TS_COLS] : 0.f;
+                        }
+                    if (!(op.flags & EPI_STORE_GLOBAL)) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(bar_rempty + rs));
+                    }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+                    for (int c = 0; c < NC; ++c)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) g[c][i] = 0.f;
                 }
+                if (prof) P.prof[6 * e + 1] = clock64();
                 if (op.wait_mma >= 0) {
                     mbar_wait(smem_u32(bar_mma + op.wait_mma), par);
                     tc_fence_after();
                 }
-                if (prof) P.prof[3 * e + 1] = clock64();
+                if (prof) P.prof[6 * e + 2] = clock64();
                 if (op.flags & EPI_FROM_TMEM) {
-                    uint32_t v[TS_MAX_CHUNKS8][8];
+                    uint32_t v[NC][8];
 #pragma unroll
-                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
-                        if (c < nch) tmem_ld8(tlane + op.src_col + 8 * c, v[c]);
+                    for (int c = 0; c < NC; ++c)
+                        if (2 * c + half < nch) tmem_ld8(tlane + op.src_col + 8 * (2 * c + half), v[c]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
+                    for (int c = 0; c < NC; ++c)
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (c < nch) g[c][i] = (c * 8 + i < nv) ? g[c][i] + __uint_as_float(v[c][i]) : 0.f;
-                }
-                if (op.flags & EPI_STORE_GLOBAL) {
-                    float *dst = sc + (size_t)op.row_out * TS_COLS;
+                            if (2 * c + half < nch) g[c][i] = ((2 * c + half) * 8 + i < nv) ? g[c][i] + __uint_as_float(v[c][i]) : 0.f;
+                    if (op.flags & EPI_ZERO_SRC) {
+                        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (c * 8 + i < nv) __stcg(dst + (size_t)(c * 8 + i) * TS_COLS, g[c][i]);
-                    if (op.flags & EPI_LAST_FWD_STORE) {             // hand the forward sweep's rows to the row loader
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(bar_fwd));
+                        for (int c = 0; c < NC; ++c)
+                            if (2 * c + half < nch) tmem_st8(tlane + op.src_col + 8 * (2 * c + half), z);
                     }
                 }
+                if (prof) P.prof[6 * e + 3] = clock64();
+                if (op.flags & EPI_STORE_GLOBAL) {                   // into the op's ring stage; the storer bulk-stores it
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = (2 * c + half) * 8 + i;
+                            if (r < nv) stage_col[r * TS_COLS] = g[c][i];
+                        }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(bar_sdone + rs));
+                }
+                if (prof) P.prof[6 * e + 4] = clock64();
                 if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT)) {
                     const bool split = (op.flags & EPI_ST_SPLIT) != 0;
 #pragma unroll
-                    for (int c = 0; c < TS_MAX_CHUNKS8; ++c)
-                        if (c < nch) {
+                    for (int c = 0; c < NC; ++c)
+                        if (2 * c + half < nch) {
                             uint32_t hi[8], lo[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
@@ -283,17 +342,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                                 hi[i] = split ? (u & 0xFFFFE000u) : u;
                                 lo[i] = __float_as_uint(g[c][i] - __uint_as_float(hi[i])) & 0xFFFFE000u;
                             }
-                            tmem_st8(tlane + op.hi_col + 8 * c, hi);
-                            if (split) tmem_st8(tlane + op.lo_col + 8 * c, lo);
+                            tmem_st8(tlane + op.hi_col + 8 * (2 * c + half), hi);
+                            if (split) tmem_st8(tlane + op.lo_col + 8 * (2 * c + half), lo);
                         }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
+                if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT | EPI_ZERO_SRC)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 if (op.signal_epi >= 0) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(bar_epi + op.signal_epi));
                 }
-                if (prof) P.prof[3 * e + 2] = clock64();
+                if (prof) P.prof[6 * e + 5] = clock64();
             }
         }
     }
@@ -309,7 +368,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
 
 size_t solve_tc_smem_bytes(int n_mma, int n_epi) {
     return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)TS_ROWRING * TS_ROWSTAGE_BYTES +
-           (size_t)(2 * TS_RING + 2 * TS_ROWRING + 1 + 2 * TS_MAX_EVENTS) * 8 + 16 +
+           (size_t)(2 * TS_RING + 3 * TS_ROWRING + 1 + 2 * TS_MAX_EVENTS) * 8 + 16 +
            (size_t)n_mma * sizeof(MmaOp) + (size_t)n_epi * sizeof(EpiOp);
 }
 

@@ -216,6 +216,7 @@ struct Builder {
     std::vector<char> epi_signals, mma_commits;
     int last_epi_write[TS_TMEM_COLS], last_epi_read[TS_TMEM_COLS], last_mma_write[TS_TMEM_COLS], last_mma_read[TS_TMEM_COLS];
     uint32_t chunk_fill = 0;
+    int epi_waited_mma = -1, mma_waited_epi = -1;           // latest op of the other stream each stream has already waited for
 
     struct Range { int c0, c1; };
 
@@ -226,6 +227,9 @@ struct Builder {
         for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) need = std::max(need, std::max(last_mma_write[c], last_mma_read[c]));
         for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) last_epi_read[c] = e;
         for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) last_epi_write[c] = e;
+        // both streams run in order, so an event implies every earlier one of its stream: skip redundant waits
+        if (need <= epi_waited_mma) need = -1;
+        else epi_waited_mma = need;
         if (need >= 0) mma_commits[need] = 1;
         epi_wait_op.push_back(need);
         epi_signals.push_back(0);
@@ -242,6 +246,8 @@ struct Builder {
         for (int c = 0; c < N; ++c) need = std::max(need, std::max(last_epi_write[op.d_col + c], last_epi_read[op.d_col + c]));
         for (int c = 0; c < K; ++c) last_mma_read[op.a_hi_col + c] = last_mma_read[op.a_lo_col + c] = m;
         for (int c = 0; c < N; ++c) last_mma_write[op.d_col + c] = m;
+        if (need <= mma_waited_epi) need = -1;
+        else mma_waited_epi = need;
         if (need >= 0) epi_signals[need] = 1;
         mma_wait_op.push_back(need);
         mma_commits.push_back(0);
@@ -308,21 +314,16 @@ struct Builder {
         auto slot_lo = [&](int k) { return s0 + k * 2 * kmax + kmax; };
 
         // ---- forward sweep
-        std::vector<char> inited(nodes.size(), 0);
+        // the accumulator stack starts at zero; a separator's columns are zeroed again when it is read
+        for (int c0 = 0; c0 < acc_cols; c0 += TS_MAX_NODE) {
+            EpiOp op{};
+            op.flags = EPI_ST_RAW;
+            op.n_chunks = (uint16_t)(std::min(TS_MAX_NODE, acc_cols - c0) / 8);
+            op.hi_col = (uint16_t)c0;
+            add_epi(op, {}, {{c0, c0 + op.n_chunks * 8}});
+        }
         auto emit_prep = [&](int i) {
             const TNode &nd = nodes[steps[i]];
-            for (auto it = nd.anc.rbegin(); it != nd.anc.rend(); ++it) {
-                const TNode &an = nodes[*it];
-                if (inited[*it] || an.rows.empty()) continue;
-                inited[*it] = 1;
-                EpiOp op{};
-                op.flags = EPI_ADD_GLOBAL | EPI_ST_RAW;
-                op.n_chunks = (uint16_t)(pad_to((int)an.rows.size(), 16) / 8);
-                op.n_valid = (uint16_t)an.rows.size();
-                op.hi_col = (uint16_t)an.acc_off;
-                op.row_in = (uint32_t)an.row0;
-                add_epi(op, {}, {{an.acc_off, an.acc_off + op.n_chunks * 8}});
-            }
             const int k = (int)nd.rows.size(), k8 = pad_to(k, 8), sl = i % n_slots;
             EpiOp op{};
             op.n_chunks = (uint16_t)(k8 / 8);
@@ -334,11 +335,14 @@ struct Builder {
                 op.flags = EPI_ADD_GLOBAL | EPI_ST_SPLIT;
                 op.row_in = (uint32_t)nd.row0;
             } else {
-                op.flags = EPI_FROM_TMEM | EPI_ST_SPLIT;
+                op.flags = EPI_FROM_TMEM | EPI_ADD_GLOBAL | EPI_ST_SPLIT | EPI_ZERO_SRC;
                 op.src_col = (uint16_t)nd.acc_off;
+                op.row_in = (uint32_t)nd.row0;
                 rd.push_back({nd.acc_off, nd.acc_off + k8});
             }
-            add_epi(op, rd, {{slot_hi(sl), slot_hi(sl) + k8}, {slot_lo(sl), slot_lo(sl) + k8}});
+            std::vector<Range> wr = {{slot_hi(sl), slot_hi(sl) + k8}, {slot_lo(sl), slot_lo(sl) + k8}};
+            if (!nd.children.empty()) wr.push_back({nd.acc_off, nd.acc_off + k8});
+            add_epi(op, rd, wr);
         };
         const int ns = (int)steps.size();
         if (ns == 0) { err = "empty system"; return false; }

@@ -43,6 +43,7 @@ enum EpiFlags : uint16_t {
     EPI_ST_SPLIT     = 16,    // tmem[hi_col + i] = tf32(v), tmem[lo_col + i] = tf32(v - tf32(v))
     EPI_LAST_FWD_STORE = 32,  // the forward sweep's last store: after it the rows it wrote may be bulk-loaded
     EPI_AFTER_STORES = 64,    // the first op that adds rows stored earlier in the tile (start of the backward sweep)
+    EPI_ZERO_SRC     = 128,   // tmem[src_col + i] = 0 after reading (accumulator columns handed to the next subtree)
 };
 
 struct EpiOp {                // 32 bytes

@@ -11,6 +11,7 @@ import numpy as np
 
 f32 = np.float32
 EPI_FROM_TMEM, EPI_ADD_GLOBAL, EPI_STORE_GLOBAL, EPI_ST_RAW, EPI_ST_SPLIT = 1, 2, 4, 8, 16
+EPI_ZERO_SRC = 128
 MMA_ACCUMULATE, MMA_CHUNK_FIRST, MMA_CHUNK_LAST = 1, 2, 4
 TS_COLS, STAGE_BYTES, TMEM_COLS = 128, 32768, 512
 
@@ -93,6 +94,8 @@ def solve_tile(pl, scratch, seed=0, columns=TS_COLS):
             t = tmem[:, int(op["src_col"]):int(op["src_col"]) + 8 * nch]
             assert not np.isnan(t[:, :nv]).any(), "EPI reads tensor memory that was never written"
             v[:, :nv] = v[:, :nv] + t[:, :nv]
+            if fl & EPI_ZERO_SRC:
+                tmem[:, int(op["src_col"]):int(op["src_col"]) + 8 * nch] = 0
         v[:, nv:] = 0
         if fl & EPI_STORE_GLOBAL:
             scratch[int(op["row_out"]):int(op["row_out"]) + nv] = v[:, :nv].T
