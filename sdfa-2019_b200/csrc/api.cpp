@@ -107,7 +107,7 @@ static std::vector<int32_t> compact_map(const sdfa_handle *h) {
             const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
             if (src < 0) continue;
             for (int j = 0; j < 9; ++j)
-                map[(size_t)ap.blk_coff[b] + (size_t)(j / 3) * ap.blk_plane[b] + e * 3 + j % 3] = src * 9 + j;
+                map[(size_t)ap.blk_coff[b] + (size_t)e * 9 + j] = src * 9 + j;
         }
     }
     return map;
@@ -116,20 +116,39 @@ static std::vector<int32_t> compact_map(const sdfa_handle *h) {
 static int upload_base(sdfa_handle *h) {
     if (h->dev.device < 0) return SDFA_OK;
     const HostPlan &p = h->host;
-    // x_base is kept in the Cholesky order (row iperm[f]); the kernels index it by scratch row
-    std::vector<float> hi(p.x_base.size()), lo(p.x_base.size());
-    for (int f = 0; f < p.n_free; ++f)
-        for (int c = 0; c < 3; ++c) {
+    DevicePlan &d = h->dev;
+    // the output kernel's per-chunk tables: element -> free line (or constant), line -> scratch offset + base.
+    // x_base is kept in the Cholesky order (row iperm[f]); lines are indexed by scratch row.
+    constexpr int VC = 64, EC = VC * 3;
+    const int chunks = (p.n_verts + VC - 1) / VC;
+    std::vector<int16_t> line_of((size_t)chunks * EC, -1);
+    std::vector<float> cval((size_t)chunks * EC, 0.f), hi, lo;
+    std::vector<int32_t> ptr(chunks + 1, 0), off;
+    int max_lines = 0;
+    for (int k = 0; k < chunks; ++k) {
+        ptr[k] = (int32_t)off.size();
+        for (int e = 0; e < EC; ++e) {
+            const int v = k * VC + e / 3, c = e % 3;
+            if (v >= p.n_verts) break;
+            const int f = p.vi_to_free[v];
+            if (f < 0) { cval[(size_t)k * EC + e] = p.cnst_pos[(size_t)p.vi_to_cnst[v] * 3 + c]; continue; }
             const double x = p.x_base[(size_t)p.iperm[f] * 3 + c];
-            const size_t i = (size_t)p.scratch_row[f] * 3 + c;
-            hi[i] = (float)x;
-            lo[i] = (float)(x - (double)hi[i]);
+            line_of[(size_t)k * EC + e] = (int16_t)((int)off.size() - ptr[k]);
+            off.push_back(p.scratch_row[f] * d.layout.row_stride + c * d.layout.c_stride);
+            hi.push_back((float)x);
+            lo.push_back((float)(x - (double)hi.back()));
         }
-    CUDA_TRY(cudaSetDevice(h->dev.device));
-    CUDA_TRY(cudaMemcpy(h->dev.xbase_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(h->dev.xbase_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
-    if (p.n_cnsts > 0)
-        CUDA_TRY(cudaMemcpy(h->dev.cnst_pos, p.cnst_pos.data(), p.cnst_pos.size() * 4, cudaMemcpyHostToDevice));
+        max_lines = std::max(max_lines, (int)off.size() - ptr[k]);
+    }
+    ptr[chunks] = (int32_t)off.size();
+    d.out_max_lines = max_lines;
+    CUDA_TRY(cudaSetDevice(d.device));
+    CUDA_TRY(cudaMemcpy(d.out_line_of, line_of.data(), line_of.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.out_cval, cval.data(), cval.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.out_line_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.out_line_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.out_line_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.out_line_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
     return SDFA_OK;
 }
 
@@ -206,18 +225,22 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             if ((r = upload(h, ap.eq_id, &d.asm_eq_id))) return r;
             if ((r = upload(h, ap.eq_u, &d.asm_eq_u))) return r;
             if ((r = upload(h, ap.row_perm, &d.asm_row_perm))) return r;
-            if ((r = upload(h, ap.row_ptr, &d.asm_row_ptr))) return r;
-            if ((r = upload(h, ap.inc, &d.asm_inc))) return r;
+            {
+                std::vector<short4> er(ap.eq_rows.size() / 4);
+                for (size_t i = 0; i < er.size(); ++i) er[i] = make_short4(ap.eq_rows[4 * i], ap.eq_rows[4 * i + 1], ap.eq_rows[4 * i + 2], 0);
+                std::vector<int32_t> ncol;
+                for (auto &b : ap.blocks) ncol.push_back(b.n_colours);
+                if ((r = upload(h, er, &d.asm_eq_rows))) return r;
+                if ((r = upload(h, ncol, &d.asm_n_colours))) return r;
+                if ((r = upload(h, ap.colour_ptr, &d.asm_colour_ptr))) return r;
+            }
             d.n_asm_blocks = (int)ap.blocks.size();
             d.asm_max_eq = ap.max_eq_per_block;
             d.asm_max_rows = ap.max_rows_per_block;
             std::vector<int32_t> tmp(p.n_eq, 0);
             if ((r = upload_mut(h, tmp, &d.eq_src))) return r;
             if ((r = upload(h, ap.blk_coff, &d.asm_coff))) return r;
-            if ((r = upload(h, ap.blk_plane, &d.asm_plane))) return r;
             d.compact_stride = ap.compact_stride;
-            d.asm_max_plane = 0;
-            for (int pl : ap.blk_plane) d.asm_max_plane = std::max(d.asm_max_plane, pl);
             if ((r = upload(h, p.prog.bytes, &d.prog))) return r;
             if ((r = upload(h, p.prog.stage_off, &d.stage_off))) return r;
             if ((r = upload(h, p.prog.io_desc, &d.io_desc))) return r;
@@ -227,7 +250,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             d.n_phases_fwd = p.prog.n_phases_fwd;
             d.n_phases_bwd = p.prog.n_phases_bwd;
             d.frames_per_tile = p.prog.frames_per_tile;
-            d.layout.sub = 1;
+            d.layout.FL = d.frames_per_tile;
             d.layout.tile_stride = (long long)p.n_free * slot_words(d.frames_per_tile);
             d.layout.row_stride = 3 * d.frames_per_tile;
             d.layout.c_stride = d.frames_per_tile;
@@ -245,21 +268,23 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
                 d.ts_n_chunks = (int)tp.chunk_off.size() - 1;
                 d.ts_n_mma_events = tp.n_mma_events;
                 d.ts_n_epi_events = tp.n_epi_events;
-                d.frames_per_tile = 32;                          // K2 / K5 tile; four of them share a 128-column solve tile
-                d.layout.sub = TS_COLS / 32;
+                d.layout.FL = TS_COLS;
                 d.layout.tile_stride = 3LL * p.n_free * TS_COLS;
                 d.layout.row_stride = TS_COLS;
                 d.layout.c_stride = p.n_free * TS_COLS;
             }
-            std::vector<int32_t> vert_row(p.n_verts);
-            for (int v = 0; v < p.n_verts; ++v)
-                vert_row[v] = p.vi_to_free[v] >= 0 ? p.scratch_row[p.vi_to_free[v]] : -1 - p.vi_to_cnst[v];
-            if ((r = upload(h, vert_row, &d.vert_row))) return r;
-            std::vector<float> z((size_t)p.n_free * 3, 0.f);
-            if ((r = upload_mut(h, z, &d.xbase_hi))) return r;
-            if ((r = upload_mut(h, z, &d.xbase_lo))) return r;
-            std::vector<float> cz((size_t)p.n_cnsts * 3, 0.f);
-            if ((r = upload_mut(h, cz, &d.cnst_pos))) return r;
+            {
+                const size_t chunks = ((size_t)p.n_verts + 63) / 64;
+                std::vector<int16_t> z16(chunks * 192, -1);
+                std::vector<float> zf(chunks * 192, 0.f), zl((size_t)p.n_free * 3, 0.f);
+                std::vector<int32_t> zp(chunks + 1, 0), zo((size_t)p.n_free * 3, 0);
+                if ((r = upload_mut(h, z16, &d.out_line_of))) return r;
+                if ((r = upload_mut(h, zf, &d.out_cval))) return r;
+                if ((r = upload_mut(h, zp, &d.out_line_ptr))) return r;
+                if ((r = upload_mut(h, zo, &d.out_line_off))) return r;
+                if ((r = upload_mut(h, zl, &d.out_line_hi))) return r;
+                if ((r = upload_mut(h, zl, &d.out_line_lo))) return r;
+            }
             if ((r = upload_base(h))) return r;
             if ((r = upload_eq_src(h))) return r;
             if (std::getenv("SDFA_SOLVE_PROFILE")) {
@@ -504,16 +529,15 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
         std::vector<int32_t> src_s, off_s, src_r, off_r;
         for (size_t b = 0; b < ap.blocks.size(); ++b) {
             const int ne = ap.blocks[b].eq_end - ap.blocks[b].eq_begin;
-            for (int pl = 0; pl < 3; ++pl)
-                for (int e = 0; e < ne; ++e) {
-                    const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
-                    if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
-                    for (int j = 0; j < 3; ++j) {
-                        const int32_t off = ap.blk_coff[b] + pl * ap.blk_plane[b] + e * 3 + j;
-                        if (pl < 2) { src_s.push_back(src < 0 ? -1 : src * 6 + pl * 3 + j); off_s.push_back(off); }
-                        else { src_r.push_back(src < 0 ? -1 : src * 3 + j); off_r.push_back(off); }
-                    }
+            for (int e = 0; e < ne; ++e) {
+                const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
+                if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
+                for (int j = 0; j < 9; ++j) {
+                    const int32_t off = ap.blk_coff[b] + e * 9 + j;
+                    if (j < 6) { src_s.push_back(src < 0 ? -1 : src * 6 + j); off_s.push_back(off); }
+                    else { src_r.push_back(src < 0 ? -1 : src * 3 + (j - 6)); off_r.push_back(off); }
                 }
+            }
         }
         auto build = [&](const float *W, const float *m, int K, const std::vector<int32_t> &src, const std::vector<int32_t> &off,
                          float **dw, float **db, int32_t **doff, int *mt) -> int {
@@ -537,7 +561,7 @@ static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, co
                                    int n_frames, float *out_dev, cudaStream_t s) {
     int rc;
     const long long stride = h->dev.compact_stride;
-    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, (size_t)n_frames * stride))) return rc;
+    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, ((size_t)n_frames + 31) / 32 * 32 * stride))) return rc;
     if ((rc = time_mark(h, 0, s))) return rc;
     if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
     if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
@@ -692,8 +716,8 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
     if (w == "asm_eq_id") return give(p.asmplan.eq_id, dst, cap);
     if (w == "asm_eq_u") return give(p.asmplan.eq_u, dst, cap);
     if (w == "asm_row_perm") return give(p.asmplan.row_perm, dst, cap);
-    if (w == "asm_row_ptr") return give(p.asmplan.row_ptr, dst, cap);
-    if (w == "asm_inc") return give(p.asmplan.inc, dst, cap);
+    if (w == "asm_eq_rows") return give(p.asmplan.eq_rows, dst, cap);
+    if (w == "asm_colour_ptr") return give(p.asmplan.colour_ptr, dst, cap);
     if (w == "scratch_row") return give(p.scratch_row, dst, cap);
     if (w == "ts_mma") return give(p.tplan.mma, dst, cap);
     if (w == "ts_epi") return give(p.tplan.epi, dst, cap);
@@ -709,7 +733,7 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
     }
     if (w == "asm_blocks") {
         std::vector<int> b;
-        for (auto &x : p.asmplan.blocks) { b.push_back(x.eq_begin); b.push_back(x.eq_end); b.push_back(x.row_begin); b.push_back(x.row_end); }
+        for (auto &x : p.asmplan.blocks) { b.push_back(x.eq_begin); b.push_back(x.eq_end); b.push_back(x.row_begin); b.push_back(x.row_end); b.push_back(x.n_colours); }
         return give(b, dst, cap);
     }
     if (w == "solve_prof") {

@@ -5,10 +5,11 @@
 // is a cuBLAS SGEMM + cat in the reference.
 //
 // GEMM shape (per basis: "scale" K=85 with 6 outputs per triangle, "rotation" K=180 with 3):
-//      D[m, n] = sum_k W[m, k] * X[n, k]       m = basis row (output value), n = frame
-// i.e. the basis rows are the MMA M dimension (TMEM lanes) and the frames the N dimension (TMEM columns),
-// so an epilogue warp holds 32 consecutive output values of one frame per register and its stores to
-// dgrad[frame][triangle*9 + c] are coalesced without a shared-memory transpose.
+//      D[n, m] = sum_k X[n, k] * W[m, k]       n = frame, m = basis row (output value = "slot")
+// i.e. the frames are the MMA M dimension (TMEM lanes) and the basis rows the N dimension (TMEM columns): an
+// epilogue warp owns 32 consecutive frames (lane = frame), holds one output value per register, and every
+// store instruction writes one full 128-byte line of the frame-tiled compact dgrad [tile of 32 frames][slot][32]
+// -- the layout the assembly kernel (lane = frame as well) reads back with coalesced lines.
 //
 // fp32 accuracy from TF32 tensor cores: both operands are split x = hi + lo with hi = x truncated to
 // TF32 (the 19 bits the tensor core reads) and lo = x - hi (exact), and every K-step issues three MMAs
@@ -116,9 +117,9 @@ struct GemmParams {
     const float *w_img;      // [m_tiles][kb][hi,lo][128x32 swizzled]
     const float *x_img;      // [n_tiles][kb][hi,lo][128x32 swizzled]
     const float *bias;       // [m_tiles*128]
-    const int32_t *out_off;  // [m_tiles*128] offset inside a frame's dgrad row, -1 for padding rows
-    float *out;
-    long long out_stride;    // floats per frame
+    const int32_t *out_off;  // [m_tiles*128] slot of the row in the compact dgrad, -1 for padding rows
+    float *out;              // [tiles of 32 frames][out_stride][32]
+    long long out_stride;    // slots per frame
     int n_frames, m_tiles, n_tiles, kb;
 };
 
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                 const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);         // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                const uint32_t d_tmem = tmem_base + acc * TC_BM;
                 for (int kb = 0; kb < P.kb; ++kb, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
@@ -188,9 +189,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                         const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_TILE_BYTES + k * 32);
                         const uint64_t x_hi = umma_desc(base + 2 * TC_TILE_BYTES + k * 32);
                         const uint64_t x_lo = umma_desc(base + 3 * TC_TILE_BYTES + k * 32);
-                        umma_tf32(d_tmem, w_hi, x_hi, TC_IDESC, (kb | k) != 0);
-                        umma_tf32(d_tmem, w_hi, x_lo, TC_IDESC, 1u);
-                        umma_tf32(d_tmem, w_lo, x_hi, TC_IDESC, 1u);
+                        umma_tf32(d_tmem, x_hi, w_hi, TC_IDESC, (kb | k) != 0);      // A = frames (M), B = basis rows (N)
+                        umma_tf32(d_tmem, x_lo, w_hi, TC_IDESC, 1u);
+                        umma_tf32(d_tmem, x_hi, w_lo, TC_IDESC, 1u);
                     }
                     tc_commit(bar_empty + 8 * s);                  // stage reusable once these MMAs have read it
                 }
@@ -199,33 +200,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
         }
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
-        const int lane_grp = warp & 3;                              // TMEM lanes 32*lane_grp .. +31 belong to this warp
-        const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (frames) it drains
+        const int lane_grp = warp & 3;                              // TMEM lanes = frames 32*lane_grp .. +31 of the 128-frame tile
+        const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (basis rows) it drains
         uint32_t tc = 0;
         for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
             const int m = tile % P.m_tiles, n = tile / P.m_tiles;
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-            const int row = m * TC_BM + lane_grp * 32 + lane;
-            const int off = P.out_off[row];
-            const float b = P.bias[row];
+            const int tile32 = n * (TC_BN / 32) + lane_grp;
+            const bool live = tile32 * 32 < P.n_frames;             // 32-frame tiles past the batch are not stored
+            float *out_tile = P.out + (size_t)tile32 * P.out_stride * 32 + lane;
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BN + col_half * (TC_BN / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BM + col_half * (TC_BM / 2);
 #pragma unroll 1
-            for (int chunk = 0; chunk < TC_BN / 64; ++chunk) {
+            for (int chunk = 0; chunk < TC_BM / 64; ++chunk) {
+                const int row0 = m * TC_BM + col_half * (TC_BM / 2) + chunk * 32;
+                const int off_l = P.out_off[row0 + lane];           // this lane's column's slot and bias, shuffled out below
+                const float b_l = P.bias[row0 + lane];
                 uint32_t v[32];
                 tmem_ld32(taddr + chunk * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int f0 = n * TC_BN + col_half * (TC_BN / 2) + chunk * 32;
-                if (off >= 0) {
-                    float *dst = P.out + (long long)f0 * P.out_stride + off;
-                    if (f0 + 32 <= P.n_frames) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) { *dst = __uint_as_float(v[c]) + b; dst += P.out_stride; }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) { if (f0 + c < P.n_frames) *dst = __uint_as_float(v[c]) + b; dst += P.out_stride; }
-                    }
+                for (int c = 0; c < 32; ++c) {
+                    const int off = __shfl_sync(0xffffffffu, off_l, c);
+                    const float b = __shfl_sync(0xffffffffu, b_l, c);
+                    if (live && off >= 0) __stcs(out_tile + (size_t)off * 32, __uint_as_float(v[c]) + b);
                 }
             }
             tc_fence_before();

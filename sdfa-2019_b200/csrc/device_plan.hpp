@@ -7,12 +7,12 @@
 
 namespace sdfa {
 
-// Where element (32-frame tile t, row, coordinate c, lane) of the solve scratch lives:
-//   (t / sub) * tile_stride + (t % sub) * 32 + row * row_stride + c * c_stride + lane
-// SIMT solve: sub = 1, rows of [3][F] floats ("tile-major"); tensor solve: sub = 4, one [n_free][128] matrix per
-// (128-frame tile, coordinate).
+// Where element (frame f, row, coordinate c) of the solve scratch lives:
+//   (f / FL) * tile_stride + f % FL + row * row_stride + c * c_stride
+// SIMT solve: FL = F frames per solve tile, rows of [3][F] floats ("tile-major"); tensor solve: FL = 128, one
+// [n_free][128] matrix per (128-frame tile, coordinate).
 struct ScratchLayout {
-    int sub = 1;
+    int FL = 32;
     long long tile_stride = 0;
     int row_stride = 0, c_stride = 0;
 };
@@ -26,12 +26,12 @@ struct DevicePlan {
     int4           *asm_blocks = nullptr;   // {eq_begin, eq_end, row_begin, row_end}
     const int32_t  *asm_eq_id = nullptr;    // block-local equation -> equation block
     const float    *asm_eq_u = nullptr;     // 6 floats per block-local equation
+    const short4   *asm_eq_rows = nullptr;  // block rows of the equation's three corners
     const int32_t  *asm_row_perm = nullptr;
-    const int32_t  *asm_row_ptr = nullptr;
-    const uint16_t *asm_inc = nullptr;
+    const int32_t  *asm_n_colours = nullptr, *asm_colour_ptr = nullptr;
     int32_t        *eq_src = nullptr;       // equation block -> source triangle (>=0), -1 identity, -2 zero block
-    const int32_t  *asm_coff = nullptr, *asm_plane = nullptr;   // block-planar compact dgrad layout
-    int compact_stride = 0, asm_max_plane = 0;
+    const int32_t  *asm_coff = nullptr;     // first slot of each block in the frame-tiled compact dgrad
+    int compact_stride = 0;
     // ---- solve (K3)
     const uint8_t  *prog = nullptr;         // 16-byte aligned stage stream
     const uint32_t *stage_off = nullptr;
@@ -48,9 +48,13 @@ struct DevicePlan {
     const uint32_t *ts_chunk_off = nullptr;
     int ts_n_mma = 0, ts_n_epi = 0, ts_n_chunks = 0, ts_n_mma_events = 0, ts_n_epi_events = 0;
     // ---- output (K5)
-    const int32_t  *vert_row = nullptr;     // vertex -> permuted row (>= 0) or -1 - constraint index
-    float          *xbase_hi = nullptr, *xbase_lo = nullptr;   // [n_free*3] permuted order
-    float          *cnst_pos = nullptr;     // [n_cnsts*3]
+    // per 64-vertex chunk tables of the output kernel (rebuilt by upload_base when the base / constraints change)
+    int16_t        *out_line_of = nullptr;  // [chunks*192]
+    float          *out_cval = nullptr;     // [chunks*192]
+    int32_t        *out_line_ptr = nullptr; // [chunks+1]
+    int32_t        *out_line_off = nullptr; // [n_free*3]
+    float          *out_line_hi = nullptr, *out_line_lo = nullptr;
+    int out_max_lines = 0;
     // ---- decode (K1)
     int k_scale = 0, k_rotat = 0;
     float *wfull_scale = nullptr, *mfull_scale = nullptr, *wfull_rotat = nullptr, *mfull_rotat = nullptr;

@@ -10,6 +10,7 @@
 #include "device_plan.hpp"
 #include "plan.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 
@@ -54,31 +55,35 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 
 // =============================================================================================
-// K2: per-equation transform + A^T (T^T - I) assembly.
+// K2: per-equation transform + A^T (T^T - I) assembly, lane = frame.
 //
-// grid = (row blocks, frame tiles); a CTA owns one row block for the 32 frames of one tile.  Per frame:
-//   phase 1  thread per block-local equation: E = R*S - I from the 9 dgrad values
-//            (impl.hpp:226-244; rotation_log_exp::exp, rotation/utils_rotation.cpp:20-51), then the two
-//            corner vectors g2 = E*U0, g3 = E*U1 and g1 = -(g2+g3) (coefficients of impl.hpp:106-116)
-//            -> shared memory [eq][corner][3] (stride 9 words: conflict free)
-//   phase 2  thread per row: sum the corner vectors incident to the row (CSR, no atomics) into a
-//            [row*3+c][33] transpose buffer
-// and after the 32 frames the buffer is written out as the solve kernel's tile-major rows
-// scratch[tile][row][c][frame] (one coalesced 128-byte line per warp instruction).
+// grid = (row blocks, tiles of 32 frames); a CTA owns one row block for one tile.  A warp takes an equation of
+// the block and evaluates, for its 32 frames at once (lane = frame),
+//      E = R*S - I from the 9 dgrad values (impl.hpp:226-244; rotation_log_exp::exp, rotation/utils_rotation.cpp:20-51)
+//      the corner vectors g2 = E*U0, g3 = E*U1, g1 = -(g2+g3)   (coefficients of impl.hpp:106-116)
+// and adds them to the rows of the block's accumulator acc[row][xyz][frame] in shared memory (conflict free: a
+// lane only ever touches its own frame).  The host coloured the block's equations so that one colour never
+// touches a row twice (schedule.cpp); colours run in order with a block barrier in between, so there are no
+// atomics and the summation order is fixed.  At the end the accumulator rows leave as the solve scratch's
+// rows, one 128-byte line per warp instruction.
 // E is evaluated without ever forming 1 + small:  E u = t + Q (u + t),  t = Es u,
 //   Q v = a W v + b W (W v),  a = sin(th)/th,  b = (1 - cos th)/th^2 = 2 sin^2(th/2)/th^2.
+// Input: STAGED = the decode kernel's frame-tiled compact buffer [tile][slot][32] (nine coalesced lines per
+// equation); !STAGED = any [frame][triangle][9] tensor (the reference's dgrad layout), gathered per lane.
 struct AsmParams {
-    const int4 *blocks;
+    const int4 *blocks;                      // {eq_begin, eq_end, row_begin, row_end}
+    const int32_t *n_colours;                // per block
+    const int32_t *colour_ptr;               // [blocks][ASM_MAX_COLOURS + 1]
     const int32_t *eq_id;
     const float *eq_u;
-    const int32_t *row_perm, *row_ptr;
-    const uint16_t *inc;
+    const short4 *eq_rows;
+    const int32_t *row_perm;
     const int32_t *eq_src;
-    const int32_t *blk_coff, *blk_plane;    // block-planar compact layout (staged variant)
+    const int32_t *blk_coff;
     const float *dgrad;
-    long long frame_stride;
+    long long frame_stride;                  // !STAGED: floats per frame; STAGED: slots per frame
     float *rhs;
-    int n_frames, n_free, mode, max_eq, max_plane, max_rows, F;   // F = frames per solve tile
+    int n_frames, mode, max_rows;
     ScratchLayout L;
 };
 
@@ -101,98 +106,40 @@ __device__ __forceinline__ void corner_vec(const float *d, float a, float b, con
 }
 
 constexpr int ASM_THREADS = 256;
-constexpr int TPAD = 33;          // transpose-buffer row stride (odd: conflict free both ways)
+constexpr int ASM_WARPS = ASM_THREADS / 32;
 
-// STAGED: the input is the decode kernel's block-planar compact buffer; the block's span of a frame is one
-// contiguous run, fetched two frames ahead by a TMA bulk copy into a double-buffered stage (mbarrier
-// completion), and read back conflict-free (three planes of stride-3 triples).
-// !STAGED: any [frame][triangle][9] layout (the reference's dgrad tensor): every thread gathers its
-// equations' nine values with 4-byte cp.async copies into the same double-buffered stage, two frames ahead.
 template <bool STAGED>
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
-    extern __shared__ __align__(128) float sh[];
-    float *stage = sh;                                              // [2][3*max_plane]: the frame's dgrad, block-planar
-    float *g_sh0 = sh + 6 * P.max_plane;                            // [2][max_eq][9]: corner vectors, double buffered
-    float *t_sh = g_sh0 + 2 * P.max_eq * 9;                         // [rows*3][33]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(t_sh + ((P.max_rows * 3 * TPAD + 3) & ~3));
+    extern __shared__ __align__(16) float acc[];                     // [row][3][32]
     const int4 blk = P.blocks[blockIdx.x];
-    const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
+    const int n_rows = blk.w - blk.z;
     const int tile = blockIdx.y;
-    const int frame0 = tile * P.F;
-    const int nvalid = min(P.F, P.n_frames - frame0);
-    // frame-invariant per-equation data stays in registers: thread t owns equations t, t+128, ...
-    constexpr int KMAX = ASM_MAX_EQ / ASM_THREADS;
-    int src_k[KMAX];
-    float u_k[KMAX][6];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-        const int e = threadIdx.x + k * ASM_THREADS;
-        src_k[k] = -1;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) u_k[k][j] = 0.f;
-        if (e < n_eq) {
-            src_k[k] = P.eq_src[P.eq_id[blk.x + e]];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) u_k[k][j] = __ldg(P.eq_u + (blk.x + e) * 6 + j);
-        }
-    }
-    const int plane = P.blk_plane[blockIdx.x];
-    uint32_t span_bytes = 0;
-    const float *span0 = nullptr;
-    // !STAGED: asynchronous gather of frame `ft` into stage `si` (one commit group per frame and thread)
-    auto gather = [&](int ft, int si) {
-        const float *row = P.dgrad + (long long)(frame0 + ft) * P.frame_stride;
-        float *dst = stage + si * 3 * P.max_plane;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            const int e = threadIdx.x + k * ASM_THREADS;
-            if (e >= n_eq || src_k[k] < 0) continue;
-            const float *src = row + (long long)src_k[k] * 9;
-#pragma unroll
-            for (int j = 0; j < 9; ++j)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (j / 3) * plane + e * 3 + (j % 3))),
-                             "l"(src + j) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (STAGED) {
-        span_bytes = 3u * (uint32_t)plane * 4u;
-        span0 = P.dgrad + (long long)frame0 * P.frame_stride + P.blk_coff[blockIdx.x];
-        if (threadIdx.x == 0) {
-            mbar_init(smem_u32(&bars[0]), 1);
-            mbar_init(smem_u32(&bars[1]), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            fence_async_smem();
-            for (int f = 0; f < 2 && f < nvalid; ++f) {
-                mbar_arrive_expect_tx(smem_u32(&bars[f]), span_bytes);
-                tma_bulk_g2s(smem_u32(stage + f * 3 * P.max_plane), span0 + (long long)f * P.frame_stride, span_bytes, smem_u32(&bars[f]));
-            }
-        }
-        __syncthreads();
-    } else {
-        gather(0, 0);
-        if (nvalid > 1) gather(1, 1);
-        else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");      // frame 0 has landed (this thread's part)
-        __syncthreads();
-    }
-    // Software pipeline over the tile's frames with ONE block barrier per frame: iteration f computes the
-    // corner vectors of frame f into g_sh[f&1] and sums the rows of frame f-1 out of g_sh[(f-1)&1].
-    for (int f = 0; f <= nvalid; ++f) {
-        const float *st = stage + (f & 1) * 3 * P.max_plane;
-        float *g_sh = g_sh0 + (f & 1) * P.max_eq * 9;
-        if (STAGED && f < nvalid) mbar_wait(smem_u32(&bars[f & 1]), (uint32_t)(f >> 1) & 1u);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            const int e = threadIdx.x + k * ASM_THREADS;
-            if (e >= n_eq || f >= nvalid) break;
-            const int src = src_k[k];
-            const float *u0 = &u_k[k][0], *u1 = &u_k[k][3];
+    const int frame0 = tile * 32;
+    const int nvalid = min(32, P.n_frames - frame0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < n_rows * 96; i += ASM_THREADS) acc[i] = 0.f;
+    const int32_t *cptr = P.colour_ptr + (size_t)blockIdx.x * (ASM_MAX_COLOURS + 1);
+    const int nc = P.n_colours[blockIdx.x];
+    // STAGED: line j of block-local equation e; !STAGED: this lane's frame (clamped inside the batch)
+    const float *in = STAGED ? P.dgrad + ((long long)tile * P.frame_stride + P.blk_coff[blockIdx.x]) * 32 + lane
+                             : P.dgrad + (long long)min(frame0 + lane, P.n_frames - 1) * P.frame_stride;
+    __syncthreads();
+    for (int k = 0; k < nc; ++k) {
+        const int e1 = cptr[k + 1];
+        for (int e = cptr[k] + warp; e < e1; e += ASM_WARPS) {
+            const int ge = blk.x + e;
+            const int src = P.eq_src[P.eq_id[ge]];
+            if (src == -1) continue;                                 // identity block (impl.hpp:264-268): T - I = 0
+            const float4 ua = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2);
+            const float4 ub = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2 + 1);
+            const short4 rw = __ldg(P.eq_rows + ge);
+            const float u0[3] = {ua.x, ua.y, ua.z}, u1[3] = {ua.w, ub.x, ub.y};
             float g2[3], g3[3];
             if (src >= 0) {
                 float d[9];
+                const float *q = STAGED ? in + (size_t)e * 9 * 32 : in + (long long)src * 9;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) d[j] = st[(j / 3) * plane + e * 3 + (j % 3)];
+                for (int j = 0; j < 9; ++j) d[j] = STAGED ? __ldcs(q + j * 32) : __ldg(q + j);
                 if (P.mode == ASM_DGRAD) {
                     const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
                     float a = 0.f, b = 0.f;
@@ -219,72 +166,47 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
                                 (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u1[2];
                     }
                 }
-            } else if (src == -1) {             // identity block (impl.hpp:264-268): T - I = 0
-#pragma unroll
-                for (int c = 0; c < 3; ++c) g2[c] = g3[c] = 0.f;
             } else {                            // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { g2[c] = -u0[c]; g3[c] = -u1[c]; }
             }
-            float *g = g_sh + e * 9;
+            // corner 0 (v1) gets -(g2+g3), corner 1 (v2) g2, corner 2 (v3) g3
+            if (rw.x >= 0) {
+                float *t = acc + rw.x * 96 + lane;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { g[c] = -(g2[c] + g3[c]); g[3 + c] = g2[c]; g[6 + c] = g3[c]; }
-        }
-        if (f >= 1) {
-            const float *gp = g_sh0 + ((f - 1) & 1) * P.max_eq * 9;
-            // rows are dealt from the top thread ids down: the low threads carry the extra equations above
-            for (int r = ASM_THREADS - 1 - threadIdx.x; r < n_rows; r += ASM_THREADS) {
-                const int gr = blk.z + r;
-                const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-                for (int q = q0; q < q1; ++q) {
-                    const float *g = gp + 3 * (int)P.inc[q];
-                    s0 += g[0]; s1 += g[1]; s2 += g[2];
-                }
-                float *t = t_sh + (3 * r) * TPAD + (f - 1);
-                t[0] = s0; t[TPAD] = s1; t[2 * TPAD] = s2;
+                for (int c = 0; c < 3; ++c) t[c * 32] -= g2[c] + g3[c];
+            }
+            if (rw.y >= 0) {
+                float *t = acc + rw.y * 96 + lane;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) t[c * 32] += g2[c];
+            }
+            if (rw.z >= 0) {
+                float *t = acc + rw.z * 96 + lane;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) t[c * 32] += g3[c];
             }
         }
-        if (!STAGED) asm volatile("cp.async.wait_group 0;" ::: "memory");   // frame f+1 has landed (this thread's part)
         __syncthreads();
-        if (!STAGED && f + 2 < nvalid) gather(f + 2, f & 1);         // stage f&1 has been consumed
-        if (STAGED && threadIdx.x == 0 && f + 2 < nvalid) {          // stage f&1 has been consumed: prefetch frame f+2
-            fence_async_smem();
-            mbar_arrive_expect_tx(smem_u32(&bars[f & 1]), span_bytes);
-            tma_bulk_g2s(smem_u32(stage + (f & 1) * 3 * P.max_plane), span0 + (long long)(f + 2) * P.frame_stride, span_bytes,
-                         smem_u32(&bars[f & 1]));
-        }
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // transposed write-out: line (row, c) = F consecutive frames
-    float *dst_tile = P.rhs + (long long)(tile / P.L.sub) * P.L.tile_stride + (tile % P.L.sub) * 32;
-    if (lane < P.F)
-        for (int line = warp; line < n_rows * 3; line += ASM_THREADS / 32) {
-            const int r = line / 3, c = line - 3 * r;
-            const float v = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
-            dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride + lane] = v;
-        }
-}
-
-static size_t asm_smem_bytes(const DevicePlan &d, bool staged) {
-    size_t fl = 2 * (size_t)d.asm_max_eq * 9 + (((size_t)d.asm_max_rows * 3 * TPAD + 3) & ~(size_t)3);
-    fl += 6 * (size_t)d.asm_max_plane;
-    (void)staged;
-    return fl * sizeof(float) + 16;
+    const int fr = frame0 + lane;
+    float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
+    for (int line = warp; line < n_rows * 3; line += ASM_WARPS) {
+        const int r = line / 3, c = line - 3 * r;
+        dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride] = lane < nvalid ? acc[line * 32 + lane] : 0.f;
+    }
 }
 
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    AsmParams P{d.asm_blocks, d.asm_eq_id, d.asm_eq_u, d.asm_row_perm, d.asm_row_ptr, d.asm_inc, d.eq_src,
-                d.asm_coff, d.asm_plane, dgrad, frame_stride, rhs, n_frames, d.n_free, mode, d.asm_max_eq,
-                d.asm_max_plane, d.asm_max_rows, d.frames_per_tile, d.layout};
-    const size_t smem = asm_smem_bytes(d, staged);
+    AsmParams P{d.asm_blocks, d.asm_n_colours, d.asm_colour_ptr, d.asm_eq_id, d.asm_eq_u, d.asm_eq_rows, d.asm_row_perm,
+                d.eq_src, d.asm_coff, dgrad, frame_stride, rhs, n_frames, mode, d.asm_max_rows, d.layout};
+    const size_t smem = (size_t)d.asm_max_rows * 96 * sizeof(float);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int n_tiles = (n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
-    dim3 grid((unsigned)d.n_asm_blocks, (unsigned)n_tiles);
+    dim3 grid((unsigned)d.n_asm_blocks, (unsigned)((n_frames + 31) / 32));
     if (staged) k_assemble<true><<<grid, ASM_THREADS, smem, stream>>>(P);
     else k_assemble<false><<<grid, ASM_THREADS, smem, stream>>>(P);
     g_launches++;
@@ -544,8 +466,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
 }
 
 size_t scratch_floats(const DevicePlan &d, int n_frames) {
-    const size_t n_tiles = ((size_t)n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
-    return (n_tiles + d.layout.sub - 1) / d.layout.sub * (size_t)d.layout.tile_stride;
+    // K2 writes whole 32-frame tiles
+    const size_t n32 = ((size_t)n_frames + 31) / 32 * 32;
+    return (n32 + d.layout.FL - 1) / d.layout.FL * (size_t)d.layout.tile_stride;
 }
 
 size_t solve_smem_bytes(int n_slots, int frames_per_tile) {
@@ -588,82 +511,73 @@ cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cuda
 }
 
 // =============================================================================================
-// K5: output.  Transposes the solved displacement rows scratch[tile][row][c][frame] into the reference
-// layout out[frame][vertex][3] (pybind.cpp:108), adds the fp64-computed base solution (kept as a
-// hi/lo float pair) and copies the constrained vertices through (impl.hpp:295-308) -- every output
-// byte is written exactly once, coalesced.
+// K5: output.  Transposes the solved displacement rows (one line of FR consecutive frames per free vertex
+// coordinate in the solve scratch) into the reference layout out[frame][vertex][3] (pybind.cpp:108), adds the
+// fp64-computed base solution (kept as a hi/lo float pair) and copies the constrained vertices through
+// (impl.hpp:295-308) -- every output byte is written exactly once, coalesced.
+// A CTA owns 64 vertices x FR frames: phase 1 stages the chunk's free lines (+ base) in shared memory, one
+// coalesced line per warp instruction; phase 2 has one thread per output element of the chunk walk the frames,
+// its line index / constant in registers, so a frame's 192 floats leave as six full-warp stores.  The per-chunk
+// tables (which element is which line, constants, base) are built on the host (api.cpp: upload_base).
 constexpr int OUT_VC = 64;                       // vertices per CTA
+constexpr int OUT_THREADS = OUT_VC * 3;
 struct OutParams {
     const float *scratch;
-    const int32_t *vert_row;                     // vertex -> permuted row, or -1-(constraint index)
-    const float *xb_hi, *xb_lo, *cnst_pos;
+    const int16_t *line_of;                      // [chunks][192] free line of the element inside its chunk, -1 = constrained
+    const float *cval;                           // [chunks][192] constrained value of the element
+    const int32_t *line_ptr;                     // [chunks + 1] first line of the chunk
+    const int32_t *line_off;                     // [lines] scratch offset of the line inside a tile
+    const float *line_hi, *line_lo;              // [lines] base solution
     float *out;
-    int n_frames, n_free, n_verts, F;
-    ScratchLayout L;
+    int n_frames, n_verts, FR, FC;               // FR = frames per scratch line, FC <= FR = frames per CTA
+    long long tile_stride;
 };
 
-// Only the free vertices' lines go through the transpose buffer; constrained vertices (3/4 of FLAME) are
-// frame independent and are written from a per-CTA constant table.
-__global__ void __launch_bounds__(256) k_output(OutParams P) {
-    __shared__ float t_sh[OUT_VC * 3 * TPAD];    // [free line][33]
-    __shared__ float cval[OUT_VC * 3];           // constrained values per output element
-    __shared__ short line_of[OUT_VC * 3];        // output element -> free line in t_sh, -1 if constrained
-    __shared__ int free_row[OUT_VC * 3];         // free line -> scratch word offset row*96 + c*32
-    __shared__ float free_hi[OUT_VC * 3], free_lo[OUT_VC * 3];
-    __shared__ int n_free_lines;
-    const int v0 = blockIdx.x * OUT_VC;
-    const int nv = min(OUT_VC, P.n_verts - v0);
-    const int ne = nv * 3;
-    const int tile = blockIdx.y;
-    const int frame0 = tile * P.F;
-    const int nvalid = min(P.F, P.n_frames - frame0);
+__global__ void __launch_bounds__(OUT_THREADS) k_output(OutParams P) {
+    extern __shared__ float t_sh[];              // [line][FC + 1]
+    const int chunk = blockIdx.x, grp = blockIdx.y;
+    const int frame0 = grp * P.FC;
+    const int nvalid = min(P.FC, P.n_frames - frame0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0) {                             // compact the free lines of this vertex chunk (ballot scan)
-        int base = 0;
-        for (int e0 = 0; e0 < ne; e0 += 32) {
-            const int e = e0 + lane;
-            int row = -1;
-            if (e < ne) row = __ldg(P.vert_row + v0 + e / 3);
-            const unsigned m = __ballot_sync(0xffffffffu, e < ne && row >= 0);
-            if (e < ne) {
-                const int c = e % 3;
-                if (row >= 0) {
-                    const int i = base + __popc(m & ((1u << lane) - 1u));
-                    line_of[e] = (short)i;
-                    free_row[i] = row * P.L.row_stride + c * P.L.c_stride;
-                    free_hi[i] = __ldg(P.xb_hi + row * 3 + c);
-                    free_lo[i] = __ldg(P.xb_lo + row * 3 + c);
-                } else {
-                    line_of[e] = -1;
-                    cval[e] = __ldg(P.cnst_pos + (-1 - row) * 3 + c);
-                }
-            }
-            base += __popc(m);
-        }
-        if (lane == 0) n_free_lines = base;
+    const int l0 = P.line_ptr[chunk], nl = P.line_ptr[chunk + 1] - l0;
+    const int pitch = P.FC + 1;
+    const float *src_tile = P.scratch + (long long)(frame0 / P.FR) * P.tile_stride + frame0 % P.FR;
+    if (lane < P.FC) {
+#pragma unroll 4
+        for (int i = warp; i < nl; i += OUT_THREADS / 32)
+            t_sh[i * pitch + lane] = P.line_hi[l0 + i] + (P.line_lo[l0 + i] + __ldcs(src_tile + P.line_off[l0 + i] + lane));
     }
     __syncthreads();
-    const int nl = n_free_lines;
-    const float *src_tile = P.scratch + (long long)(tile / P.L.sub) * P.L.tile_stride + (tile % P.L.sub) * 32;
-    if (lane < P.F)
-        for (int i = warp; i < nl; i += 8)
-            t_sh[i * TPAD + lane] = free_hi[i] + (free_lo[i] + src_tile[free_row[i] + lane]);
-    __syncthreads();
-    for (int f = warp; f < nvalid; f += 8) {
-        float *dst = P.out + ((long long)(frame0 + f) * P.n_verts + v0) * 3;
-        for (int e = lane; e < ne; e += 32) {
-            const int i = line_of[e];
-            dst[e] = i >= 0 ? t_sh[i * TPAD + f] : cval[e];
-        }
+    const int e = threadIdx.x;
+    const long long row = (long long)P.n_verts * 3;
+    if ((long long)chunk * OUT_THREADS + e >= row) return;
+    const int line = P.line_of[chunk * OUT_THREADS + e];
+    const float c = P.cval[chunk * OUT_THREADS + e];
+    float *dst = P.out + (long long)frame0 * row + (long long)chunk * OUT_THREADS + e;
+    if (line < 0) {
+#pragma unroll 4
+        for (int f = 0; f < nvalid; ++f) __stcs(dst + f * row, c);
+    } else {
+        const float *src = t_sh + line * pitch;
+#pragma unroll 4
+        for (int f = 0; f < nvalid; ++f) __stcs(dst + f * row, src[f]);
     }
 }
 
 cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    OutParams P{scratch, d.vert_row, d.xbase_hi, d.xbase_lo, d.cnst_pos, out, n_frames, d.n_free, d.n_verts, d.frames_per_tile, d.layout};
-    const int n_tiles = (n_frames + d.frames_per_tile - 1) / d.frames_per_tile;
-    dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)n_tiles);
-    k_output<<<grid, 256, 0, stream>>>(P);
+    const int FR = d.layout.FL, FC = std::min(FR, 32);
+    OutParams P{scratch, d.out_line_of, d.out_cval, d.out_line_ptr, d.out_line_off, d.out_line_hi, d.out_line_lo,
+                out, n_frames, d.n_verts, FR, FC, d.layout.tile_stride};
+    const size_t smem = (size_t)std::max(d.out_max_lines, 1) * (FC + 1) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_output, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));
+    k_output<<<grid, OUT_THREADS, smem, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
 }

@@ -80,29 +80,32 @@ struct SolveProgram {
 };
 
 // ------------------------------------------------------------------------------------------
-// Assembly plan (kernel K2): the free rows are grouped into row blocks; a CTA handles one
-// (row block, frame): phase 1 computes the two corner vectors of every equation block that touches
-// the row block, phase 2 sums, per row, the corner vectors incident to it (CSR, no atomics).
+// Assembly plan (kernel K2): the free rows are grouped into row blocks; a CTA handles one (row block, tile of 32
+// frames) with lane = frame: a warp evaluates an equation's two corner vectors for the 32 frames and adds them
+// to the block's row accumulators in shared memory.  The block's equations are coloured so that one colour never
+// touches a row twice, and the colours are processed in order with a barrier in between: no atomics, a fixed
+// summation order.
+constexpr int ASM_MAX_COLOURS = 32;
 struct AssemblyBlock {
     int eq_begin, eq_end;       // range in eq_* arrays (block-local equations, duplicates across blocks allowed)
-    int row_begin, row_end;     // range in row_* arrays
+    int row_begin, row_end;     // range in row_perm
+    int n_colours;
 };
 struct AssemblyPlan {
     std::vector<AssemblyBlock> blocks;
-    // per block-local equation: which equation block it is (index into the active list) and the
-    // frame of its target triangle: U0[3], U1[3]  (rows of U = R^-1 Q^T, impl.hpp:98-100)
+    // per block-local equation (sorted by colour): which equation block it is, the frame of its target triangle
+    // U0[3], U1[3] (rows of U = R^-1 Q^T, impl.hpp:98-100) and the block-local rows of its three corners
     std::vector<int32_t> eq_id;         // global equation-block index (0..n_eq)
-    std::vector<float>   eq_u;          // 6 floats per entry
-    // per block-local row: permuted row index (where to write) and incidence range
-    std::vector<int32_t>  row_perm;
-    std::vector<int32_t>  row_ptr;      // size rows + 1 per block, concatenated with global offsets
-    std::vector<uint16_t> inc;          // incidence: local_eq * 3 + corner
+    std::vector<float>   eq_u;          // 8 floats per entry (6 used)
+    std::vector<int16_t> eq_rows;       // 4 per entry: block row of corner 0, 1, 2 (-1: not a row of this block), pad
+    std::vector<int32_t> colour_ptr;    // ASM_MAX_COLOURS + 1 per block: first block-local equation of each colour
+    std::vector<int32_t> row_perm;      // per block-local row: scratch row (where to write)
     int max_eq_per_block = 0, max_rows_per_block = 0;
-    // Block-planar compact dgrad (what the decode kernel writes and the staged assembly reads with one TMA
-    // bulk copy per block and frame): block b owns floats [blk_coff[b], +3*blk_plane[b]) of a frame's compact
-    // row = three planes [eq][s00,s01,s02], [eq][s11,s12,s22], [eq][r01,r02,r12], each padded to 16 bytes.
-    std::vector<int32_t> blk_coff, blk_plane;
-    int compact_stride = 0;             // floats per frame
+    // Frame-tiled compact dgrad (what the decode kernel writes and the staged assembly reads):
+    // [tile of 32 frames][slot][32 frames], slot = blk_coff[b] + 9 * (block-local equation) + component
+    // (components in the reference order s00,s01,s02,s11,s12,s22,r01,r02,r12).
+    std::vector<int32_t> blk_coff;
+    int compact_stride = 0;             // slots = floats per frame
 };
 
 // ------------------------------------------------------------------------------------------

@@ -592,7 +592,6 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
     std::iota(by_key.begin(), by_key.end(), 0);
     std::stable_sort(by_key.begin(), by_key.end(), [&](int x, int y) { return key[x] < key[y]; });
     size_t seed_pos = 0;
-    ap.row_ptr.push_back(0);
     int n_taken = 0;
     while (n_taken < n) {
         while (taken[by_key[seed_pos]]) ++seed_pos;
@@ -630,33 +629,58 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
         }
         for (int k : eqs) in_eqs[k] = 0;
         std::sort(eqs.begin(), eqs.end());
+        // Colour the block's equations so that no two of one colour touch the same block row: the kernel adds the
+        // corner vectors of a colour into the row accumulators without atomics, colours in a fixed order.
+        std::vector<int> local_row(n, -1);
+        for (size_t i = 0; i < rows.size(); ++i) local_row[rows[i]] = (int)i;
+        std::vector<uint32_t> row_colours(rows.size(), 0);
+        std::vector<int> colour(eqs.size(), 0);
+        int n_colours = 0;
+        for (size_t i = 0; i < eqs.size(); ++i) {
+            uint32_t used = 0;
+            for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) used |= row_colours[local_row[g]];
+            int c = 0;
+            while (c < ASM_MAX_COLOURS && (used >> c & 1u)) ++c;
+            if (c == ASM_MAX_COLOURS) throw std::runtime_error("assembly plan: more than 32 equation colours in a row block");
+            colour[i] = c;
+            n_colours = std::max(n_colours, c + 1);
+            for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) row_colours[local_row[g]] |= 1u << c;
+        }
+        std::vector<int> order(eqs.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colour[x] < colour[y]; });
         AssemblyBlock blk;
         blk.eq_begin = (int)ap.eq_id.size();
         blk.row_begin = (int)ap.row_perm.size();
-        for (int k : eqs) {
+        std::vector<int32_t> cptr(ASM_MAX_COLOURS + 1, (int32_t)eqs.size());
+        for (size_t i = 0; i < order.size(); ++i) {
+            const int k = eqs[order[i]];
+            if (i == 0 || colour[order[i]] != colour[order[i - 1]])
+                for (int c = (i == 0 ? 0 : colour[order[i - 1]] + 1); c <= colour[order[i]]; ++c) cptr[c] = (int32_t)i;
             ap.eq_id.push_back(k);
             const double *u = &p.tri_u[(size_t)p.eq_tri[k] * 6];
             for (int d = 0; d < 6; ++d) ap.eq_u.push_back((float)u[d]);
-        }
-        for (int f : rows) {
-            ap.row_perm.push_back(p.scratch_row[f]);
-            for (auto &kc : inc[f]) {
-                int local = (int)(std::lower_bound(eqs.begin(), eqs.end(), kc.first) - eqs.begin());
-                ap.inc.push_back((uint16_t)(local * 3 + kc.second));
+            ap.eq_u.push_back(0.f); ap.eq_u.push_back(0.f);          // 8 floats per entry: two aligned float4 loads
+            const uint32_t *t = &p.tris[(size_t)p.eq_tri[k] * 3];
+            for (int c = 0; c < 3; ++c) {
+                const int f = p.vi_to_free[t[c]];
+                ap.eq_rows.push_back((int16_t)(f >= 0 ? local_row[f] : -1));
             }
-            ap.row_ptr.push_back((int32_t)ap.inc.size());
+            ap.eq_rows.push_back(0);
         }
+        ap.colour_ptr.insert(ap.colour_ptr.end(), cptr.begin(), cptr.end());
+        for (int f : rows) ap.row_perm.push_back(p.scratch_row[f]);
         blk.eq_end = (int)ap.eq_id.size();
         blk.row_end = (int)ap.row_perm.size();
+        blk.n_colours = n_colours;
         ap.max_eq_per_block = std::max(ap.max_eq_per_block, blk.eq_end - blk.eq_begin);
         ap.max_rows_per_block = std::max(ap.max_rows_per_block, blk.row_end - blk.row_begin);
         ap.blocks.push_back(blk);
     }
+    // frame-tiled compact dgrad: slot = blk_coff[b] + 9 * (block-local equation) + component
     for (auto &blk : ap.blocks) {
-        const int plane = (3 * (blk.eq_end - blk.eq_begin) + 3) / 4 * 4;
         ap.blk_coff.push_back(ap.compact_stride);
-        ap.blk_plane.push_back(plane);
-        ap.compact_stride += 3 * plane;
+        ap.compact_stride += 9 * (blk.eq_end - blk.eq_begin);
     }
 }
 

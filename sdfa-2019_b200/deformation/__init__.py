@@ -241,23 +241,24 @@ class Reconstructor:
         return out
 
     def compact_layout(self):
-        """Map of the internal block-planar compact dgrad: entry i = source_triangle*9 + component, -1 = padding."""
+        """Map of the internal compact dgrad: slot i = source_triangle*9 + component, -1 = padding."""
         n = lib.sdfa_compact_layout(self._h, None, 0)
         out = np.empty(n, dtype=np.int32)
         lib.sdfa_compact_layout(self._h, ptr(out), n)
         return out
 
     def decode_compact(self, coeff_scale, coeff_rotat, stream=None):
-        """Coefficients -> compact dgrad [N, stride] as laid out by compact_layout() (torch.cuda; tcgen05 kernel)."""
+        """Coefficients -> compact dgrad (torch.cuda; tcgen05 kernel).  The kernel writes the frame-tiled layout
+        [ceil(N/32), slots, 32] the assembly kernel reads; returned here as [N, slots] (slots as in compact_layout())."""
         import torch
         a = coeff_scale.contiguous().reshape(-1, self.k_scale)
         b = coeff_rotat.contiguous().reshape(-1, self.k_rotat)
-        stride = lib.sdfa_compact_layout(self._h, None, 0)
-        out = torch.zeros((a.shape[0], stride), dtype=torch.float32, device=a.device)
+        slots = lib.sdfa_compact_layout(self._h, None, 0)
+        n = a.shape[0]
+        out = torch.zeros(((n + 31) // 32, slots, 32), dtype=torch.float32, device=a.device)
         s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
-        check(lib.sdfa_decode_compact_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), a.shape[0],
-                                          ptr(out.data_ptr()), ptr(s)))
-        return out
+        check(lib.sdfa_decode_compact_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), n, ptr(out.data_ptr()), ptr(s)))
+        return out.permute(0, 2, 1).reshape(-1, slots)[:n]
 
     # ------------------------------------------------------------------------------ measurement
     def set_timing(self, enable=True):

@@ -89,8 +89,8 @@ _DEBUG_DTYPES = {
     "perm": np.int32, "parent": np.int32, "free_to_vi": np.int32, "l_colptr": np.int32, "l_rowidx": np.int32,
     "l_val": np.float64, "m_colptr": np.int32, "m_rowidx": np.int32, "m_val": np.float64, "x_base": np.float64,
     "active_eq": np.int32, "tri_u": np.float64, "prog": np.uint8, "stage_off": np.uint32, "io_desc": np.uint32, "io_phase": np.uint32, "eq_src": np.int32,
-    "asm_eq_id": np.int32, "asm_eq_u": np.float32, "asm_row_perm": np.int32, "asm_row_ptr": np.int32,
-    "asm_inc": np.uint16, "solve_prof": np.int64, "asm_blocks": np.int32, "stats": np.int64,
+    "asm_eq_id": np.int32, "asm_eq_u": np.float32, "asm_row_perm": np.int32, "asm_eq_rows": np.int16,
+    "asm_colour_ptr": np.int32, "solve_prof": np.int64, "asm_blocks": np.int32, "stats": np.int64,
     "scratch_row": np.int32, "ts_mma": np.uint8, "ts_epi": np.uint8, "ts_matrix": np.uint8, "ts_chunk_off": np.uint32,
     "ts_why_not": np.uint8, "ts_stats": np.int64,
 }

@@ -15,13 +15,14 @@ f32 = np.float32
 def assemble(rec, dgrad, mode="dgrad"):
     """K2: dgrad [N, n_src*9] f32 -> rhs [N, n_free, 3] f32 (permuted row order)."""
     dg = np.ascontiguousarray(dgrad, dtype=f32).reshape(len(dgrad), -1, 9)
-    blocks = rec.debug("asm_blocks").reshape(-1, 4)
-    eq_id, eq_u = rec.debug("asm_eq_id"), rec.debug("asm_eq_u").reshape(-1, 6)
-    row_perm, row_ptr, inc = rec.debug("asm_row_perm"), rec.debug("asm_row_ptr"), rec.debug("asm_inc")
+    blocks = rec.debug("asm_blocks").reshape(-1, 5)
+    eq_id, eq_u = rec.debug("asm_eq_id"), rec.debug("asm_eq_u").reshape(-1, 8)[:, :6]
+    row_perm, eq_rows = rec.debug("asm_row_perm"), rec.debug("asm_eq_rows").reshape(-1, 4)
+    colour_ptr = rec.debug("asm_colour_ptr").reshape(len(blocks), -1)
     eq_src = rec.debug("eq_src")
     N = dg.shape[0]
     rhs = np.zeros((N, rec.n_free, 3), dtype=f32)
-    for eb, ee, rb, re in blocks:
+    for bi, (eb, ee, rb, re, ncol) in enumerate(blocks):
         ids = eq_id[eb:ee]
         src = eq_src[ids]
         u0, u1 = eq_u[eb:ee, :3], eq_u[eb:ee, 3:]
@@ -66,14 +67,26 @@ def assemble(rec, dgrad, mode="dgrad"):
         zero = src == -2
         if zero.any():
             g[:, zero, 1], g[:, zero, 2] = -u0[zero], -u1[zero]
-        g[:, :, 0] = -(g[:, :, 1] + g[:, :, 2])
-        gf = g.reshape(N, -1, 3)
-        for r in range(rb, re):
-            idx = inc[row_ptr[r]:row_ptr[r + 1]].astype(np.int64)
-            acc = np.zeros((N, 3), dtype=f32)
-            for i in idx:                                     # same sequential order as the kernel
-                acc = acc + gf[:, i]
-            rhs[:, row_perm[r]] = acc
+        # the kernel's order: colours in sequence, an equation's corners 0, 1, 2; no row twice within a colour
+        acc = np.zeros((N, re - rb, 3), dtype=f32)
+        cp = colour_ptr[bi]
+        assert cp[0] == 0 and cp[ncol] == ee - eb
+        for k in range(ncol):
+            touched = set()
+            for e in range(cp[k], cp[k + 1]):
+                if src[e] == -1:
+                    continue
+                r0, r1, r2 = (int(x) for x in eq_rows[eb + e][:3])
+                mine = {r for r in (r0, r1, r2) if r >= 0}
+                assert not (mine & touched), "two equations of one colour share a row"
+                touched |= mine
+                if r0 >= 0:
+                    acc[:, r0] = acc[:, r0] - (g[:, e, 1] + g[:, e, 2])
+                if r1 >= 0:
+                    acc[:, r1] = acc[:, r1] + g[:, e, 1]
+                if r2 >= 0:
+                    acc[:, r2] = acc[:, r2] + g[:, e, 2]
+        rhs[:, row_perm[rb:re]] = acc
     return rhs
 
 
