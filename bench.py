@@ -185,8 +185,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sentences", type=int, default=296,
-                    help="240-frame sentences per step per GPU (296 -> 71 040 frames = 2220 solve tiles = 15 per SM)")
+    ap.add_argument("--sentences", type=int, default=315,
+                    help="240-frame sentences per step per GPU (315 -> 75 600 frames = 1773 solve tiles of 128 columns "
+                         "= 11.98 per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -228,11 +228,9 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             {
                 std::vector<short4> er(ap.eq_rows.size() / 4);
                 for (size_t i = 0; i < er.size(); ++i) er[i] = make_short4(ap.eq_rows[4 * i], ap.eq_rows[4 * i + 1], ap.eq_rows[4 * i + 2], 0);
-                std::vector<int32_t> ncol;
-                for (auto &b : ap.blocks) ncol.push_back(b.n_colours);
                 if ((r = upload(h, er, &d.asm_eq_rows))) return r;
-                if ((r = upload(h, ncol, &d.asm_n_colours))) return r;
-                if ((r = upload(h, ap.colour_ptr, &d.asm_colour_ptr))) return r;
+                if ((r = upload(h, ap.warp_sched, &d.asm_warp_sched))) return r;
+                if ((r = upload(h, ap.warp_ptr, &d.asm_warp_ptr))) return r;
             }
             d.n_asm_blocks = (int)ap.blocks.size();
             d.asm_max_eq = ap.max_eq_per_block;
@@ -544,7 +542,7 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
             std::vector<float> img, bias;
             std::vector<int32_t> o;
             tc_build_basis(W, m, K, src, off, img, bias, o);
-            *mt = (int)(bias.size() / 128);
+            *mt = (int)(bias.size() / 256);
             int r;
             if ((r = upload_mut(h, img, dw))) return r;
             if ((r = upload_mut(h, bias, db))) return r;

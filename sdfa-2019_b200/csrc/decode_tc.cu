@@ -28,15 +28,16 @@ namespace sdfa {
 
 namespace {
 
-constexpr int TC_BM = 128;          // basis rows per tile (UMMA M)
-constexpr int TC_BN = 128;          // frames per tile (UMMA N)
+constexpr int TC_BM = 256;          // basis rows per tile (UMMA N): 256 halves the frames-operand traffic per MMA
+constexpr int TC_BN = 128;          // frames per tile (UMMA M = TMEM lanes)
 constexpr int TC_BK = 32;           // floats per K-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB: one operand half (hi or lo)
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // W_hi, W_lo, X_hi, X_lo
+constexpr int TC_STAGES = 2;
+constexpr int TC_W_BYTES = TC_BM * TC_BK * 4;                    // 32 KB: one half (hi or lo) of the basis tile
+constexpr int TC_X_BYTES = TC_BN * TC_BK * 4;                    // 16 KB: one half of the frames tile
+constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;  // W_hi, W_lo, X_hi, X_lo = 96 KB
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each drains half of the columns
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue warps
-constexpr int TC_TMEM_COLS = 256;   // two 128-column fp32 accumulators
+constexpr int TC_TMEM_COLS = 512;   // two 256-column fp32 accumulators
 
 // float index of element (row r, k) inside a [rows x 32] K-major SWIZZLE_128B tile image:
 // 8-row groups of 1024 bytes, 16-byte chunk index XORed with the row index inside the group
@@ -114,7 +115,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
 }
 
 struct GemmParams {
-    const float *w_img;      // [m_tiles][kb][hi,lo][128x32 swizzled]
+    const float *w_img;      // [m_tiles][kb][hi,lo][256x32 swizzled]
     const float *x_img;      // [n_tiles][kb][hi,lo][128x32 swizzled]
     const float *bias;       // [m_tiles*128]
     const int32_t *out_off;  // [m_tiles*128] slot of the row in the compact dgrad, -1 for padding rows
@@ -123,8 +124,8 @@ struct GemmParams {
     int n_frames, m_tiles, n_tiles, kb;
 };
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 128, M = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 256 rows, M = 128 frames
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(TC_BN >> 4) << 24);
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     mbar_arrive_expect_tx(bar_full + 8 * s, TC_STAGE_BYTES);
                     const uint32_t dst = smem_u32(stages + s * TC_STAGE_BYTES);
-                    tma_bulk_g2s(dst, P.w_img + ((size_t)m * P.kb + kb) * (2 * TC_BM * TC_BK), 2 * TC_TILE_BYTES, bar_full + 8 * s);
-                    tma_bulk_g2s(dst + 2 * TC_TILE_BYTES, P.x_img + ((size_t)n * P.kb + kb) * (2 * TC_BN * TC_BK), 2 * TC_TILE_BYTES,
+                    tma_bulk_g2s(dst, P.w_img + ((size_t)m * P.kb + kb) * (2 * TC_BM * TC_BK), 2 * TC_W_BYTES, bar_full + 8 * s);
+                    tma_bulk_g2s(dst + 2 * TC_W_BYTES, P.x_img + ((size_t)n * P.kb + kb) * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES,
                                  bar_full + 8 * s);
                 }
             }
@@ -186,9 +187,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                     const uint32_t base = smem_u32(stages + s * TC_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {          // UMMA K = 8 floats = 32 bytes
-                        const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_TILE_BYTES + k * 32);
-                        const uint64_t x_hi = umma_desc(base + 2 * TC_TILE_BYTES + k * 32);
-                        const uint64_t x_lo = umma_desc(base + 3 * TC_TILE_BYTES + k * 32);
+                        const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_W_BYTES + k * 32);
+                        const uint64_t x_hi = umma_desc(base + 2 * TC_W_BYTES + k * 32);
+                        const uint64_t x_lo = umma_desc(base + 2 * TC_W_BYTES + TC_X_BYTES + k * 32);
                         umma_tf32(d_tmem, x_hi, w_hi, TC_IDESC, (kb | k) != 0);      // A = frames (M), B = basis rows (N)
                         umma_tf32(d_tmem, x_lo, w_hi, TC_IDESC, 1u);
                         umma_tf32(d_tmem, x_hi, w_lo, TC_IDESC, 1u);

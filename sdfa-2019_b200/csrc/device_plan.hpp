@@ -28,7 +28,8 @@ struct DevicePlan {
     const float    *asm_eq_u = nullptr;     // 6 floats per block-local equation
     const short4   *asm_eq_rows = nullptr;  // block rows of the equation's three corners
     const int32_t  *asm_row_perm = nullptr;
-    const int32_t  *asm_n_colours = nullptr, *asm_colour_ptr = nullptr;
+    const int16_t  *asm_warp_sched = nullptr;   // per (block, warp) walk: equations, barrier marks, end mark
+    const int32_t  *asm_warp_ptr = nullptr;
     int32_t        *eq_src = nullptr;       // equation block -> source triangle (>=0), -1 identity, -2 zero block
     const int32_t  *asm_coff = nullptr;     // first slot of each block in the frame-tiled compact dgrad
     int compact_stride = 0;

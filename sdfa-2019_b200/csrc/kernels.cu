@@ -72,8 +72,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // equation); !STAGED = any [frame][triangle][9] tensor (the reference's dgrad layout), gathered per lane.
 struct AsmParams {
     const int4 *blocks;                      // {eq_begin, eq_end, row_begin, row_end}
-    const int32_t *n_colours;                // per block
-    const int32_t *colour_ptr;               // [blocks][ASM_MAX_COLOURS + 1]
+    const int16_t *warp_sched;               // per (block, warp): equations, ASM_SCHED_BARRIER, ..., ASM_SCHED_END
+    const int32_t *warp_ptr;
     const int32_t *eq_id;
     const float *eq_u;
     const short4 *eq_rows;
@@ -105,8 +105,8 @@ __device__ __forceinline__ void corner_vec(const float *d, float a, float b, con
     g[2] = t2 + a * p2 + b * q2;
 }
 
-constexpr int ASM_THREADS = 256;
-constexpr int ASM_WARPS = ASM_THREADS / 32;
+constexpr int ASM_WARPS = ASM_WARPS_PER_BLOCK;
+constexpr int ASM_THREADS = 32 * ASM_WARPS;
 
 template <bool STAGED>
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
@@ -118,76 +118,91 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     const int nvalid = min(32, P.n_frames - frame0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < n_rows * 96; i += ASM_THREADS) acc[i] = 0.f;
-    const int32_t *cptr = P.colour_ptr + (size_t)blockIdx.x * (ASM_MAX_COLOURS + 1);
-    const int nc = P.n_colours[blockIdx.x];
     // STAGED: line j of block-local equation e; !STAGED: this lane's frame (clamped inside the batch)
     const float *in = STAGED ? P.dgrad + ((long long)tile * P.frame_stride + P.blk_coff[blockIdx.x]) * 32 + lane
                              : P.dgrad + (long long)min(frame0 + lane, P.n_frames - 1) * P.frame_stride;
-    __syncthreads();
-    for (int k = 0; k < nc; ++k) {
-        const int e1 = cptr[k + 1];
-        for (int e = cptr[k] + warp; e < e1; e += ASM_WARPS) {
-            const int ge = blk.x + e;
-            const int src = P.eq_src[P.eq_id[ge]];
-            if (src == -1) continue;                                 // identity block (impl.hpp:264-268): T - I = 0
-            const float4 ua = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2);
-            const float4 ub = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2 + 1);
-            const short4 rw = __ldg(P.eq_rows + ge);
-            const float u0[3] = {ua.x, ua.y, ua.z}, u1[3] = {ua.w, ub.x, ub.y};
-            float g2[3], g3[3];
-            if (src >= 0) {
-                float d[9];
-                const float *q = STAGED ? in + (size_t)e * 9 * 32 : in + (long long)src * 9;
+    const int16_t *walk = P.warp_sched + P.warp_ptr[blockIdx.x * ASM_WARPS + warp];
+    // fetch of one equation: its source triangle and the nine values of this lane's frame
+    auto fetch = [&](int e, int &src, float (&d)[9]) {
+        src = -1;
+        if (e < 0) return;
+        src = P.eq_src[P.eq_id[blk.x + e]];
+        if (src < 0) return;
+        const float *q = STAGED ? in + (size_t)e * 9 * 32 : in + (long long)src * 9;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) d[j] = STAGED ? __ldcs(q + j * 32) : __ldg(q + j);
-                if (P.mode == ASM_DGRAD) {
-                    const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
-                    float a = 0.f, b = 0.f;
-                    if (th2 >= 1e-12f) {        // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
-                        if (th2 <= 1.f) {
-                            // Taylor series in th^2 (remainder < 3e-8 for th <= 1): no sqrt, sin or division
-                            a = 1.f - th2 * (1.f / 6.f) * (1.f - th2 * (1.f / 20.f) * (1.f - th2 * (1.f / 42.f) * (1.f - th2 * (1.f / 72.f))));
-                            b = 0.5f - th2 * (1.f / 24.f) * (1.f - th2 * (1.f / 30.f) * (1.f - th2 * (1.f / 56.f) * (1.f - th2 * (1.f / 90.f))));
-                        } else {
-                            const float th = sqrtf(th2);
-                            const float sh2 = sinf(0.5f * th);
-                            a = sinf(th) / th;
-                            b = 2.f * sh2 * sh2 / th2;
-                        }
-                    }
-                    corner_vec(d, a, b, u0, g2);
-                    corner_vec(d, a, b, u1, g3);
-                } else {                        // raw row-major T (impl.hpp:391-397): E = T - I
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        g2[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u0[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u0[1] +
-                                (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u0[2];
-                        g3[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u1[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u1[1] +
-                                (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u1[2];
+        for (int j = 0; j < 9; ++j) d[j] = STAGED ? __ldcs(q + j * 32) : __ldg(q + j);
+    };
+    // the equation's corner vectors for this lane's frame, added to the block rows of its three corners
+    auto apply = [&](int e, int src, const float (&d)[9]) {
+        if (src == -1) return;                                       // identity block (impl.hpp:264-268): T - I = 0
+        const int ge = blk.x + e;
+        const float4 ua = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2);
+        const float4 ub = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2 + 1);
+        const short4 rw = __ldg(P.eq_rows + ge);
+        const float u0[3] = {ua.x, ua.y, ua.z}, u1[3] = {ua.w, ub.x, ub.y};
+        float g2[3], g3[3];
+        if (src >= 0) {
+            if (P.mode == ASM_DGRAD) {
+                const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
+                float a = 0.f, b = 0.f;
+                if (th2 >= 1e-12f) {        // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
+                    if (th2 <= 1.f) {
+                        // Taylor series in th^2 (remainder < 3e-8 for th <= 1): no sqrt, sin or division
+                        a = 1.f - th2 * (1.f / 6.f) * (1.f - th2 * (1.f / 20.f) * (1.f - th2 * (1.f / 42.f) * (1.f - th2 * (1.f / 72.f))));
+                        b = 0.5f - th2 * (1.f / 24.f) * (1.f - th2 * (1.f / 30.f) * (1.f - th2 * (1.f / 56.f) * (1.f - th2 * (1.f / 90.f))));
+                    } else {
+                        const float th = sqrtf(th2);
+                        const float sh2 = sinf(0.5f * th);
+                        a = sinf(th) / th;
+                        b = 2.f * sh2 * sh2 / th2;
                     }
                 }
-            } else {                            // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
+                corner_vec(d, a, b, u0, g2);
+                corner_vec(d, a, b, u1, g3);
+            } else {                        // raw row-major T (impl.hpp:391-397): E = T - I
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { g2[c] = -u0[c]; g3[c] = -u1[c]; }
+                for (int c = 0; c < 3; ++c) {
+                    g2[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u0[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u0[1] +
+                            (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u0[2];
+                    g3[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u1[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u1[1] +
+                            (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u1[2];
+                }
             }
-            // corner 0 (v1) gets -(g2+g3), corner 1 (v2) g2, corner 2 (v3) g3
-            if (rw.x >= 0) {
-                float *t = acc + rw.x * 96 + lane;
+        } else {                            // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
 #pragma unroll
-                for (int c = 0; c < 3; ++c) t[c * 32] -= g2[c] + g3[c];
-            }
-            if (rw.y >= 0) {
-                float *t = acc + rw.y * 96 + lane;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) t[c * 32] += g2[c];
-            }
-            if (rw.z >= 0) {
-                float *t = acc + rw.z * 96 + lane;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) t[c * 32] += g3[c];
-            }
+            for (int c = 0; c < 3; ++c) { g2[c] = -u0[c]; g3[c] = -u1[c]; }
         }
-        __syncthreads();
+        // corner 0 (v1) gets -(g2+g3), corner 1 (v2) g2, corner 2 (v3) g3
+        if (rw.x >= 0) {
+            float *t = acc + rw.x * 96 + lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) t[c * 32] -= g2[c] + g3[c];
+        }
+        if (rw.y >= 0) {
+            float *t = acc + rw.y * 96 + lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) t[c * 32] += g2[c];
+        }
+        if (rw.z >= 0) {
+            float *t = acc + rw.z * 96 + lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) t[c * 32] += g3[c];
+        }
+    };
+    // software pipeline over the warp's walk: the next equation's values are in flight while this one is applied
+    // (also across the colour barriers)
+    int e0 = *walk++, s0, e1, s1;
+    float d0[9], d1[9];
+    fetch(e0, s0, d0);
+    __syncthreads();
+    while (e0 != ASM_SCHED_END) {
+        e1 = *walk++;
+        fetch(e1, s1, d1);
+        if (e0 == ASM_SCHED_BARRIER) __syncthreads(); else apply(e0, s0, d0);
+        if (e1 == ASM_SCHED_END) break;
+        e0 = *walk++;
+        fetch(e0, s0, d0);
+        if (e1 == ASM_SCHED_BARRIER) __syncthreads(); else apply(e1, s1, d1);
     }
     const int fr = frame0 + lane;
     float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    AsmParams P{d.asm_blocks, d.asm_n_colours, d.asm_colour_ptr, d.asm_eq_id, d.asm_eq_u, d.asm_eq_rows, d.asm_row_perm,
+    AsmParams P{d.asm_blocks, d.asm_warp_sched, d.asm_warp_ptr, d.asm_eq_id, d.asm_eq_u, d.asm_eq_rows, d.asm_row_perm,
                 d.eq_src, d.asm_coff, dgrad, frame_stride, rhs, n_frames, mode, d.asm_max_rows, d.layout};
     const size_t smem = (size_t)d.asm_max_rows * 96 * sizeof(float);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)

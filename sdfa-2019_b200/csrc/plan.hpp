@@ -86,6 +86,8 @@ struct SolveProgram {
 // touches a row twice, and the colours are processed in order with a barrier in between: no atomics, a fixed
 // summation order.
 constexpr int ASM_MAX_COLOURS = 32;
+constexpr int ASM_WARPS_PER_BLOCK = 8;
+constexpr int16_t ASM_SCHED_BARRIER = -1, ASM_SCHED_END = -2;
 struct AssemblyBlock {
     int eq_begin, eq_end;       // range in eq_* arrays (block-local equations, duplicates across blocks allowed)
     int row_begin, row_end;     // range in row_perm
@@ -100,6 +102,8 @@ struct AssemblyPlan {
     std::vector<int16_t> eq_rows;       // 4 per entry: block row of corner 0, 1, 2 (-1: not a row of this block), pad
     std::vector<int32_t> colour_ptr;    // ASM_MAX_COLOURS + 1 per block: first block-local equation of each colour
     std::vector<int32_t> row_perm;      // per block-local row: scratch row (where to write)
+    std::vector<int16_t> warp_sched;    // per (block, warp): block-local equations, ASM_SCHED_BARRIER between colours, ASM_SCHED_END
+    std::vector<int32_t> warp_ptr;      // [blocks * ASM_WARPS_PER_BLOCK] start of each walk in warp_sched
     int max_eq_per_block = 0, max_rows_per_block = 0;
     // Frame-tiled compact dgrad (what the decode kernel writes and the staged assembly reads):
     // [tile of 32 frames][slot][32 frames], slot = blk_coff[b] + 9 * (block-local equation) + component

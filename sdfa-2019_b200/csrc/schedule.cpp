@@ -636,15 +636,30 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
         std::vector<uint32_t> row_colours(rows.size(), 0);
         std::vector<int> colour(eqs.size(), 0);
         int n_colours = 0;
-        for (size_t i = 0; i < eqs.size(); ++i) {
-            uint32_t used = 0;
-            for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) used |= row_colours[local_row[g]];
-            int c = 0;
-            while (c < ASM_MAX_COLOURS && (used >> c & 1u)) ++c;
-            if (c == ASM_MAX_COLOURS) throw std::runtime_error("assembly plan: more than 32 equation colours in a row block");
-            colour[i] = c;
-            n_colours = std::max(n_colours, c + 1);
-            for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) row_colours[local_row[g]] |= 1u << c;
+        // pass 1: first-fit gives the number of colours; pass 2: same number, each equation into the emptiest
+        // colour its rows allow, so the colours (= the work between two barriers) come out even
+        for (int pass = 0; pass < 2; ++pass) {
+            std::fill(row_colours.begin(), row_colours.end(), 0u);
+            std::vector<int> load(ASM_MAX_COLOURS, 0);
+            const int limit = pass == 0 ? ASM_MAX_COLOURS : n_colours;
+            for (size_t i = 0; i < eqs.size(); ++i) {
+                uint32_t used = 0;
+                for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) used |= row_colours[local_row[g]];
+                int c = -1;
+                for (int q = 0; q < limit; ++q) {
+                    if (used >> q & 1u) continue;
+                    if (pass == 0) { c = q; break; }
+                    if (c < 0 || load[q] < load[c]) c = q;
+                }
+                if (c < 0) {
+                    for (int q = limit; q < ASM_MAX_COLOURS && c < 0; ++q) if (!(used >> q & 1u)) c = q;
+                    if (c < 0) throw std::runtime_error("assembly plan: more than 32 equation colours in a row block");
+                }
+                colour[i] = c;
+                ++load[c];
+                n_colours = std::max(n_colours, c + 1);
+                for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) row_colours[local_row[g]] |= 1u << c;
+            }
         }
         std::vector<int> order(eqs.size());
         std::iota(order.begin(), order.end(), 0);
@@ -669,6 +684,15 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
             ap.eq_rows.push_back(0);
         }
         ap.colour_ptr.insert(ap.colour_ptr.end(), cptr.begin(), cptr.end());
+        // per-warp walk of the block: the warp's equations of colour 0, a barrier, colour 1, ...
+        for (int w = 0; w < ASM_WARPS_PER_BLOCK; ++w) {
+            ap.warp_ptr.push_back((int32_t)ap.warp_sched.size());
+            for (int c = 0; c < n_colours; ++c) {
+                for (int e = cptr[c] + w; e < cptr[c + 1]; e += ASM_WARPS_PER_BLOCK) ap.warp_sched.push_back((int16_t)e);
+                ap.warp_sched.push_back(ASM_SCHED_BARRIER);
+            }
+            ap.warp_sched.push_back(ASM_SCHED_END);
+        }
         for (int f : rows) ap.row_perm.push_back(p.scratch_row[f]);
         blk.eq_end = (int)ap.eq_id.size();
         blk.row_end = (int)ap.row_perm.size();

@@ -179,16 +179,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     }
                     if (prof) P.prof[6 * P.n_epi + 3 * m + 1] = clock64();
                     const uint32_t idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
-                    const uint32_t d = tmem_base + op.d_col, a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
-                    const uint32_t kb_bytes = (uint32_t)op.n * 128u;
+                    const uint32_t d = tmem_base + op.d_col;
+                    uint32_t a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
+                    // descriptor low words (address >> 4): +2 per K = 8 step inside a 32-wide K block, then on to the next block image
+                    constexpr uint64_t DESC_HI = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
+                    uint32_t b_hi = (((stage + op.b_hi_off) >> 4) & 0x3FFFu) | (1u << 16);
+                    uint32_t b_lo = (((stage + op.b_lo_off) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t kb_step = (uint32_t)op.n * 8u - 6u;               // (n * 128 - 96) >> 4
                     uint32_t acc = (op.flags & MMA_ACCUMULATE) ? 1u : 0u;
                     for (uint32_t j = 0; j < op.k8; ++j) {
-                        const uint32_t off = (j >> 2) * kb_bytes + (j & 3u) * 32u;
-                        const uint64_t b_hi = umma_desc(stage + op.b_hi_off + off), b_lo = umma_desc(stage + op.b_lo_off + off);
-                        umma_tf32_ts(d, a_hi + 8 * j, b_hi, idesc, acc);
-                        umma_tf32_ts(d, a_lo + 8 * j, b_hi, idesc, 1u);
-                        umma_tf32_ts(d, a_hi + 8 * j, b_lo, idesc, 1u);
+                        umma_tf32_ts(d, a_hi, DESC_HI | b_hi, idesc, acc);
+                        umma_tf32_ts(d, a_lo, DESC_HI | b_hi, idesc, 1u);
+                        umma_tf32_ts(d, a_hi, DESC_HI | b_lo, idesc, 1u);
                         acc = 1u;
+                        a_hi += 8; a_lo += 8;
+                        const uint32_t step = (j & 3u) == 3u ? kb_step : 2u;
+                        b_hi += step; b_lo += step;
                     }
                     if (op.flags & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
                     if (op.commit_mma >= 0) tc_commit(smem_u32(bar_mma + op.commit_mma));
