@@ -97,18 +97,15 @@ static int upload_eq_src(sdfa_handle *h) {
     return SDFA_OK;
 }
 
-// compact float -> (source triangle * 9 + component) of the block-planar decode layout, -1 where nothing is decoded
+// compact slot -> (source triangle * 9 + component) of the frame-tiled decode layout, -1 where nothing is decoded
 static std::vector<int32_t> compact_map(const sdfa_handle *h) {
     const AssemblyPlan &ap = h->host.asmplan;
     std::vector<int32_t> map((size_t)ap.compact_stride, -1);
-    for (size_t b = 0; b < ap.blocks.size(); ++b) {
-        const int ne = ap.blocks[b].eq_end - ap.blocks[b].eq_begin;
-        for (int e = 0; e < ne; ++e) {
-            const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
-            if (src < 0) continue;
-            for (int j = 0; j < 9; ++j)
-                map[(size_t)ap.blk_coff[b] + (size_t)e * 9 + j] = src * 9 + j;
-        }
+    for (size_t g = 0; g < ap.eq_id.size(); ++g) {
+        const int src = h->eq_src_host[ap.eq_id[g]];
+        if (src < 0) continue;
+        for (int j = 0; j < 6; ++j) map[g * 6 + j] = src * 9 + j;
+        for (int j = 0; j < 3; ++j) map[(size_t)ap.compact_s_rows + g * 3 + j] = src * 9 + 6 + j;
     }
     return map;
 }
@@ -237,8 +234,8 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             d.asm_max_rows = ap.max_rows_per_block;
             std::vector<int32_t> tmp(p.n_eq, 0);
             if ((r = upload_mut(h, tmp, &d.eq_src))) return r;
-            if ((r = upload(h, ap.blk_coff, &d.asm_coff))) return r;
             d.compact_stride = ap.compact_stride;
+            d.compact_s_rows = ap.compact_s_rows;
             if ((r = upload(h, p.prog.bytes, &d.prog))) return r;
             if ((r = upload(h, p.prog.stage_off, &d.stage_off))) return r;
             if ((r = upload(h, p.prog.io_desc, &d.io_desc))) return r;
@@ -520,36 +517,27 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     d.k_scale = k_scale; d.k_rotat = k_rotat;
     if ((rc = pack_full(compT_scale, means_scale, 6, k_scale, &d.wfull_scale, &d.mfull_scale))) return rc;
     if ((rc = pack_full(compT_rotat, means_rotat, 3, k_rotat, &d.wfull_rotat, &d.mfull_rotat))) return rc;
-    // tensor-core path: one GEMM row per float of the block-planar compact layout (planes 0,1 from the
-    // scale basis, plane 2 from the rotation basis), split into TF32 hi/lo and stored as tile images
+    // tensor-core path: one GEMM row per slot of the frame-tiled compact layout (scale part, rotation part), split
+    // into TF32 hi/lo and stored as tile images; the means ride along as an extra K column
     {
         const AssemblyPlan &ap = h->host.asmplan;
-        std::vector<int32_t> src_s, off_s, src_r, off_r;
-        for (size_t b = 0; b < ap.blocks.size(); ++b) {
-            const int ne = ap.blocks[b].eq_end - ap.blocks[b].eq_begin;
-            for (int e = 0; e < ne; ++e) {
-                const int src = h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]];
-                if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
-                for (int j = 0; j < 9; ++j) {
-                    const int32_t off = ap.blk_coff[b] + e * 9 + j;
-                    if (j < 6) { src_s.push_back(src < 0 ? -1 : src * 6 + j); off_s.push_back(off); }
-                    else { src_r.push_back(src < 0 ? -1 : src * 3 + (j - 6)); off_r.push_back(off); }
-                }
-            }
+        std::vector<int32_t> src_s, src_r;
+        for (size_t g = 0; g < ap.eq_id.size(); ++g) {
+            const int src = h->eq_src_host[ap.eq_id[g]];
+            if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
+            for (int j = 0; j < 6; ++j) src_s.push_back(src < 0 ? -1 : src * 6 + j);
+            for (int j = 0; j < 3; ++j) src_r.push_back(src < 0 ? -1 : src * 3 + j);
         }
-        auto build = [&](const float *W, const float *m, int K, const std::vector<int32_t> &src, const std::vector<int32_t> &off,
-                         float **dw, float **db, int32_t **doff, int *mt) -> int {
-            std::vector<float> img, bias;
-            std::vector<int32_t> o;
-            tc_build_basis(W, m, K, src, off, img, bias, o);
-            *mt = (int)(bias.size() / 256);
-            int r;
-            if ((r = upload_mut(h, img, dw))) return r;
-            if ((r = upload_mut(h, bias, db))) return r;
-            return upload_mut(h, o, doff);
+        auto build = [&](const float *W, const float *m, int K, const std::vector<int32_t> &src, float **dw, int *mt) -> int {
+            std::vector<float> img;
+            *mt = tc_build_basis(W, m, K, src, img);
+            return upload_mut(h, img, dw);
         };
-        if ((rc = build(compT_scale, means_scale, k_scale, src_s, off_s, &d.tc_w_scale, &d.tc_b_scale, &d.tc_o_scale, &d.tc_mt_scale))) return rc;
-        if ((rc = build(compT_rotat, means_rotat, k_rotat, src_r, off_r, &d.tc_w_rotat, &d.tc_b_rotat, &d.tc_o_rotat, &d.tc_mt_rotat))) return rc;
+        if ((rc = build(compT_scale, means_scale, k_scale, src_s, &d.tc_w_scale, &d.tc_mt_scale))) return rc;
+        if ((rc = build(compT_rotat, means_rotat, k_rotat, src_r, &d.tc_w_rotat, &d.tc_mt_rotat))) return rc;
+        if (d.tc_mt_scale * tc_rows_per_tile() != d.compact_s_rows ||
+            d.tc_mt_rotat * tc_rows_per_tile() != d.compact_stride - d.compact_s_rows)
+            return fail(SDFA_ERR_STATE, "sdfa_set_pca: compact layout and decode tiles disagree");
     }
     h->has_pca = h->has_full_pca = true;
     return SDFA_OK;

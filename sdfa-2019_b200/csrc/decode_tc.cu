@@ -117,10 +117,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
 struct GemmParams {
     const float *w_img;      // [m_tiles][kb][hi,lo][256x32 swizzled]
     const float *x_img;      // [n_tiles][kb][hi,lo][128x32 swizzled]
-    const float *bias;       // [m_tiles*128]
-    const int32_t *out_off;  // [m_tiles*128] slot of the row in the compact dgrad, -1 for padding rows
     float *out;              // [tiles of 32 frames][out_stride][32]
-    long long out_stride;    // slots per frame
+    long long out_stride;    // slots per frame (scale part + rotation part)
+    int part_off;            // first slot of this basis' part: GEMM row r is slot part_off + r (the bias rides in the GEMM)
     int n_frames, m_tiles, n_tiles, kb;
 };
 
@@ -209,23 +208,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
             const int tile32 = n * (TC_BN / 32) + lane_grp;
             const bool live = tile32 * 32 < P.n_frames;             // 32-frame tiles past the batch are not stored
-            float *out_tile = P.out + (size_t)tile32 * P.out_stride * 32 + lane;
+            float *out_tile = P.out + ((size_t)tile32 * P.out_stride + P.part_off + (size_t)m * TC_BM + col_half * (TC_BM / 2)) * 32 + lane;
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BM + col_half * (TC_BM / 2);
 #pragma unroll 1
             for (int chunk = 0; chunk < TC_BM / 64; ++chunk) {
-                const int row0 = m * TC_BM + col_half * (TC_BM / 2) + chunk * 32;
-                const int off_l = P.out_off[row0 + lane];           // this lane's column's slot and bias, shuffled out below
-                const float b_l = P.bias[row0 + lane];
                 uint32_t v[32];
                 tmem_ld32(taddr + chunk * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (live) {
+                    float *dst = out_tile + chunk * 32 * 32;      // 32 slots further, each a line of 32 frames
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int off = __shfl_sync(0xffffffffu, off_l, c);
-                    const float b = __shfl_sync(0xffffffffu, b_l, c);
-                    if (live && off >= 0) __stcs(out_tile + (size_t)off * 32, __uint_as_float(v[c]) + b);
+                    for (int c = 0; c < 32; ++c) __stcs(dst + c * 32, __uint_as_float(v[c]));
                 }
             }
             tc_fence_before();
@@ -250,7 +245,8 @@ __global__ void k_split_coeffs(const float *__restrict__ x, int K, int n_frames,
         const int r = i / (kb_count * TC_BK), kk = i - r * (kb_count * TC_BK);
         const int kb = kk / TC_BK, k = kk - kb * TC_BK;
         const int frame = n_tile * TC_BN + r, kg = kb * TC_BK + k;
-        const float v = (frame < n_frames && kg < K) ? x[(long long)frame * K + kg] : 0.f;
+        // column K is the constant 1 that multiplies the means stored as column K of the basis images
+        const float v = kg == K ? 1.f : ((frame < n_frames && kg < K) ? x[(long long)frame * K + kg] : 0.f);
         const float hi = tf32_hi(v);
         float *tile = img + ((size_t)n_tile * kb_count + kb) * (2 * TC_BN * TC_BK);
         tile[swz(r, k)] = hi;
@@ -260,32 +256,29 @@ __global__ void k_split_coeffs(const float *__restrict__ x, int K, int n_frames,
 
 }  // namespace
 
-int tc_kblocks(int K) { return (K + TC_BK - 1) / TC_BK; }
+int tc_kblocks(int K) { return (K + 1 + TC_BK - 1) / TC_BK; }   // + the bias column
 size_t tc_ximg_floats(int n_frames, int K) {
     return (size_t)((n_frames + TC_BN - 1) / TC_BN) * tc_kblocks(K) * 2 * TC_BN * TC_BK;
 }
 
-// Host: pre-split, pre-tiled basis images + per-row bias and output offset.
-void tc_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src,
-                    const std::vector<int32_t> &rows_off, std::vector<float> &img, std::vector<float> &bias,
-                    std::vector<int32_t> &off) {
+// Host: pre-split, pre-tiled basis images; GEMM row r = compact slot r of the basis' part, rows_src[r] = row of the
+// [*, K] basis W it reproduces (-1: nothing, the slot decodes to 0); the means become column K.
+int tc_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src, std::vector<float> &img) {
     const int rows = (int)rows_src.size(), m_tiles = (rows + TC_BM - 1) / TC_BM, kbs = tc_kblocks(K);
     img.assign((size_t)m_tiles * kbs * 2 * TC_BM * TC_BK, 0.f);
-    bias.assign((size_t)m_tiles * TC_BM, 0.f);
-    off.assign((size_t)m_tiles * TC_BM, -1);
     for (int r = 0; r < rows; ++r) {
         const int m = r / TC_BM, rl = r % TC_BM, src = rows_src[r];
-        off[r] = rows_off[r];
         if (src < 0) continue;
-        bias[r] = mean[src];
-        for (int k = 0; k < K; ++k) {
-            const float v = W[(size_t)src * K + k], hi = tf32_hi(v);
+        for (int k = 0; k <= K; ++k) {
+            const float v = k < K ? W[(size_t)src * K + k] : mean[src], hi = tf32_hi(v);
             float *tile = &img[((size_t)m * kbs + k / TC_BK) * (2 * TC_BM * TC_BK)];
             tile[swz(rl, k % TC_BK)] = hi;
             tile[TC_BM * TC_BK + swz(rl, k % TC_BK)] = v - hi;
         }
     }
+    return m_tiles;
 }
+int tc_rows_per_tile() { return TC_BM; }
 
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream) {
@@ -307,8 +300,7 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
         count_launch();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        GemmParams P{g == 0 ? d.tc_w_scale : d.tc_w_rotat, ximg, g == 0 ? d.tc_b_scale : d.tc_b_rotat,
-                     g == 0 ? d.tc_o_scale : d.tc_o_rotat, dgrad_out, stride, n_frames,
+        GemmParams P{g == 0 ? d.tc_w_scale : d.tc_w_rotat, ximg, dgrad_out, stride, g == 0 ? 0 : d.compact_s_rows, n_frames,
                      g == 0 ? d.tc_mt_scale : d.tc_mt_rotat, n_tiles, kbs};
         int grid = P.m_tiles * n_tiles;
         if (grid > d.sm_count) grid = d.sm_count;

@@ -31,8 +31,7 @@ struct DevicePlan {
     const int16_t  *asm_warp_sched = nullptr;   // per (block, warp) walk: equations, barrier marks, end mark
     const int32_t  *asm_warp_ptr = nullptr;
     int32_t        *eq_src = nullptr;       // equation block -> source triangle (>=0), -1 identity, -2 zero block
-    const int32_t  *asm_coff = nullptr;     // first slot of each block in the frame-tiled compact dgrad
-    int compact_stride = 0;
+    int compact_stride = 0, compact_s_rows = 0;   // slots per frame of the compact dgrad; the rotation part starts at s_rows
     // ---- solve (K3)
     const uint8_t  *prog = nullptr;         // 16-byte aligned stage stream
     const uint32_t *stage_off = nullptr;
@@ -60,8 +59,7 @@ struct DevicePlan {
     int k_scale = 0, k_rotat = 0;
     float *wfull_scale = nullptr, *mfull_scale = nullptr, *wfull_rotat = nullptr, *mfull_rotat = nullptr;
     // tensor-core decode (decode_tc.cu): pre-split, pre-tiled basis images, bias and output offsets per row
-    float *tc_w_scale = nullptr, *tc_w_rotat = nullptr, *tc_b_scale = nullptr, *tc_b_rotat = nullptr;
-    int32_t *tc_o_scale = nullptr, *tc_o_rotat = nullptr;
+    float *tc_w_scale = nullptr, *tc_w_rotat = nullptr;
     int tc_mt_scale = 0, tc_mt_rotat = 0;
 };
 
@@ -90,10 +88,9 @@ size_t solve_smem_bytes(int n_slots, int frames_per_tile);
 void count_launch();
 long long launch_counter();
 
-// rows_src[r] = row of the [*, K] basis W that GEMM row r reproduces (or -1: zero row), rows_off[r] = where
-// its output goes inside a frame's compact row
-void tc_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src,
-                    const std::vector<int32_t> &rows_off, std::vector<float> &img, std::vector<float> &bias,
-                    std::vector<int32_t> &off);
+// rows_src[r] = row of the [*, K] basis W that GEMM row r (= compact slot r of the part) reproduces, or -1;
+// returns the number of row tiles
+int tc_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src, std::vector<float> &img);
+int tc_rows_per_tile();
 
 }  // namespace sdfa

@@ -79,9 +79,9 @@ struct AsmParams {
     const short4 *eq_rows;
     const int32_t *row_perm;
     const int32_t *eq_src;
-    const int32_t *blk_coff;
     const float *dgrad;
     long long frame_stride;                  // !STAGED: floats per frame; STAGED: slots per frame
+    int s_rows;                              // STAGED: first rotation slot
     float *rhs;
     int n_frames, mode, max_rows;
     ScratchLayout L;
@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     const int nvalid = min(32, P.n_frames - frame0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < n_rows * 96; i += ASM_THREADS) acc[i] = 0.f;
-    // STAGED: line j of block-local equation e; !STAGED: this lane's frame (clamped inside the batch)
-    const float *in = STAGED ? P.dgrad + ((long long)tile * P.frame_stride + P.blk_coff[blockIdx.x]) * 32 + lane
+    // STAGED: this tile's lines (six scale lines and three rotation lines per equation); !STAGED: this lane's frame
+    // (clamped inside the batch)
+    const float *in = STAGED ? P.dgrad + (long long)tile * P.frame_stride * 32 + lane
                              : P.dgrad + (long long)min(frame0 + lane, P.n_frames - 1) * P.frame_stride;
     const int16_t *walk = P.warp_sched + P.warp_ptr[blockIdx.x * ASM_WARPS + warp];
     // fetch of one equation: its source triangle and the nine values of this lane's frame
@@ -128,9 +129,17 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
         if (e < 0) return;
         src = P.eq_src[P.eq_id[blk.x + e]];
         if (src < 0) return;
-        const float *q = STAGED ? in + (size_t)e * 9 * 32 : in + (long long)src * 9;
+        if (STAGED) {
+            const float *qs = in + (size_t)(blk.x + e) * 6 * 32, *qr = in + ((size_t)P.s_rows + (size_t)(blk.x + e) * 3) * 32;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) d[j] = STAGED ? __ldcs(q + j * 32) : __ldg(q + j);
+            for (int j = 0; j < 6; ++j) d[j] = __ldcs(qs + j * 32);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) d[6 + j] = __ldcs(qr + j * 32);
+        } else {
+            const float *q = in + (long long)src * 9;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) d[j] = __ldg(q + j);
+        }
     };
     // the equation's corner vectors for this lane's frame, added to the block rows of its three corners
     auto apply = [&](int e, int src, const float (&d)[9]) {
@@ -216,7 +225,7 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     AsmParams P{d.asm_blocks, d.asm_warp_sched, d.asm_warp_ptr, d.asm_eq_id, d.asm_eq_u, d.asm_eq_rows, d.asm_row_perm,
-                d.eq_src, d.asm_coff, dgrad, frame_stride, rhs, n_frames, mode, d.asm_max_rows, d.layout};
+                d.eq_src, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.layout};
     const size_t smem = (size_t)d.asm_max_rows * 96 * sizeof(float);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

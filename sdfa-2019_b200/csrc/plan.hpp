@@ -106,9 +106,10 @@ struct AssemblyPlan {
     std::vector<int32_t> warp_ptr;      // [blocks * ASM_WARPS_PER_BLOCK] start of each walk in warp_sched
     int max_eq_per_block = 0, max_rows_per_block = 0;
     // Frame-tiled compact dgrad (what the decode kernel writes and the staged assembly reads):
-    // [tile of 32 frames][slot][32 frames], slot = blk_coff[b] + 9 * (block-local equation) + component
-    // (components in the reference order s00,s01,s02,s11,s12,s22,r01,r02,r12).
-    std::vector<int32_t> blk_coff;
+    // [tile of 32 frames][slot][32 frames]; block-local equation g (index into eq_id) owns the scale slots
+    // 6 g .. 6 g + 5 (s00,s01,s02,s11,s12,s22) and the rotation slots compact_s_rows + 3 g .. + 2 (r01,r02,r12);
+    // both parts are padded to whole GEMM row tiles, so a decode GEMM row is simply its slot.
+    int compact_s_rows = 0;
     int compact_stride = 0;             // slots = floats per frame
 };
 

@@ -701,11 +701,11 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
         ap.max_rows_per_block = std::max(ap.max_rows_per_block, blk.row_end - blk.row_begin);
         ap.blocks.push_back(blk);
     }
-    // frame-tiled compact dgrad: slot = blk_coff[b] + 9 * (block-local equation) + component
-    for (auto &blk : ap.blocks) {
-        ap.blk_coff.push_back(ap.compact_stride);
-        ap.compact_stride += 9 * (blk.eq_end - blk.eq_begin);
-    }
+    // frame-tiled compact dgrad: a scale part (6 slots per block-local equation) and a rotation part (3), each
+    // padded to whole 256-row GEMM tiles of the decode kernel
+    const int E = (int)ap.eq_id.size();
+    ap.compact_s_rows = (6 * E + 255) / 256 * 256;
+    ap.compact_stride = ap.compact_s_rows + (3 * E + 255) / 256 * 256;
 }
 
 }  // namespace sdfa
