@@ -94,6 +94,19 @@ static int upload_eq_src(sdfa_handle *h) {
     if (h->dev.device < 0) return SDFA_OK;
     CUDA_TRY(cudaSetDevice(h->dev.device));
     CUDA_TRY(cudaMemcpy(h->dev.eq_src, h->eq_src_host.data(), h->eq_src_host.size() * 4, cudaMemcpyHostToDevice));
+    // the assembly walks carry every equation's current source triangle next to it
+    const AssemblyPlan &ap = h->host.asmplan;
+    std::vector<int2> walk(ap.warp_sched.size());
+    for (size_t b = 0; b < ap.blocks.size(); ++b)
+        for (int w = 0; w < ASM_WARPS_PER_BLOCK; ++w)
+            for (int i = ap.warp_ptr[b * ASM_WARPS_PER_BLOCK + w]; i < ap.warp_ptr[b * ASM_WARPS_PER_BLOCK + w + 1]; ++i) {
+                const int e = ap.warp_sched[i];
+                walk[i] = make_int2(e, e >= 0 ? h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]] : -1);
+            }
+    CUDA_TRY(cudaMemcpy(h->dev.asm_walk, walk.data(), walk.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    std::vector<int32_t> local(ap.eq_id.size());
+    for (size_t g = 0; g < local.size(); ++g) local[g] = h->eq_src_host[ap.eq_id[g]];
+    CUDA_TRY(cudaMemcpy(h->dev.asm_eq_src_local, local.data(), local.size() * 4, cudaMemcpyHostToDevice));
     return SDFA_OK;
 }
 
@@ -219,15 +232,29 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             for (auto &b : ap.blocks) blocks.push_back(make_int4(b.eq_begin, b.eq_end, b.row_begin, b.row_end));
             int r;
             if ((r = upload_mut(h, blocks, &d.asm_blocks))) return r;
-            if ((r = upload(h, ap.eq_id, &d.asm_eq_id))) return r;
-            if ((r = upload(h, ap.eq_u, &d.asm_eq_u))) return r;
+            {
+                // equation record: U0, U1 and, in the two spare floats, the block rows of the three corners
+                std::vector<float4> meta(ap.eq_id.size() * 2);
+                for (size_t g = 0; g < ap.eq_id.size(); ++g) {
+                    float rec[8];
+                    std::memcpy(rec, &ap.eq_u[g * 8], 24);
+                    std::memcpy(rec + 6, &ap.eq_rows[g * 4], 8);
+                    std::memcpy(&meta[2 * g], rec, 32);
+                }
+                if ((r = upload(h, meta, &d.asm_eq_meta))) return r;
+            }
             if ((r = upload(h, ap.row_perm, &d.asm_row_perm))) return r;
             {
-                std::vector<short4> er(ap.eq_rows.size() / 4);
-                for (size_t i = 0; i < er.size(); ++i) er[i] = make_short4(ap.eq_rows[4 * i], ap.eq_rows[4 * i + 1], ap.eq_rows[4 * i + 2], 0);
-                if ((r = upload(h, er, &d.asm_eq_rows))) return r;
-                if ((r = upload(h, ap.warp_sched, &d.asm_warp_sched))) return r;
+                std::vector<int2> walk(ap.warp_sched.size(), make_int2(0, -1));
+                if ((r = upload_mut(h, walk, &d.asm_walk))) return r;          // filled by upload_eq_src
                 if ((r = upload(h, ap.warp_ptr, &d.asm_warp_ptr))) return r;
+                if ((r = upload(h, ap.colour_ptr, &d.asm_colour_ptr))) return r;
+                if ((r = upload(h, ap.row_ptr, &d.asm_row_ptr))) return r;
+                if ((r = upload(h, ap.inc, &d.asm_inc))) return r;
+                std::vector<int32_t> local(ap.eq_id.size(), -1);
+                if ((r = upload_mut(h, local, &d.asm_eq_src_local))) return r;
+                d.asm_max_walk = 0;
+                for (size_t i = 0; i + 1 < ap.warp_ptr.size(); ++i) d.asm_max_walk = std::max(d.asm_max_walk, ap.warp_ptr[i + 1] - ap.warp_ptr[i]);
             }
             d.n_asm_blocks = (int)ap.blocks.size();
             d.asm_max_eq = ap.max_eq_per_block;

@@ -24,12 +24,15 @@ struct DevicePlan {
     // ---- assembly (K2)
     int n_asm_blocks = 0, asm_max_eq = 0, asm_max_rows = 0;
     int4           *asm_blocks = nullptr;   // {eq_begin, eq_end, row_begin, row_end}
-    const int32_t  *asm_eq_id = nullptr;    // block-local equation -> equation block
-    const float    *asm_eq_u = nullptr;     // 6 floats per block-local equation
-    const short4   *asm_eq_rows = nullptr;  // block rows of the equation's three corners
+    const float4   *asm_eq_meta = nullptr;  // per block-local equation: U0[3], U1[3], then the block rows of its corners (4 x int16)
     const int32_t  *asm_row_perm = nullptr;
-    const int16_t  *asm_warp_sched = nullptr;   // per (block, warp) walk: equations, barrier marks, end mark
-    const int32_t  *asm_warp_ptr = nullptr;
+    int2           *asm_walk = nullptr;     // per (block, warp) walk: {block-local equation or barrier / end mark, its source triangle}
+    const int32_t  *asm_warp_ptr = nullptr; // [blocks * 8 + 1]
+    int asm_max_walk = 0;
+    const int32_t  *asm_colour_ptr = nullptr;   // [blocks][ASM_MAX_COLOURS + 1]
+    int32_t        *asm_eq_src_local = nullptr; // source triangle per block-local equation
+    const int32_t  *asm_row_ptr = nullptr;      // CSR incidence of the block rows (gather variant)
+    const uint16_t *asm_inc = nullptr;
     int32_t        *eq_src = nullptr;       // equation block -> source triangle (>=0), -1 identity, -2 zero block
     int compact_stride = 0, compact_s_rows = 0;   // slots per frame of the compact dgrad; the rotation part starts at s_rows
     // ---- solve (K3)

@@ -68,22 +68,23 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // rows, one 128-byte line per warp instruction.
 // E is evaluated without ever forming 1 + small:  E u = t + Q (u + t),  t = Es u,
 //   Q v = a W v + b W (W v),  a = sin(th)/th,  b = (1 - cos th)/th^2 = 2 sin^2(th/2)/th^2.
-// Input: STAGED = the decode kernel's frame-tiled compact buffer [tile][slot][32] (nine coalesced lines per
-// equation); !STAGED = any [frame][triangle][9] tensor (the reference's dgrad layout), gathered per lane.
+// Input: the decode kernel's frame-tiled compact buffer [tile][slot][32] (nine coalesced lines per equation);
+// k_assemble_gather below takes any [frame][triangle][9] tensor (the reference's dgrad layout) instead.
 struct AsmParams {
     const int4 *blocks;                      // {eq_begin, eq_end, row_begin, row_end}
-    const int16_t *warp_sched;               // per (block, warp): equations, ASM_SCHED_BARRIER, ..., ASM_SCHED_END
+    const int2 *walk;                        // per (block, warp): {equation | ASM_SCHED_BARRIER | ASM_SCHED_END, source triangle}
     const int32_t *warp_ptr;
-    const int32_t *eq_id;
-    const float *eq_u;
-    const short4 *eq_rows;
+    const float4 *eq_meta;                   // 2 per block-local equation: U0, U1, corner rows
     const int32_t *row_perm;
-    const int32_t *eq_src;
+    const int32_t *eq_src_local;             // source triangle per block-local equation (gather variant)
+    const int32_t *row_ptr;                  // CSR incidence of the block rows (gather variant)
+    const uint16_t *inc;
+    int max_eq;
     const float *dgrad;
-    long long frame_stride;                  // !STAGED: floats per frame; STAGED: slots per frame
-    int s_rows;                              // STAGED: first rotation slot
+    long long frame_stride;                  // gather variant: floats per frame; else slots per frame
+    int s_rows;                              // first rotation slot of the compact buffer
     float *rhs;
-    int n_frames, mode, max_rows;
+    int n_frames, mode, max_rows, max_walk;
     ScratchLayout L;
 };
 
@@ -105,10 +106,72 @@ __device__ __forceinline__ void corner_vec(const float *d, float a, float b, con
     g[2] = t2 + a * p2 + b * q2;
 }
 
+// The two corner vectors g2 = E*U0, g3 = E*U1 of one equation for one frame, E = R*S - I from the nine dgrad values
+// (mode ASM_DGRAD) or E = T - I from a raw row-major matrix (ASM_MATRIX).
+__device__ __forceinline__ void eq_vectors(int mode, const float (&d)[9], const float (&u0)[3], const float (&u1)[3],
+                                           float (&g2)[3], float (&g3)[3]) {
+    if (mode == ASM_DGRAD) {
+        const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
+        float a = 0.f, b = 0.f;
+        if (th2 >= 1e-12f) {        // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
+            if (th2 <= 1.f) {
+                // Taylor series in th^2 (remainder < 3e-8 for th <= 1): no sqrt, sin or division
+                a = 1.f - th2 * (1.f / 6.f) * (1.f - th2 * (1.f / 20.f) * (1.f - th2 * (1.f / 42.f) * (1.f - th2 * (1.f / 72.f))));
+                b = 0.5f - th2 * (1.f / 24.f) * (1.f - th2 * (1.f / 30.f) * (1.f - th2 * (1.f / 56.f) * (1.f - th2 * (1.f / 90.f))));
+            } else {
+                const float th = sqrtf(th2);
+                const float sh2 = sinf(0.5f * th);
+                a = sinf(th) / th;
+                b = 2.f * sh2 * sh2 / th2;
+            }
+        }
+        corner_vec(d, a, b, u0, g2);
+        corner_vec(d, a, b, u1, g3);
+    } else {                        // raw row-major T (impl.hpp:391-397): E = T - I
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            g2[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u0[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u0[1] +
+                    (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u0[2];
+            g3[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u1[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u1[1] +
+                    (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u1[2];
+        }
+    }
+}
+
+// One equation for one frame (this lane's): its corner vectors added to the accumulator rows of its corners.
+// m0, m1 = the equation record: U0, U1 and the block rows of the three corners.
+__device__ __forceinline__ void eq_apply(float *acc, int lane, int mode, int src, const float (&d)[9], float4 m0, float4 m1) {
+    if (src == -1) return;                                       // identity block (impl.hpp:264-268): T - I = 0
+    const float u0[3] = {m0.x, m0.y, m0.z}, u1[3] = {m0.w, m1.x, m1.y};
+    const uint32_t r01 = __float_as_uint(m1.z), r23 = __float_as_uint(m1.w);
+    const int rx = (short)(r01 & 0xFFFFu), ry = (short)(r01 >> 16), rz = (short)(r23 & 0xFFFFu);
+    float g2[3], g3[3];
+    if (src >= 0) eq_vectors(mode, d, u0, u1, g2, g3);
+    else {                              // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { g2[c] = -u0[c]; g3[c] = -u1[c]; }
+    }
+    // corner 0 (v1) gets -(g2+g3), corner 1 (v2) g2, corner 2 (v3) g3
+    if (rx >= 0) {
+        float *t = acc + rx * 96 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c * 32] -= g2[c] + g3[c];
+    }
+    if (ry >= 0) {
+        float *t = acc + ry * 96 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c * 32] += g2[c];
+    }
+    if (rz >= 0) {
+        float *t = acc + rz * 96 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c * 32] += g3[c];
+    }
+}
+
 constexpr int ASM_WARPS = ASM_WARPS_PER_BLOCK;
 constexpr int ASM_THREADS = 32 * ASM_WARPS;
 
-template <bool STAGED>
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     extern __shared__ __align__(16) float acc[];                     // [row][3][32]
     const int4 blk = P.blocks[blockIdx.x];
@@ -118,100 +181,42 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     const int nvalid = min(32, P.n_frames - frame0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < n_rows * 96; i += ASM_THREADS) acc[i] = 0.f;
-    // STAGED: this tile's lines (six scale lines and three rotation lines per equation); !STAGED: this lane's frame
-    // (clamped inside the batch)
-    const float *in = STAGED ? P.dgrad + (long long)tile * P.frame_stride * 32 + lane
-                             : P.dgrad + (long long)min(frame0 + lane, P.n_frames - 1) * P.frame_stride;
-    const int16_t *walk = P.warp_sched + P.warp_ptr[blockIdx.x * ASM_WARPS + warp];
-    // fetch of one equation: its source triangle and the nine values of this lane's frame
-    auto fetch = [&](int e, int &src, float (&d)[9]) {
-        src = -1;
-        if (e < 0) return;
-        src = P.eq_src[P.eq_id[blk.x + e]];
-        if (src < 0) return;
-        if (STAGED) {
-            const float *qs = in + (size_t)(blk.x + e) * 6 * 32, *qr = in + ((size_t)P.s_rows + (size_t)(blk.x + e) * 3) * 32;
+    // this tile's lines: six scale lines and three rotation lines per equation
+    const float *in = P.dgrad + (long long)tile * P.frame_stride * 32 + lane;
+    // the block's eight walks go to shared memory first, so that an entry costs a shared-memory read and the only
+    // long-latency loads are an equation's values and its record -- both issued one equation ahead
+    int2 *walk_sh = reinterpret_cast<int2 *>(acc + P.max_rows * 96);
+    {
+        const int w0 = P.warp_ptr[blockIdx.x * ASM_WARPS], w1 = P.warp_ptr[blockIdx.x * ASM_WARPS + ASM_WARPS];
+        for (int i = threadIdx.x; i < w1 - w0; i += ASM_THREADS) walk_sh[i] = P.walk[w0 + i];
+    }
+    const int2 *walk = walk_sh + (P.warp_ptr[blockIdx.x * ASM_WARPS + warp] - P.warp_ptr[blockIdx.x * ASM_WARPS]);
+    struct Eq { int e, src; float4 m0, m1; float d[9]; };
+    auto fetch = [&](int2 ent, Eq &q) {
+        q.e = ent.x; q.src = ent.y;
+        if (ent.x < 0) return;
+        q.m0 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2);
+        q.m1 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2 + 1);
+        // slots of identity / zero blocks hold zeros: always readable
+        const float *qs = in + (size_t)(blk.x + ent.x) * 6 * 32, *qr = in + ((size_t)P.s_rows + (size_t)(blk.x + ent.x) * 3) * 32;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) d[j] = __ldcs(qs + j * 32);
+        for (int j = 0; j < 6; ++j) q.d[j] = __ldcs(qs + j * 32);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) d[6 + j] = __ldcs(qr + j * 32);
-        } else {
-            const float *q = in + (long long)src * 9;
-#pragma unroll
-            for (int j = 0; j < 9; ++j) d[j] = __ldg(q + j);
-        }
+        for (int j = 0; j < 3; ++j) q.d[6 + j] = __ldcs(qr + j * 32);
     };
     // the equation's corner vectors for this lane's frame, added to the block rows of its three corners
-    auto apply = [&](int e, int src, const float (&d)[9]) {
-        if (src == -1) return;                                       // identity block (impl.hpp:264-268): T - I = 0
-        const int ge = blk.x + e;
-        const float4 ua = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2);
-        const float4 ub = __ldg(reinterpret_cast<const float4 *>(P.eq_u) + (size_t)ge * 2 + 1);
-        const short4 rw = __ldg(P.eq_rows + ge);
-        const float u0[3] = {ua.x, ua.y, ua.z}, u1[3] = {ua.w, ub.x, ub.y};
-        float g2[3], g3[3];
-        if (src >= 0) {
-            if (P.mode == ASM_DGRAD) {
-                const float th2 = d[6] * d[6] + d[7] * d[7] + d[8] * d[8];
-                float a = 0.f, b = 0.f;
-                if (th2 >= 1e-12f) {        // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
-                    if (th2 <= 1.f) {
-                        // Taylor series in th^2 (remainder < 3e-8 for th <= 1): no sqrt, sin or division
-                        a = 1.f - th2 * (1.f / 6.f) * (1.f - th2 * (1.f / 20.f) * (1.f - th2 * (1.f / 42.f) * (1.f - th2 * (1.f / 72.f))));
-                        b = 0.5f - th2 * (1.f / 24.f) * (1.f - th2 * (1.f / 30.f) * (1.f - th2 * (1.f / 56.f) * (1.f - th2 * (1.f / 90.f))));
-                    } else {
-                        const float th = sqrtf(th2);
-                        const float sh2 = sinf(0.5f * th);
-                        a = sinf(th) / th;
-                        b = 2.f * sh2 * sh2 / th2;
-                    }
-                }
-                corner_vec(d, a, b, u0, g2);
-                corner_vec(d, a, b, u1, g3);
-            } else {                        // raw row-major T (impl.hpp:391-397): E = T - I
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    g2[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u0[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u0[1] +
-                            (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u0[2];
-                    g3[c] = (d[3 * c] - (c == 0 ? 1.f : 0.f)) * u1[0] + (d[3 * c + 1] - (c == 1 ? 1.f : 0.f)) * u1[1] +
-                            (d[3 * c + 2] - (c == 2 ? 1.f : 0.f)) * u1[2];
-                }
-            }
-        } else {                            // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { g2[c] = -u0[c]; g3[c] = -u1[c]; }
-        }
-        // corner 0 (v1) gets -(g2+g3), corner 1 (v2) g2, corner 2 (v3) g3
-        if (rw.x >= 0) {
-            float *t = acc + rw.x * 96 + lane;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) t[c * 32] -= g2[c] + g3[c];
-        }
-        if (rw.y >= 0) {
-            float *t = acc + rw.y * 96 + lane;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) t[c * 32] += g2[c];
-        }
-        if (rw.z >= 0) {
-            float *t = acc + rw.z * 96 + lane;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) t[c * 32] += g3[c];
-        }
-    };
+    auto apply = [&](const Eq &q) { eq_apply(acc, lane, P.mode, q.src, q.d, q.m0, q.m1); };
     // software pipeline over the warp's walk: the next equation's values are in flight while this one is applied
     // (also across the colour barriers)
-    int e0 = *walk++, s0, e1, s1;
-    float d0[9], d1[9];
-    fetch(e0, s0, d0);
-    __syncthreads();
-    while (e0 != ASM_SCHED_END) {
-        e1 = *walk++;
-        fetch(e1, s1, d1);
-        if (e0 == ASM_SCHED_BARRIER) __syncthreads(); else apply(e0, s0, d0);
-        if (e1 == ASM_SCHED_END) break;
-        e0 = *walk++;
-        fetch(e0, s0, d0);
-        if (e1 == ASM_SCHED_BARRIER) __syncthreads(); else apply(e1, s1, d1);
+    Eq qa, qb;
+    __syncthreads();                                                 // accumulator zeroed, walks in shared memory
+    fetch(*walk++, qa);
+    while (qa.e != ASM_SCHED_END) {
+        fetch(*walk++, qb);
+        if (qa.e == ASM_SCHED_BARRIER) __syncthreads(); else apply(qa);
+        if (qb.e == ASM_SCHED_END) break;
+        fetch(*walk++, qa);
+        if (qb.e == ASM_SCHED_BARRIER) __syncthreads(); else apply(qb);
     }
     const int fr = frame0 + lane;
     float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
@@ -221,18 +226,127 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     }
 }
 
+// Gather variant for any [frame][triangle][9] tensor (the reference's dgrad layout, possibly with correspondences).
+// The values of one frame sit in one 359 KB row, 36 bytes per active triangle, so this variant walks the tile frame
+// by frame with the whole CTA on one row at a time (neighbouring DRAM pages): thread = equation, its nine values
+// gathered with 4-byte cp.async copies two frames ahead into a double-buffered stage, corner vectors into shared
+// memory, then thread = row sums the incident corner vectors (CSR, fixed order, no atomics) into a
+// [row*3+c][33] transpose buffer; one block barrier per frame.
+constexpr int TPAD = 33;
+constexpr int ASM_KMAX = ASM_MAX_EQ / ASM_THREADS;
+
+__global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
+    extern __shared__ __align__(16) float sh[];
+    const int plane = (3 * P.max_eq + 3) & ~3;
+    float *stage = sh;                                              // [2][3 planes][plane]: the frame's values, planar
+    float *g_sh0 = sh + 6 * plane;                                  // [2][max_eq][9]: corner vectors, double buffered
+    float *t_sh = g_sh0 + 2 * P.max_eq * 9;                         // [rows*3][33]
+    int *src_sh = reinterpret_cast<int *>(t_sh + P.max_rows * 3 * TPAD);   // [max_eq]
+    const int4 blk = P.blocks[blockIdx.x];
+    const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
+    const int tile = blockIdx.y;
+    const int frame0 = tile * 32;
+    const int nvalid = min(32, P.n_frames - frame0);
+    for (int e = threadIdx.x; e < n_eq; e += ASM_THREADS) src_sh[e] = P.eq_src_local[blk.x + e];
+    __syncthreads();
+    int src_k[ASM_KMAX];
+    float4 m0_k[ASM_KMAX], m1_k[ASM_KMAX];
+#pragma unroll
+    for (int k = 0; k < ASM_KMAX; ++k) {
+        const int e = threadIdx.x + k * ASM_THREADS;
+        src_k[k] = -1;
+        m0_k[k] = m1_k[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n_eq) {
+            src_k[k] = src_sh[e];
+            m0_k[k] = __ldg(P.eq_meta + (size_t)(blk.x + e) * 2);
+            m1_k[k] = __ldg(P.eq_meta + (size_t)(blk.x + e) * 2 + 1);
+        }
+    }
+    // consecutive threads copy consecutive (equation, component) values, so that a warp's copy touches the few
+    // cache lines of three or four triangles instead of 32; one commit group per frame and thread
+    auto gather = [&](int ft, int si) {
+        const float *row = P.dgrad + (long long)(frame0 + ft) * P.frame_stride;
+        float *dst = stage + si * 3 * plane;
+        for (int v = threadIdx.x; v < n_eq * 9; v += ASM_THREADS) {
+            const int e = v / 9, j = v - 9 * e;
+            const int sr = src_sh[e];
+            if (sr < 0) continue;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (j / 3) * plane + e * 3 + (j % 3))),
+                         "l"(row + (long long)sr * 9 + j) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    gather(0, 0);
+    if (nvalid > 1) gather(1, 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");          // frame 0 has landed (this thread's part)
+    __syncthreads();
+    // iteration f computes the corner vectors of frame f into g_sh[f&1] and sums the rows of frame f-1
+    for (int f = 0; f <= nvalid; ++f) {
+        const float *st = stage + (f & 1) * 3 * plane;
+        float *g_sh = g_sh0 + (f & 1) * P.max_eq * 9;
+#pragma unroll
+        for (int k = 0; k < ASM_KMAX; ++k) {
+            const int e = threadIdx.x + k * ASM_THREADS;
+            if (e >= n_eq || f >= nvalid) break;
+            const int src = src_k[k];
+            const float u0[3] = {m0_k[k].x, m0_k[k].y, m0_k[k].z}, u1[3] = {m0_k[k].w, m1_k[k].x, m1_k[k].y};
+            float g2[3] = {0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};    // src == -1: identity block, T - I = 0
+            if (src >= 0) {
+                float d[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) d[j] = st[(j / 3) * plane + e * 3 + (j % 3)];
+                eq_vectors(P.mode, d, u0, u1, g2, g3);
+            } else if (src == -2) {             // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { g2[c] = -u0[c]; g3[c] = -u1[c]; }
+            }
+            float *g = g_sh + e * 9;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { g[c] = -(g2[c] + g3[c]); g[3 + c] = g2[c]; g[6 + c] = g3[c]; }
+        }
+        if (f >= 1) {
+            const float *gp = g_sh0 + ((f - 1) & 1) * P.max_eq * 9;
+            // rows are dealt from the top thread ids down: the low threads carry the extra equations above
+            for (int r = ASM_THREADS - 1 - threadIdx.x; r < n_rows; r += ASM_THREADS) {
+                const int gr = blk.z + r;
+                const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+                for (int q = q0; q < q1; ++q) {
+                    const float *g = gp + 3 * (int)P.inc[q];
+                    s0 += g[0]; s1 += g[1]; s2 += g[2];
+                }
+                float *t = t_sh + (3 * r) * TPAD + (f - 1);
+                t[0] = s0; t[TPAD] = s1; t[2 * TPAD] = s2;
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");       // frame f+1 has landed (this thread's copies; the barrier covers the rest)
+        __syncthreads();
+        if (f + 2 < nvalid) gather(f + 2, f & 1);                    // stage f&1 has been consumed
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fr = frame0 + lane;
+    float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
+    for (int line = warp; line < n_rows * 3; line += ASM_WARPS) {
+        const int r = line / 3, c = line - 3 * r;
+        dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride] = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
+    }
+}
+
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    AsmParams P{d.asm_blocks, d.asm_warp_sched, d.asm_warp_ptr, d.asm_eq_id, d.asm_eq_u, d.asm_eq_rows, d.asm_row_perm,
-                d.eq_src, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.layout};
-    const size_t smem = (size_t)d.asm_max_rows * 96 * sizeof(float);
-    cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    AsmParams P{d.asm_blocks, d.asm_walk, d.asm_warp_ptr, d.asm_eq_meta, d.asm_row_perm, d.asm_eq_src_local, d.asm_row_ptr, d.asm_inc,
+                d.asm_max_eq, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.asm_max_walk, d.layout};
+    const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
+    const size_t smem = staged ? (size_t)d.asm_max_rows * 96 * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int2)
+                               : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * TPAD + d.asm_max_eq) * sizeof(float);
+    cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)d.n_asm_blocks, (unsigned)((n_frames + 31) / 32));
-    if (staged) k_assemble<true><<<grid, ASM_THREADS, smem, stream>>>(P);
-    else k_assemble<false><<<grid, ASM_THREADS, smem, stream>>>(P);
+    if (staged) k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
+    else k_assemble_gather<<<grid, ASM_THREADS, smem, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
 }

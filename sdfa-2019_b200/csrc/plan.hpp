@@ -102,8 +102,10 @@ struct AssemblyPlan {
     std::vector<int16_t> eq_rows;       // 4 per entry: block row of corner 0, 1, 2 (-1: not a row of this block), pad
     std::vector<int32_t> colour_ptr;    // ASM_MAX_COLOURS + 1 per block: first block-local equation of each colour
     std::vector<int32_t> row_perm;      // per block-local row: scratch row (where to write)
+    std::vector<int32_t> row_ptr;       // rows + 1: incidence ranges (gather variant: per-row sums, frame at a time)
+    std::vector<uint16_t> inc;          // incidence: block-local equation * 3 + corner
     std::vector<int16_t> warp_sched;    // per (block, warp): block-local equations, ASM_SCHED_BARRIER between colours, ASM_SCHED_END
-    std::vector<int32_t> warp_ptr;      // [blocks * ASM_WARPS_PER_BLOCK] start of each walk in warp_sched
+    std::vector<int32_t> warp_ptr;      // [blocks * ASM_WARPS_PER_BLOCK + 1] start of each walk in warp_sched
     int max_eq_per_block = 0, max_rows_per_block = 0;
     // Frame-tiled compact dgrad (what the decode kernel writes and the staged assembly reads):
     // [tile of 32 frames][slot][32 frames]; block-local equation g (index into eq_id) owns the scale slots

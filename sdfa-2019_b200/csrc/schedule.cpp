@@ -587,6 +587,7 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
     // Row blocks by greedy growth over the mesh: start at the unassigned row with the smallest equation
     // index and keep adding the neighbouring row that brings the fewest new equations, so that few
     // equations are evaluated by more than one block (FLAME: 1.17x instead of 1.67x for index-sorted rows).
+    ap.row_ptr.push_back(0);
     std::vector<char> taken(n, 0), in_eqs(p.n_eq, 0);
     std::vector<int> by_key(n);
     std::iota(by_key.begin(), by_key.end(), 0);
@@ -693,7 +694,19 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
             }
             ap.warp_sched.push_back(ASM_SCHED_END);
         }
-        for (int f : rows) ap.row_perm.push_back(p.scratch_row[f]);
+        // row -> incident (equation, corner) pairs of the block (CSR), for the frame-at-a-time gather variant
+        {
+            std::vector<int> pos(eqs.size());
+            for (size_t i = 0; i < order.size(); ++i) pos[order[i]] = (int)i;
+            for (int f : rows) {
+                ap.row_perm.push_back(p.scratch_row[f]);
+                for (auto &kc : inc[f]) {
+                    const int sorted = (int)(std::lower_bound(eqs.begin(), eqs.end(), kc.first) - eqs.begin());
+                    ap.inc.push_back((uint16_t)(pos[sorted] * 3 + kc.second));
+                }
+                ap.row_ptr.push_back((int32_t)ap.inc.size());
+            }
+        }
         blk.eq_end = (int)ap.eq_id.size();
         blk.row_end = (int)ap.row_perm.size();
         blk.n_colours = n_colours;
@@ -701,6 +714,7 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
         ap.max_rows_per_block = std::max(ap.max_rows_per_block, blk.row_end - blk.row_begin);
         ap.blocks.push_back(blk);
     }
+    ap.warp_ptr.push_back((int32_t)ap.warp_sched.size());
     // frame-tiled compact dgrad: a scale part (6 slots per block-local equation) and a rotation part (3), each
     // padded to whole 256-row GEMM tiles of the decode kernel
     const int E = (int)ap.eq_id.size();
