@@ -7,15 +7,15 @@
 Workload (config.workload): configs[1] of BASELINE.json -- PCA-coefficient decode + reconstruction of
 240-frame sentences (4 s at 60 fps) on the FLAME template with the default mask (5023 v / 9976 tris, 3762
 constrained vertices, 2601 active triangles), random PCA basis (K = 85 scale + 180 rotation).  One step =
-one batch of S sentences per GPU (default 296 -> 71 040 frames), i.e. the three kernels of the path:
-K1 decode -> K2 assembly -> K3 solve (+ constrained-vertex fill).  Frames are sharded over ranks with no
+one batch of S sentences per GPU (default 315 -> 75 600 frames), i.e. the kernels of the path:
+K1 decode -> K2 assembly -> K3 solve -> K5 output (transpose + base + constrained vertices).  Frames are sharded over ranks with no
 data-path collective ("weak": per-GPU batch fixed).
 
   value     frames/s, inputs (coefficients, basis, factor) resident in HBM, CUDA-event timed, max over ranks
   e2e       same through the host-buffer C-ABI call (pinned host coefficients in, host vertices out)
   dgrad_resident  the same frames with the decoded dgrad [N, 9976*9] fp32 already in HBM (K2+K3 only):
             the literal "dgrad -> mesh" number SURVEY 8(d)'s 153 912 B/frame figure refers to
-  roofline  dominant kernel, live CUDA-event time from the library's per-stage events
+  roofline  dominant kernel, live CUDA-event time from the library's per-stage events; roofline_kernels lists all four
   cpu_baseline  the UNMODIFIED reference solver (oracle/_ref, all host threads) on a bounded sample
 """
 import argparse
@@ -37,12 +37,14 @@ N_VERTS, N_TRIS, N_FREE, N_ACTIVE = 5023, 9976, 1261, 2601
 BYTES_PATH = 36 * N_ACTIVE + 12 * N_VERTS          # 153 912 B/frame, SURVEY 8(d)
 BYTES_SOLVE = 2 * 12 * N_FREE                      # 30 264 B/frame: rhs in + solution out
 BYTES_ASSEMBLY = 36 * N_ACTIVE + 12 * N_FREE       # dgrad of the active triangles in + rhs out
+BYTES_OUTPUT = 12 * N_FREE + 12 * N_VERTS          # solved rows in + vertices out
 DECODE_FLOP = 2 * (N_ACTIVE * 6 * 85 + N_ACTIVE * 3 * 180)   # 5 462 100 useful FLOP/frame
 
 
 def ncu_traffic(kernel, n_frames):
     """DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json holds
-    bytes per frame measured at 15 360 frames per launch), scaled to this launch; None if absent."""
+    bytes per frame measured at 15 360 frames per launch, both decode launches added up), scaled to this launch;
+    None if absent."""
     path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         with open(path) as fp:
@@ -280,19 +282,34 @@ def main():
         return
     peaks, peak_src = measured_peaks()
     total = n * world
-    dom = max(("solve_ms", "assembly_ms", "decode_ms"), key=lambda k: stage[k])
+    dom = max(("solve_ms", "assembly_ms", "decode_ms", "output_ms"), key=lambda k: stage[k])
     if dom == "decode_ms":
-        ach = DECODE_FLOP * n / (stage[dom] * 1e-3) / 1e12
-        roof = {"kernel": "k_decode (K1)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
-                "note": "useful FLOP (active triangles) / launch time; fp32 CUDA-core kernel in this round"}
+        # issued MMA work: 3 TF32 products per K step, K padded to 32-wide blocks (the means ride in one of the pad
+        # columns), rows padded to 256-row tiles; peak = dense TF32 = half of the measured dense bf16 rate
+        rows_s, rows_r = -(-6 * rec.n_active // 256) * 256, -(-3 * rec.n_active // 256) * 256
+        issued = 3 * 2 * (rows_s * 96 + rows_r * 192)
+        ach = issued * n / (stage[dom] * 1e-3) / 1e12
+        peak = peaks["bf16_tflops"] / 2
+        roof = {"kernel": "k_decode_tc (K1)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": ncu_traffic("k_decode_tc", n),
+                "issued_flop_per_frame": issued, "useful_flop_per_frame": DECODE_FLOP,
+                "useful_tflops": DECODE_FLOP * n / (stage[dom] * 1e-3) / 1e12,
+                "note": "kind::tf32 3xTF32; peak = measured dense bf16 / 2 (no TF32 entry in MEASURED_PEAKS.json); "
+                        "the kernel also writes the 94 KB/frame compact dgrad"}
     else:
-        b = BYTES_SOLVE if dom == "solve_ms" else BYTES_ASSEMBLY
+        b, kname = {"solve_ms": (BYTES_SOLVE, "k_solve_tc" if rec.debug("ts_stats")[0] else "k_solve"),
+                    "assembly_ms": (BYTES_ASSEMBLY, "k_assemble"), "output_ms": (BYTES_OUTPUT, "k_output")}[dom]
         ach = b * n / (stage[dom] * 1e-3) / 1e9
-        kname = "k_solve" if dom == "solve_ms" else "k_assemble"
-        roof = {"kernel": kname + (" (K3)" if dom == "solve_ms" else " (K2)"), "bound": "hbm", "achieved": ach,
+        tag = {"solve_ms": " (K3)", "assembly_ms": " (K2)", "output_ms": " (K5)"}[dom]
+        roof = {"kernel": kname + tag, "bound": "hbm", "achieved": ach,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(kname, n),
                 "algorithmic_bytes_per_frame": b, "algorithmic_bytes_per_launch": b * n}
+    # every kernel of the path against its own algorithmic bytes (decode: the compact dgrad it must write)
+    per_kernel = {}
+    for key, nm, by in (("decode_ms", "k_decode_tc", 36 * N_ACTIVE), ("assembly_ms", "k_assemble", BYTES_ASSEMBLY),
+                        ("solve_ms", "k_solve", BYTES_SOLVE), ("output_ms", "k_output", BYTES_OUTPUT)):
+        gbs = by * n / (stage[key] * 1e-3) / 1e9
+        per_kernel[nm] = {"ms": stage[key], "algorithmic_bytes_per_frame": by, "achieved_gbs": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"]}
     roof["peak_source"] = peak_src
     path_gbs = BYTES_PATH * n / (ms_dgrad * 1e-3) / 1e9
     result = {
@@ -313,6 +330,7 @@ def main():
                           "achieved": path_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": path_gbs / peaks["hbm_gbs"]},
         "dgrad_resident": {"value": total / (ms_dgrad * 1e-3), "unit": "frames/s", "ms_per_step": ms_dgrad},
         "kernel_ms_per_step": stage,
+        "roofline_kernels": per_kernel,
     }
     if not args.no_cpu_baseline:
         ref = CpuReference(V, F, nfv, pca, os.cpu_count() or 1)

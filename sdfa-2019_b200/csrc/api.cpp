@@ -96,14 +96,15 @@ static int upload_eq_src(sdfa_handle *h) {
     CUDA_TRY(cudaMemcpy(h->dev.eq_src, h->eq_src_host.data(), h->eq_src_host.size() * 4, cudaMemcpyHostToDevice));
     // the assembly walks carry every equation's current source triangle next to it
     const AssemblyPlan &ap = h->host.asmplan;
-    std::vector<int2> walk(ap.warp_sched.size());
+    std::vector<int4> walk(ap.warp_sched.size());
     for (size_t b = 0; b < ap.blocks.size(); ++b)
         for (int w = 0; w < ASM_WARPS_PER_BLOCK; ++w)
             for (int i = ap.warp_ptr[b * ASM_WARPS_PER_BLOCK + w]; i < ap.warp_ptr[b * ASM_WARPS_PER_BLOCK + w + 1]; ++i) {
                 const int e = ap.warp_sched[i];
-                walk[i] = make_int2(e, e >= 0 ? h->eq_src_host[ap.eq_id[ap.blocks[b].eq_begin + e]] : -1);
+                const int g = ap.blocks[b].eq_begin + e;
+                walk[i] = e >= 0 ? make_int4(e, h->eq_src_host[ap.eq_id[g]], ap.eq_slot[g], 0) : make_int4(e, -1, 0, 0);
             }
-    CUDA_TRY(cudaMemcpy(h->dev.asm_walk, walk.data(), walk.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->dev.asm_walk, walk.data(), walk.size() * sizeof(int4), cudaMemcpyHostToDevice));
     std::vector<int32_t> local(ap.eq_id.size());
     for (size_t g = 0; g < local.size(); ++g) local[g] = h->eq_src_host[ap.eq_id[g]];
     CUDA_TRY(cudaMemcpy(h->dev.asm_eq_src_local, local.data(), local.size() * 4, cudaMemcpyHostToDevice));
@@ -114,8 +115,8 @@ static int upload_eq_src(sdfa_handle *h) {
 static std::vector<int32_t> compact_map(const sdfa_handle *h) {
     const AssemblyPlan &ap = h->host.asmplan;
     std::vector<int32_t> map((size_t)ap.compact_stride, -1);
-    for (size_t g = 0; g < ap.eq_id.size(); ++g) {
-        const int src = h->eq_src_host[ap.eq_id[g]];
+    for (size_t g = 0; g < h->host.active_eq.size(); ++g) {
+        const int src = h->eq_src_host[h->host.active_eq[g]];
         if (src < 0) continue;
         for (int j = 0; j < 6; ++j) map[g * 6 + j] = src * 9 + j;
         for (int j = 0; j < 3; ++j) map[(size_t)ap.compact_s_rows + g * 3 + j] = src * 9 + 6 + j;
@@ -245,7 +246,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             }
             if ((r = upload(h, ap.row_perm, &d.asm_row_perm))) return r;
             {
-                std::vector<int2> walk(ap.warp_sched.size(), make_int2(0, -1));
+                std::vector<int4> walk(ap.warp_sched.size(), make_int4(0, -1, 0, 0));
                 if ((r = upload_mut(h, walk, &d.asm_walk))) return r;          // filled by upload_eq_src
                 if ((r = upload(h, ap.warp_ptr, &d.asm_warp_ptr))) return r;
                 if ((r = upload(h, ap.colour_ptr, &d.asm_colour_ptr))) return r;
@@ -549,8 +550,8 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     {
         const AssemblyPlan &ap = h->host.asmplan;
         std::vector<int32_t> src_s, src_r;
-        for (size_t g = 0; g < ap.eq_id.size(); ++g) {
-            const int src = h->eq_src_host[ap.eq_id[g]];
+        for (size_t g = 0; g < h->host.active_eq.size(); ++g) {
+            const int src = h->eq_src_host[h->host.active_eq[g]];
             if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
             for (int j = 0; j < 6; ++j) src_s.push_back(src < 0 ? -1 : src * 6 + j);
             for (int j = 0; j < 3; ++j) src_r.push_back(src < 0 ? -1 : src * 3 + j);

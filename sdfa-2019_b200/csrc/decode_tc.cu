@@ -114,14 +114,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
         : "r"(taddr) : "memory");
 }
 
+// Both GEMMs (part 0 = scale basis, part 1 = rotation basis) run in ONE launch with their tiles interleaved
+// scale, scale, rotation: a scale tile (K = 96) is bound by its 128 KB of stores, a rotation tile (K = 192, same
+// stores, twice the MMAs) by the tensor pipe, so next to each other they overlap.
 struct GemmParams {
-    const float *w_img;      // [m_tiles][kb][hi,lo][256x32 swizzled]
-    const float *x_img;      // [n_tiles][kb][hi,lo][128x32 swizzled]
+    const float *w_img[2];   // [m_tiles][kb][hi,lo][256x32 swizzled]
+    const float *x_img[2];   // [n_tiles][kb][hi,lo][128x32 swizzled]
     float *out;              // [tiles of 32 frames][out_stride][32]
     long long out_stride;    // slots per frame (scale part + rotation part)
-    int part_off;            // first slot of this basis' part: GEMM row r is slot part_off + r (the bias rides in the GEMM)
-    int n_frames, m_tiles, n_tiles, kb;
+    int part_off[2];         // first slot of the part: GEMM row r is slot part_off + r (the bias rides in the GEMM)
+    int m_tiles[2], kb[2];
+    int n_frames, n_tiles;
 };
+
+struct TileInfo { int part, m, n; };
+// tile t of the launch: frame tile n = t / (m_tiles[0] + m_tiles[1]); inside it scale, scale, rotation, ... while both last
+__device__ __forceinline__ TileInfo tile_info(const GemmParams &P, int t) {
+    const int per_n = P.m_tiles[0] + P.m_tiles[1];
+    TileInfo ti;
+    ti.n = t / per_n;
+    const int q = t - ti.n * per_n;
+    const int triples = min(P.m_tiles[0] / 2, P.m_tiles[1]);
+    if (q < 3 * triples) {
+        const int tr = q / 3, r = q - 3 * tr;
+        ti.part = r == 2;
+        ti.m = r == 2 ? tr : 2 * tr + r;
+    } else {                                   // leftovers of the longer list
+        const int rest = q - 3 * triples, left0 = P.m_tiles[0] - 2 * triples;
+        ti.part = rest >= left0;
+        ti.m = ti.part ? triples + rest - left0 : 2 * triples + rest;
+    }
+    return ti;
+}
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 256 rows, M = 128 frames
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(TC_BN >> 4) << 24);
@@ -151,22 +175,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int n_tiles_total = P.m_tiles * P.n_tiles;
+    const int n_tiles_total = (P.m_tiles[0] + P.m_tiles[1]) * P.n_tiles;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-                const int m = tile % P.m_tiles, n = tile / P.m_tiles;
-                for (int kb = 0; kb < P.kb; ++kb, ++it) {
+                const TileInfo ti = tile_info(P, tile);
+                const int kbs = P.kb[ti.part];
+                const float *w = P.w_img[ti.part] + (size_t)ti.m * kbs * (2 * TC_BM * TC_BK);
+                const float *x = P.x_img[ti.part] + (size_t)ti.n * kbs * (2 * TC_BN * TC_BK);
+                for (int kb = 0; kb < kbs; ++kb, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     mbar_arrive_expect_tx(bar_full + 8 * s, TC_STAGE_BYTES);
                     const uint32_t dst = smem_u32(stages + s * TC_STAGE_BYTES);
-                    tma_bulk_g2s(dst, P.w_img + ((size_t)m * P.kb + kb) * (2 * TC_BM * TC_BK), 2 * TC_W_BYTES, bar_full + 8 * s);
-                    tma_bulk_g2s(dst + 2 * TC_W_BYTES, P.x_img + ((size_t)n * P.kb + kb) * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES,
-                                 bar_full + 8 * s);
+                    tma_bulk_g2s(dst, w + (size_t)kb * (2 * TC_BM * TC_BK), 2 * TC_W_BYTES, bar_full + 8 * s);
+                    tma_bulk_g2s(dst + 2 * TC_W_BYTES, x + (size_t)kb * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES, bar_full + 8 * s);
                 }
             }
         }
@@ -179,7 +205,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                 mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);         // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TC_BM;
-                for (int kb = 0; kb < P.kb; ++kb, ++it) {
+                const int kbs = P.kb[tile_info(P, tile).part];
+                for (int kb = 0; kb < kbs; ++kb, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
@@ -204,11 +231,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
         const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (basis rows) it drains
         uint32_t tc = 0;
         for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
-            const int m = tile % P.m_tiles, n = tile / P.m_tiles;
+            const TileInfo ti = tile_info(P, tile);
+            const int m = ti.m, n = ti.n;
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
             const int tile32 = n * (TC_BN / 32) + lane_grp;
             const bool live = tile32 * 32 < P.n_frames;             // 32-frame tiles past the batch are not stored
-            float *out_tile = P.out + ((size_t)tile32 * P.out_stride + P.part_off + (size_t)m * TC_BM + col_half * (TC_BM / 2)) * 32 + lane;
+            float *out_tile = P.out + ((size_t)tile32 * P.out_stride + P.part_off[ti.part] + (size_t)m * TC_BM + col_half * (TC_BM / 2)) * 32 + lane;
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BM + col_half * (TC_BM / 2);
@@ -294,21 +322,20 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
     const long long stride = d.compact_stride;
     for (int g = 0; g < 2; ++g) {
         const float *x = g == 0 ? coeff_scale : coeff_rotat;
-        const int K = g == 0 ? d.k_scale : d.k_rotat, kbs = tc_kblocks(K);
-        float *ximg = g == 0 ? ximg_scale : ximg_rotat;
-        k_split_coeffs<<<dim3(8, (unsigned)n_tiles), 256, 0, stream>>>(x, K, n_frames, kbs, ximg);
+        const int K = g == 0 ? d.k_scale : d.k_rotat;
+        k_split_coeffs<<<dim3(8, (unsigned)n_tiles), 256, 0, stream>>>(x, K, n_frames, tc_kblocks(K), g == 0 ? ximg_scale : ximg_rotat);
         count_launch();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        GemmParams P{g == 0 ? d.tc_w_scale : d.tc_w_rotat, ximg, dgrad_out, stride, g == 0 ? 0 : d.compact_s_rows, n_frames,
-                     g == 0 ? d.tc_mt_scale : d.tc_mt_rotat, n_tiles, kbs};
-        int grid = P.m_tiles * n_tiles;
-        if (grid > d.sm_count) grid = d.sm_count;
-        k_decode_tc<<<grid, TC_THREADS, smem, stream>>>(P);
-        count_launch();
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
     }
+    GemmParams P{{d.tc_w_scale, d.tc_w_rotat}, {ximg_scale, ximg_rotat}, dgrad_out, stride, {0, d.compact_s_rows},
+                 {d.tc_mt_scale, d.tc_mt_rotat}, {tc_kblocks(d.k_scale), tc_kblocks(d.k_rotat)}, n_frames, n_tiles};
+    int grid = (P.m_tiles[0] + P.m_tiles[1]) * n_tiles;
+    if (grid > d.sm_count) grid = d.sm_count;
+    k_decode_tc<<<grid, TC_THREADS, smem, stream>>>(P);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 

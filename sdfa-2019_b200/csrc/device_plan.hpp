@@ -26,7 +26,8 @@ struct DevicePlan {
     int4           *asm_blocks = nullptr;   // {eq_begin, eq_end, row_begin, row_end}
     const float4   *asm_eq_meta = nullptr;  // per block-local equation: U0[3], U1[3], then the block rows of its corners (4 x int16)
     const int32_t  *asm_row_perm = nullptr;
-    int2           *asm_walk = nullptr;     // per (block, warp) walk: {block-local equation or barrier / end mark, its source triangle}
+    int4           *asm_walk = nullptr;     // per (block, warp) walk: {block-local equation or barrier / end mark, its source triangle,
+                                            //  its slot group in the compact dgrad, -}
     const int32_t  *asm_warp_ptr = nullptr; // [blocks * 8 + 1]
     int asm_max_walk = 0;
     const int32_t  *asm_colour_ptr = nullptr;   // [blocks][ASM_MAX_COLOURS + 1]

@@ -72,7 +72,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // k_assemble_gather below takes any [frame][triangle][9] tensor (the reference's dgrad layout) instead.
 struct AsmParams {
     const int4 *blocks;                      // {eq_begin, eq_end, row_begin, row_end}
-    const int2 *walk;                        // per (block, warp): {equation | ASM_SCHED_BARRIER | ASM_SCHED_END, source triangle}
+    const int4 *walk;                        // per (block, warp): {equation | ASM_SCHED_BARRIER | ASM_SCHED_END, source triangle, slot group, -}
     const int32_t *warp_ptr;
     const float4 *eq_meta;                   // 2 per block-local equation: U0, U1, corner rows
     const int32_t *row_perm;
@@ -185,20 +185,20 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     const float *in = P.dgrad + (long long)tile * P.frame_stride * 32 + lane;
     // the block's eight walks go to shared memory first, so that an entry costs a shared-memory read and the only
     // long-latency loads are an equation's values and its record -- both issued one equation ahead
-    int2 *walk_sh = reinterpret_cast<int2 *>(acc + P.max_rows * 96);
+    int4 *walk_sh = reinterpret_cast<int4 *>(acc + P.max_rows * 96);
     {
         const int w0 = P.warp_ptr[blockIdx.x * ASM_WARPS], w1 = P.warp_ptr[blockIdx.x * ASM_WARPS + ASM_WARPS];
         for (int i = threadIdx.x; i < w1 - w0; i += ASM_THREADS) walk_sh[i] = P.walk[w0 + i];
     }
-    const int2 *walk = walk_sh + (P.warp_ptr[blockIdx.x * ASM_WARPS + warp] - P.warp_ptr[blockIdx.x * ASM_WARPS]);
+    const int4 *walk = walk_sh + (P.warp_ptr[blockIdx.x * ASM_WARPS + warp] - P.warp_ptr[blockIdx.x * ASM_WARPS]);
     struct Eq { int e, src; float4 m0, m1; float d[9]; };
-    auto fetch = [&](int2 ent, Eq &q) {
+    auto fetch = [&](int4 ent, Eq &q) {
         q.e = ent.x; q.src = ent.y;
         if (ent.x < 0) return;
         q.m0 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2);
         q.m1 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2 + 1);
         // slots of identity / zero blocks hold zeros: always readable
-        const float *qs = in + (size_t)(blk.x + ent.x) * 6 * 32, *qr = in + ((size_t)P.s_rows + (size_t)(blk.x + ent.x) * 3) * 32;
+        const float *qs = in + (size_t)ent.z * 6 * 32, *qr = in + ((size_t)P.s_rows + (size_t)ent.z * 3) * 32;
 #pragma unroll
         for (int j = 0; j < 6; ++j) q.d[j] = __ldcs(qs + j * 32);
 #pragma unroll
@@ -339,7 +339,7 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
     AsmParams P{d.asm_blocks, d.asm_walk, d.asm_warp_ptr, d.asm_eq_meta, d.asm_row_perm, d.asm_eq_src_local, d.asm_row_ptr, d.asm_inc,
                 d.asm_max_eq, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.asm_max_walk, d.layout};
     const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
-    const size_t smem = staged ? (size_t)d.asm_max_rows * 96 * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int2)
+    const size_t smem = staged ? (size_t)d.asm_max_rows * 96 * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4)
                                : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * TPAD + d.asm_max_eq) * sizeof(float);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
