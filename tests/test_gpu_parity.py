@@ -254,3 +254,61 @@ def test_config5_subdivided_template():
     # KAT: zero dgrad gives back the template
     z = r.get_mesh_batch(np.zeros((1, len(F) * 9), dtype=np.float32))
     assert np.abs(z[0] - V).max() <= 1e-8
+
+
+def test_tensor_and_simt_solvers_agree(chk, flame):
+    """K3T (tcgen05 block products, operands in tensor memory) and K3 (SIMT sweeps) on the same frames, against each
+    other and the checker; frame counts around the 128-column tile boundaries of K3T."""
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    rt = D.Reconstructor(V, F, cnsts=nfv, device=0, solver="tensor")
+    rs = D.Reconstructor(V, F, cnsts=nfv, device=0, solver="simt")
+    assert rt.debug("ts_stats")[0] == 1 and rs.debug("ts_stats")[0] == 0
+    dg = W.iid_dgrad(300, len(F), sigma=0.1, seed=11)
+    for n in (1, 127, 129, 300):
+        a, b = rt.get_mesh_batch(dg[:n]), rs.get_mesh_batch(dg[:n])
+        assert not np.isnan(a).any()
+        assert np.abs(a - b).max() <= 0.2 * tol, n
+    a = rt.get_mesh_batch(dg)
+    for i in (0, 127, 128, 255, 256, 299):
+        ref = chk.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(a[i] - ref).max() <= tol, i
+    # a frame's result does not depend on what else is in the batch or where it sits in a tile
+    assert np.array_equal(rt.get_mesh_batch(dg[200:201])[0], a[200])
+
+
+def test_config3_batch_sizes_give_identical_frames(rec, flame):
+    """Config 3 (solve sweep over RHS batches 64..4096): the same frames reconstructed in batches of different size
+    are bit-identical -- tiles are independent and the summation orders are fixed (no atomics anywhere)."""
+    import torch
+    F = flame["F"]
+    base = torch.from_numpy(W.iid_dgrad(64, len(F), sigma=0.02, seed=21)).cuda()
+    big = base.repeat(64, 1)                                   # 4096 frames
+    ref = rec.get_mesh_batch(base)
+    for n in (64, 128, 256, 512, 1024, 2048, 4096):
+        out = rec.get_mesh_batch(big[:n])
+        assert torch.equal(out[:64], ref) and torch.equal(out[n - 64:], ref), n
+
+
+def test_config4_network_to_mesh_on_device(rec, chk, flame):
+    """Config 4 in miniature: audio features -> random-init temporal network (plain torch, stands in for
+    speech_anime's model, config/model/dgrad.py:60-86) -> PCA coefficients -> K1..K5, everything staying on the
+    device; checked against fp32 F.linear decode + the reference solver on the same coefficients."""
+    import torch
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    cs, ms, cr, mr = W.random_pca(len(F), seed=1)
+    rec.set_pca(cs, ms, cr, mr)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv1d(128 * 3, 256, 5, padding=2), torch.nn.ReLU(),
+                              torch.nn.Conv1d(256, 85 + 180, 5, padding=2)).cuda()
+    feats = torch.randn(2, 128 * 3, 240, device="cuda")        # 2 utterances x 240 frames of mel + deltas
+    with torch.no_grad():
+        y = net(feats).permute(0, 2, 1).reshape(-1, 85 + 180)  # [480, 265]
+    xs, xr = y[:, :85].contiguous(), y[:, 85:].contiguous()
+    out = rec.decode_and_get_mesh(xs, xr)
+    assert out.is_cuda and out.shape == (480, 5023, 3)
+    lin_s = torch.nn.functional.linear(xs.cpu(), torch.from_numpy(cs), torch.from_numpy(ms))
+    lin_r = torch.nn.functional.linear(xr.cpu(), torch.from_numpy(cr), torch.from_numpy(mr))
+    dg = torch.cat((lin_s.view(480, -1, 6), lin_r.view(480, -1, 3)), dim=-1).view(480, -1).numpy()
+    for i in (0, 239, 240, 479):
+        ref = chk.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(out[i].cpu().numpy() - ref).max() <= tol, i
