@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -51,6 +52,7 @@ struct Builder {
     std::vector<std::vector<int>> adj;
     std::vector<TNode> nodes;
     int leaf_max;
+    int merge_cap = TS_MAX_NODE;          // largest separator node that folding may create
     std::string err;
 
     Builder(HostPlan &hp, int lm) : p(hp), t(hp.tplan), n(hp.n_free), leaf_max(lm) {}
@@ -106,6 +108,32 @@ struct Builder {
             nodes[me].children.push_back(c);
         }
         return me;
+    }
+
+    // Every separator is a serial hand-off between the two instruction streams in both sweeps, and bisection leaves
+    // many tiny ones near the leaves: fold a separator into its parent separator while the union still fits a tree
+    // node.  The union is eliminated after everything below either of them, so the block factorisation stays exact;
+    // the folded node's children move up.
+    void coarsen(int v) {
+        for (size_t i = 0; i < nodes[v].children.size(); ++i) coarsen(nodes[v].children[i]);
+        if (nodes[v].children.empty()) return;
+        const int cap = std::min(TS_MAX_NODE, merge_cap);
+        for (bool again = true; again;) {
+            again = false;
+            int best = -1;
+            for (int c : nodes[v].children)
+                if (!nodes[c].children.empty() && (int)(nodes[v].rows.size() + nodes[c].rows.size()) <= cap &&
+                    (best < 0 || nodes[c].rows.size() < nodes[best].rows.size())) best = c;
+            if (best < 0) break;
+            TNode &p = nodes[v], &c = nodes[best];
+            p.rows.insert(p.rows.end(), c.rows.begin(), c.rows.end());
+            p.children.erase(std::find(p.children.begin(), p.children.end(), best));
+            for (int g : c.children) { nodes[g].parent = v; p.children.push_back(g); }
+            c.rows.clear();
+            c.children.clear();
+            c.parent = -2;                                        // dead
+            again = true;
+        }
     }
 
     void postorder(int v, std::vector<int> &out) {
@@ -463,6 +491,7 @@ struct Builder {
         std::iota(all.begin(), all.end(), 0);
         const int root = bisect(all, -1);
         if (!err.empty()) return false;
+        coarsen(root);
         std::vector<int> post;
         postorder(root, post);
         int row = 0;
@@ -492,6 +521,7 @@ void build_tensor_plan(HostPlan &p, int leaf_max) {
     p.tplan = TensorPlan();
     leaf_max = std::max(8, std::min(leaf_max, TS_MAX_NODE));
     Builder b(p, leaf_max);
+    if (const char *mc = std::getenv("SDFA_TS_MERGE")) b.merge_cap = std::atoi(mc);
     if (b.run()) p.tplan.valid = true;
     else {
         std::string why = b.err;
