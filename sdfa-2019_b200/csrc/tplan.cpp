@@ -53,6 +53,7 @@ struct Builder {
     std::vector<TNode> nodes;
     int leaf_max;
     int merge_cap = TS_MAX_NODE;          // largest separator node that folding may create
+    int used_slots = 0, used_ring = 0;    // pipelining depth the tensor-memory budget allowed (emit)
     std::string err;
 
     Builder(HostPlan &hp, int lm) : p(hp), t(hp.tplan), n(hp.n_free), leaf_max(lm) {}
@@ -329,8 +330,9 @@ struct Builder {
         }
         // ---- tensor-memory maps
         const int s0 = acc_cols;
-        int n_slots = 2;
-        if (s0 + n_slots * 2 * kmax + nmax > TS_TMEM_COLS) n_slots = 1;
+        int n_slots = 3;                                    // source slots: more of them let the loads run further ahead
+        if (const char *ns = std::getenv("SDFA_TS_SLOTS")) n_slots = std::max(1, std::min(4, std::atoi(ns)));
+        while (n_slots > 1 && pad_to(s0 + n_slots * 2 * kmax, 16) + nmax > TS_TMEM_COLS) --n_slots;
         const int du = pad_to(s0 + n_slots * 2 * kmax, 16);
         t.tmem_fwd = du + nmax;
         if (t.tmem_fwd > TS_TMEM_COLS) { err = "forward sweep needs " + std::to_string(t.tmem_fwd) + " tensor-memory columns"; return false; }
@@ -338,6 +340,8 @@ struct Builder {
         const int ring = std::min(3, (TS_TMEM_COLS - dx0) / std::max(nmax, 1));
         if (ring < 1) { err = "backward sweep needs " + std::to_string(dx0 + nmax) + " tensor-memory columns"; return false; }
         t.tmem_bwd = dx0 + ring * nmax;
+        used_slots = n_slots;
+        used_ring = ring;
         auto slot_hi = [&](int k) { return s0 + k * 2 * kmax; };
         auto slot_lo = [&](int k) { return s0 + k * 2 * kmax + kmax; };
 
@@ -518,16 +522,21 @@ struct Builder {
 }  // namespace
 
 void build_tensor_plan(HostPlan &p, int leaf_max) {
-    p.tplan = TensorPlan();
     leaf_max = std::max(8, std::min(leaf_max, TS_MAX_NODE));
-    Builder b(p, leaf_max);
-    if (const char *mc = std::getenv("SDFA_TS_MERGE")) b.merge_cap = std::atoi(mc);
-    if (b.run()) p.tplan.valid = true;
-    else {
-        std::string why = b.err;
+    // Folding separators shortens the serial chain but deepens the accumulator stack; take the coarsest tree that
+    // still leaves tensor memory for two source slots and a two-deep result ring (SDFA_TS_MERGE fixes the cap).
+    std::vector<int> caps = {64, 56, 48, 40, 32, 0};
+    if (const char *mc = std::getenv("SDFA_TS_MERGE")) caps = {std::atoi(mc)};
+    std::string why;
+    for (size_t i = 0; i < caps.size(); ++i) {
         p.tplan = TensorPlan();
-        p.tplan.why_not = why;
+        Builder b(p, leaf_max);
+        b.merge_cap = caps[i];
+        if (!b.run()) { why = b.err; continue; }
+        if ((b.used_slots >= 2 && b.used_ring >= 2) || i + 1 == caps.size()) { p.tplan.valid = true; return; }
     }
+    p.tplan = TensorPlan();
+    p.tplan.why_not = why;
 }
 
 }  // namespace sdfa
