@@ -82,7 +82,11 @@ struct Builder {
         }
         const int ax = widest_axis(idx, P);
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return pos(a)[ax] < pos(b)[ax]; });
-        const int half = (int)idx.size() / 2;
+        // cut so that both sides can be tiled by the fewest leaves: k = leaves needed for this part, the low side
+        // gets floor(k/2) of them (a plain median cut turns a 130-row part into four leaves instead of three)
+        const int k_leaves = ((int)idx.size() + leaf_max - 1) / leaf_max;
+        const int half = std::getenv("SDFA_TS_MEDIAN") ? (int)idx.size() / 2
+                                                        : (int)((long long)idx.size() * (k_leaves / 2) / k_leaves);
         std::vector<int> side(n, -1);                       // -1 outside, 0 / 1 the two sides
         for (int i = 0; i < (int)idx.size(); ++i) side[idx[i]] = i < half ? 0 : 1;
         std::vector<int> bnd[2];
