@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
 // gathered with 4-byte cp.async copies two frames ahead into a double-buffered stage, corner vectors into shared
 // memory, then thread = row sums the incident corner vectors (CSR, fixed order, no atomics) into a
 // [row*3+c][33] transpose buffer; one block barrier per frame.
-constexpr int TPAD = 33;
+constexpr int ASM_GF = 16;                      // frames per CTA of the gather variant (smaller tile: more CTAs per SM)
+constexpr int ASM_GPAD = ASM_GF + 1;
 constexpr int ASM_KMAX = ASM_MAX_EQ / ASM_THREADS;
 
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
@@ -241,12 +242,12 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
     float *stage = sh;                                              // [2][3 planes][plane]: the frame's values, planar
     float *g_sh0 = sh + 6 * plane;                                  // [2][max_eq][9]: corner vectors, double buffered
     float *t_sh = g_sh0 + 2 * P.max_eq * 9;                         // [rows*3][33]
-    int *src_sh = reinterpret_cast<int *>(t_sh + P.max_rows * 3 * TPAD);   // [max_eq]
+    int *src_sh = reinterpret_cast<int *>(t_sh + P.max_rows * 3 * ASM_GPAD);   // [max_eq]
     const int4 blk = P.blocks[blockIdx.x];
     const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
     const int tile = blockIdx.y;
-    const int frame0 = tile * 32;
-    const int nvalid = min(32, P.n_frames - frame0);
+    const int frame0 = tile * ASM_GF;
+    const int nvalid = max(0, min(ASM_GF, P.n_frames - frame0));    // 0: a tile past the batch only zero-fills its lanes
     for (int e = threadIdx.x; e < n_eq; e += ASM_THREADS) src_sh[e] = P.eq_src_local[blk.x + e];
     __syncthreads();
     int src_k[ASM_KMAX];
@@ -276,7 +277,8 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    gather(0, 0);
+    if (nvalid > 0) gather(0, 0);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
     if (nvalid > 1) gather(1, 1);
     else asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");          // frame 0 has landed (this thread's part)
@@ -316,20 +318,23 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
                     const float *g = gp + 3 * (int)P.inc[q];
                     s0 += g[0]; s1 += g[1]; s2 += g[2];
                 }
-                float *t = t_sh + (3 * r) * TPAD + (f - 1);
-                t[0] = s0; t[TPAD] = s1; t[2 * TPAD] = s2;
+                float *t = t_sh + (3 * r) * ASM_GPAD + (f - 1);
+                t[0] = s0; t[ASM_GPAD] = s1; t[2 * ASM_GPAD] = s2;
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");       // frame f+1 has landed (this thread's copies; the barrier covers the rest)
         __syncthreads();
         if (f + 2 < nvalid) gather(f + 2, f & 1);                    // stage f&1 has been consumed
     }
+    // write-out: a warp stores 32 / ASM_GF lines of ASM_GF frames per instruction
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int fr = frame0 + lane;
+    constexpr int LPW = 32 / ASM_GF;
+    const int fl = lane % ASM_GF, sub = lane / ASM_GF;
+    const int fr = frame0 + fl;
     float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
-    for (int line = warp; line < n_rows * 3; line += ASM_WARPS) {
+    for (int line = warp * LPW + sub; line < n_rows * 3; line += ASM_WARPS * LPW) {
         const int r = line / 3, c = line - 3 * r;
-        dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride] = lane < nvalid ? t_sh[line * TPAD + lane] : 0.f;
+        dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride] = fl < nvalid ? t_sh[line * ASM_GPAD + fl] : 0.f;
     }
 }
 
@@ -340,13 +345,17 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
                 d.asm_max_eq, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.asm_max_walk, d.layout};
     const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
     const size_t smem = staged ? (size_t)d.asm_max_rows * 96 * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4)
-                               : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * TPAD + d.asm_max_eq) * sizeof(float);
+                               : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * ASM_GPAD + d.asm_max_eq) * sizeof(float);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)d.n_asm_blocks, (unsigned)((n_frames + 31) / 32));
     if (staged) k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
-    else k_assemble_gather<<<grid, ASM_THREADS, smem, stream>>>(P);
+    else {
+        // whole 32-frame groups are covered so that the scratch's idle lanes of a partial group hold zeros
+        grid.y = (unsigned)((n_frames + 31) / 32 * (32 / ASM_GF));
+        k_assemble_gather<<<grid, ASM_THREADS, smem, stream>>>(P);
+    }
     g_launches++;
     return cudaGetLastError();
 }
