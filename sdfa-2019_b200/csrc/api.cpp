@@ -249,7 +249,6 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
                 std::vector<int4> walk(ap.warp_sched.size(), make_int4(0, -1, 0, 0));
                 if ((r = upload_mut(h, walk, &d.asm_walk))) return r;          // filled by upload_eq_src
                 if ((r = upload(h, ap.warp_ptr, &d.asm_warp_ptr))) return r;
-                if ((r = upload(h, ap.colour_ptr, &d.asm_colour_ptr))) return r;
                 if ((r = upload(h, ap.row_ptr, &d.asm_row_ptr))) return r;
                 if ((r = upload(h, ap.inc, &d.asm_inc))) return r;
                 std::vector<int32_t> local(ap.eq_id.size(), -1);

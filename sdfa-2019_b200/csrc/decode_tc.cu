@@ -313,11 +313,9 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
     if (n_frames <= 0) return cudaSuccess;
     const int n_tiles = (n_frames + TC_BN - 1) / TC_BN;
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    {
         cudaError_t e = cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const long long stride = d.compact_stride;
     for (int g = 0; g < 2; ++g) {

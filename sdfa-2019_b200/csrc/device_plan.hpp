@@ -30,7 +30,6 @@ struct DevicePlan {
                                             //  its slot group in the compact dgrad, -}
     const int32_t  *asm_warp_ptr = nullptr; // [blocks * 8 + 1]
     int asm_max_walk = 0;
-    const int32_t  *asm_colour_ptr = nullptr;   // [blocks][ASM_MAX_COLOURS + 1]
     int32_t        *asm_eq_src_local = nullptr; // source triangle per block-local equation
     const int32_t  *asm_row_ptr = nullptr;      // CSR incidence of the block rows (gather variant)
     const uint16_t *asm_inc = nullptr;

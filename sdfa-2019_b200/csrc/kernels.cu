@@ -717,12 +717,8 @@ cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frame
     OutParams P{scratch, d.out_line_of, d.out_cval, d.out_line_ptr, d.out_line_off, d.out_line_hi, d.out_line_lo,
                 out, n_frames, d.n_verts, FR, FC, d.layout.tile_stride};
     const size_t smem = (size_t)std::max(d.out_max_lines, 1) * (FC + 1) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_output, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = cudaFuncSetAttribute(k_output, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));
     k_output<<<grid, OUT_THREADS, smem, stream>>>(P);
     g_launches++;
