@@ -113,8 +113,8 @@ int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const fl
                           int n_frames, float *dgrad_dev, void *stream);
 
 /* decode only, into the internal frame-tiled compact layout the assembly kernel consumes (what
- * sdfa_decode_reconstruct_* produces with the tcgen05 kernel): [ceil(n_frames/32), slots, 32] float32
- * (tile of 32 frames, slot, frame inside the tile).
+ * sdfa_decode_reconstruct_* produces with the tcgen05 kernel): [ceil(n_frames/64), slots, 64] float32
+ * (tile of 64 frames, slot, frame inside the tile).
  * sdfa_compact_layout returns `slots` and copies the map slot -> source_triangle*9 + component
  * (-1 = nothing decoded there); map may be NULL. */
 int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,

@@ -574,7 +574,7 @@ static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, co
                                    int n_frames, float *out_dev, cudaStream_t s) {
     int rc;
     const long long stride = h->dev.compact_stride;
-    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, ((size_t)n_frames + 31) / 32 * 32 * stride))) return rc;
+    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, ((size_t)n_frames + COMPACT_TILE - 1) / COMPACT_TILE * COMPACT_TILE * stride))) return rc;
     if ((rc = time_mark(h, 0, s))) return rc;
     if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
     if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
@@ -732,6 +732,7 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
     if (w == "asm_eq_rows") return give(p.asmplan.eq_rows, dst, cap);
     if (w == "asm_colour_ptr") return give(p.asmplan.colour_ptr, dst, cap);
     if (w == "scratch_row") return give(p.scratch_row, dst, cap);
+    if (w == "compact_tile") { std::vector<int32_t> v = {COMPACT_TILE}; return give(v, dst, cap); }
     if (w == "ts_mma") return give(p.tplan.mma, dst, cap);
     if (w == "ts_epi") return give(p.tplan.epi, dst, cap);
     if (w == "ts_matrix") return give(p.tplan.matrix, dst, cap);

@@ -120,7 +120,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
 struct GemmParams {
     const float *w_img[2];   // [m_tiles][kb][hi,lo][256x32 swizzled]
     const float *x_img[2];   // [n_tiles][kb][hi,lo][128x32 swizzled]
-    float *out;              // [tiles of 32 frames][out_stride][32]
+    float *out;              // [tiles of COMPACT_TILE frames][out_stride][COMPACT_TILE]
     long long out_stride;    // slots per frame (scale part + rotation part)
     int part_off[2];         // first slot of the part: GEMM row r is slot part_off + r (the bias rides in the GEMM)
     int m_tiles[2], kb[2];
@@ -234,9 +234,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
             const TileInfo ti = tile_info(P, tile);
             const int m = ti.m, n = ti.n;
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-            const int tile32 = n * (TC_BN / 32) + lane_grp;
-            const bool live = tile32 * 32 < P.n_frames;             // 32-frame tiles past the batch are not stored
-            float *out_tile = P.out + ((size_t)tile32 * P.out_stride + P.part_off[ti.part] + (size_t)m * TC_BM + col_half * (TC_BM / 2)) * 32 + lane;
+            // this warp's 32 frames inside the compact dgrad's tiles of COMPACT_TILE frames
+            const int frame0 = n * TC_BN + lane_grp * 32;
+            const bool live = frame0 < P.n_frames;                  // 32-frame groups past the batch are not stored
+            float *out_tile = P.out + ((size_t)(frame0 / COMPACT_TILE) * P.out_stride + P.part_off[ti.part] + (size_t)m * TC_BM +
+                                       col_half * (TC_BM / 2)) * COMPACT_TILE + frame0 % COMPACT_TILE + lane;
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * TC_BM + col_half * (TC_BM / 2);
@@ -246,9 +248,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                 tmem_ld32(taddr + chunk * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (live) {
-                    float *dst = out_tile + chunk * 32 * 32;      // 32 slots further, each a line of 32 frames
+                    float *dst = out_tile + chunk * 32 * COMPACT_TILE;      // 32 slots further
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) __stcs(dst + c * 32, __uint_as_float(v[c]));
+                    for (int c = 0; c < 32; ++c) __stcs(dst + c * COMPACT_TILE, __uint_as_float(v[c]));
                 }
             }
             tc_fence_before();

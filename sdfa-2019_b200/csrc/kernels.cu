@@ -172,40 +172,134 @@ __device__ __forceinline__ void eq_apply(float *acc, int lane, int mode, int src
 constexpr int ASM_WARPS = ASM_WARPS_PER_BLOCK;
 constexpr int ASM_THREADS = 32 * ASM_WARPS;
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 of sm_100): a lane carries two frames
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// corner_vec for two frames at once; nd6..nd8 = -d6..-d8
+__device__ __forceinline__ void corner_vec2(const float2 *d, float2 nd6, float2 nd7, float2 nd8, float2 a, float2 b, const float *u, float2 *g) {
+    const float2 u0 = f2(u[0]), u1 = f2(u[1]), u2 = f2(u[2]);
+    const float2 t0 = fma2(d[2], u2, fma2(d[1], u1, mul2(d[0], u0)));
+    const float2 t1 = fma2(d[4], u2, fma2(d[3], u1, mul2(d[1], u0)));
+    const float2 t2 = fma2(d[5], u2, fma2(d[4], u1, mul2(d[2], u0)));
+    const float2 s0 = add2(u0, t0), s1 = add2(u1, t1), s2 = add2(u2, t2);
+    const float2 p0 = fma2(d[7], s2, mul2(d[6], s1));
+    const float2 p1 = fma2(d[8], s2, mul2(nd6, s0));
+    const float2 p2 = fma2(nd8, s1, mul2(nd7, s0));
+    const float2 q0 = fma2(d[7], p2, mul2(d[6], p1));
+    const float2 q1 = fma2(d[8], p2, mul2(nd6, p0));
+    const float2 q2 = fma2(nd8, p1, mul2(nd7, p0));
+    g[0] = fma2(b, q0, fma2(a, p0, t0));
+    g[1] = fma2(b, q1, fma2(a, p1, t1));
+    g[2] = fma2(b, q2, fma2(a, p2, t2));
+}
+
+// a = sin(th)/th, b = (1 - cos th)/th^2 for one frame (th2 = th^2); see eq_vectors
+__device__ __forceinline__ void rot_coeffs(float th2, float &a, float &b) {
+    a = b = 0.f;
+    if (th2 < 1e-12f) return;           // angle < 1e-6 => R = I (utils_rotation.cpp:46-47)
+    const float th = sqrtf(th2), sh2 = sinf(0.5f * th);
+    a = sinf(th) / th;
+    b = 2.f * sh2 * sh2 / th2;
+}
+
+// One equation for the two frames of this lane (k_assemble): corner vectors added to the accumulator rows of its corners;
+// the same arithmetic as eq_apply, packed.
+__device__ __forceinline__ void eq_apply2(float *acc, int lane, int mode, int src, const float2 (&d)[9], float4 m0, float4 m1) {
+    if (src == -1) return;                                       // identity block (impl.hpp:264-268): T - I = 0
+    const float u0[3] = {m0.x, m0.y, m0.z}, u1[3] = {m0.w, m1.x, m1.y};
+    const uint32_t r01 = __float_as_uint(m1.z), r23 = __float_as_uint(m1.w);
+    const int rx = (short)(r01 & 0xFFFFu), ry = (short)(r01 >> 16), rz = (short)(r23 & 0xFFFFu);
+    float2 g2[3], g3[3];
+    if (src >= 0) {
+        if (mode == ASM_DGRAD) {
+            const float2 th2 = fma2(d[8], d[8], fma2(d[7], d[7], mul2(d[6], d[6])));
+            // Taylor series in th^2 (remainder < 3e-8 for th <= 1): no sqrt, sin or division
+            const float2 one = f2(1.f);
+            float2 a = fma2(mul2(th2, f2(-1.f / 72.f)), one, one);
+            a = fma2(mul2(th2, f2(-1.f / 42.f)), a, one);
+            a = fma2(mul2(th2, f2(-1.f / 20.f)), a, one);
+            a = fma2(mul2(th2, f2(-1.f / 6.f)), a, one);
+            float2 b = fma2(mul2(th2, f2(-1.f / 90.f)), one, one);
+            b = fma2(mul2(th2, f2(-1.f / 56.f)), b, one);
+            b = fma2(mul2(th2, f2(-1.f / 30.f)), b, one);
+            b = fma2(mul2(th2, f2(-1.f / 24.f)), b, f2(0.5f));
+            // out of the series' range (angle < 1e-6 => R = I, or th > 1): per frame, rarely
+            if (th2.x < 1e-12f || th2.x > 1.f) rot_coeffs(th2.x, a.x, b.x);
+            if (th2.y < 1e-12f || th2.y > 1.f) rot_coeffs(th2.y, a.y, b.y);
+            const float2 nd6 = neg2(d[6]), nd7 = neg2(d[7]), nd8 = neg2(d[8]);
+            corner_vec2(d, nd6, nd7, nd8, a, b, u0, g2);
+            corner_vec2(d, nd6, nd7, nd8, a, b, u1, g3);
+        } else {                        // raw row-major T (impl.hpp:391-397): E = T - I
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float2 e0 = add2(d[3 * c], f2(c == 0 ? -1.f : 0.f)), e1 = add2(d[3 * c + 1], f2(c == 1 ? -1.f : 0.f)),
+                             e2 = add2(d[3 * c + 2], f2(c == 2 ? -1.f : 0.f));
+                g2[c] = fma2(e2, f2(u0[2]), fma2(e1, f2(u0[1]), mul2(e0, f2(u0[0]))));
+                g3[c] = fma2(e2, f2(u1[2]), fma2(e1, f2(u1[1]), mul2(e0, f2(u1[0]))));
+            }
+        }
+    } else {                            // block left at zero by setZero (impl.hpp:224): T = 0, E = -I
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { g2[c] = f2(-u0[c]); g3[c] = f2(-u1[c]); }
+    }
+    // corner 0 (v1) gets -(g2+g3), corner 1 (v2) g2, corner 2 (v3) g3
+    if (rx >= 0) {
+        float2 *t = reinterpret_cast<float2 *>(acc + rx * 3 * COMPACT_TILE) + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c * (COMPACT_TILE / 2)] = add2(t[c * (COMPACT_TILE / 2)], neg2(add2(g2[c], g3[c])));
+    }
+    if (ry >= 0) {
+        float2 *t = reinterpret_cast<float2 *>(acc + ry * 3 * COMPACT_TILE) + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c * (COMPACT_TILE / 2)] = add2(t[c * (COMPACT_TILE / 2)], g2[c]);
+    }
+    if (rz >= 0) {
+        float2 *t = reinterpret_cast<float2 *>(acc + rz * 3 * COMPACT_TILE) + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c * (COMPACT_TILE / 2)] = add2(t[c * (COMPACT_TILE / 2)], g3[c]);
+    }
+}
+
+static_assert(COMPACT_TILE == 64, "k_assemble carries two frames per lane");
+
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
-    extern __shared__ __align__(16) float acc[];                     // [row][3][32]
+    extern __shared__ __align__(16) float acc[];                     // [row][3][64]
+    constexpr int CT = COMPACT_TILE;
     const int4 blk = P.blocks[blockIdx.x];
     const int n_rows = blk.w - blk.z;
     const int tile = blockIdx.y;
-    const int frame0 = tile * 32;
-    const int nvalid = min(32, P.n_frames - frame0);
+    const int frame0 = tile * CT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < n_rows * 96; i += ASM_THREADS) acc[i] = 0.f;
-    // this tile's lines: six scale lines and three rotation lines per equation
-    const float *in = P.dgrad + (long long)tile * P.frame_stride * 32 + lane;
+    for (int i = threadIdx.x; i < n_rows * 3 * CT; i += ASM_THREADS) acc[i] = 0.f;
+    // this tile's lines (six scale lines and three rotation lines per equation); the lane's two frames are adjacent
+    const float2 *in = reinterpret_cast<const float2 *>(P.dgrad + (long long)tile * P.frame_stride * CT) + lane;
     // the block's eight walks go to shared memory first, so that an entry costs a shared-memory read and the only
     // long-latency loads are an equation's values and its record -- both issued one equation ahead
-    int4 *walk_sh = reinterpret_cast<int4 *>(acc + P.max_rows * 96);
+    int4 *walk_sh = reinterpret_cast<int4 *>(acc + P.max_rows * 3 * CT);
     {
         const int w0 = P.warp_ptr[blockIdx.x * ASM_WARPS], w1 = P.warp_ptr[blockIdx.x * ASM_WARPS + ASM_WARPS];
         for (int i = threadIdx.x; i < w1 - w0; i += ASM_THREADS) walk_sh[i] = P.walk[w0 + i];
     }
     const int4 *walk = walk_sh + (P.warp_ptr[blockIdx.x * ASM_WARPS + warp] - P.warp_ptr[blockIdx.x * ASM_WARPS]);
-    struct Eq { int e, src; float4 m0, m1; float d[9]; };
+    struct Eq { int e, src; float4 m0, m1; float2 d[9]; };
     auto fetch = [&](int4 ent, Eq &q) {
         q.e = ent.x; q.src = ent.y;
         if (ent.x < 0) return;
         q.m0 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2);
         q.m1 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2 + 1);
         // slots of identity / zero blocks hold zeros: always readable
-        const float *qs = in + (size_t)ent.z * 6 * 32, *qr = in + ((size_t)P.s_rows + (size_t)ent.z * 3) * 32;
+        const float2 *qs = in + (size_t)ent.z * 6 * (CT / 2), *qr = in + ((size_t)P.s_rows + (size_t)ent.z * 3) * (CT / 2);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) q.d[j] = __ldcs(qs + j * 32);
+        for (int j = 0; j < 6; ++j) q.d[j] = __ldcs(qs + j * (CT / 2));
 #pragma unroll
-        for (int j = 0; j < 3; ++j) q.d[6 + j] = __ldcs(qr + j * 32);
+        for (int j = 0; j < 3; ++j) q.d[6 + j] = __ldcs(qr + j * (CT / 2));
     };
-    // the equation's corner vectors for this lane's frame, added to the block rows of its three corners
-    auto apply = [&](const Eq &q) { eq_apply(acc, lane, P.mode, q.src, q.d, q.m0, q.m1); };
+    // the equation's corner vectors for this lane's two frames, added to the block rows of its three corners
+    auto apply = [&](const Eq &q) { eq_apply2(acc, lane, P.mode, q.src, q.d, q.m0, q.m1); };
     // software pipeline over the warp's walk: the next equation's values are in flight while this one is applied
     // (also across the colour barriers)
     Eq qa, qb;
@@ -218,11 +312,16 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
         fetch(*walk++, qa);
         if (qb.e == ASM_SCHED_BARRIER) __syncthreads(); else apply(qb);
     }
-    const int fr = frame0 + lane;
+    // write-out: the lane's two frames are adjacent in a scratch line as well (frames per line is even)
+    const int fr = frame0 + 2 * lane;
     float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
+    const float2 *acc2 = reinterpret_cast<const float2 *>(acc) + lane;
     for (int line = warp; line < n_rows * 3; line += ASM_WARPS) {
         const int r = line / 3, c = line - 3 * r;
-        dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride] = lane < nvalid ? acc[line * 32 + lane] : 0.f;
+        float2 v = acc2[line * (CT / 2)];
+        if (fr >= P.n_frames) v.x = 0.f;
+        if (fr + 1 >= P.n_frames) v.y = 0.f;
+        *reinterpret_cast<float2 *>(dst_tile + (long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride) = v;
     }
 }
 
@@ -344,12 +443,12 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
     AsmParams P{d.asm_blocks, d.asm_walk, d.asm_warp_ptr, d.asm_eq_meta, d.asm_row_perm, d.asm_eq_src_local, d.asm_row_ptr, d.asm_inc,
                 d.asm_max_eq, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.asm_max_walk, d.layout};
     const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
-    const size_t smem = staged ? (size_t)d.asm_max_rows * 96 * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4)
+    const size_t smem = staged ? (size_t)d.asm_max_rows * 3 * COMPACT_TILE * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4)
                                : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * ASM_GPAD + d.asm_max_eq) * sizeof(float);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)d.n_asm_blocks, (unsigned)((n_frames + 31) / 32));
+    dim3 grid((unsigned)d.n_asm_blocks, (unsigned)((n_frames + COMPACT_TILE - 1) / COMPACT_TILE));
     if (staged) k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
     else {
         // whole 32-frame groups are covered so that the scratch's idle lanes of a partial group hold zeros
@@ -613,9 +712,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveParams P) {
 }
 
 size_t scratch_floats(const DevicePlan &d, int n_frames) {
-    // K2 writes whole 32-frame tiles
-    const size_t n32 = ((size_t)n_frames + 31) / 32 * 32;
-    return (n32 + d.layout.FL - 1) / d.layout.FL * (size_t)d.layout.tile_stride;
+    // K2 writes whole tiles of COMPACT_TILE frames
+    const size_t nt = ((size_t)n_frames + COMPACT_TILE - 1) / COMPACT_TILE * COMPACT_TILE;
+    return (nt + d.layout.FL - 1) / d.layout.FL * (size_t)d.layout.tile_stride;
 }
 
 size_t solve_smem_bytes(int n_slots, int frames_per_tile) {

@@ -85,6 +85,7 @@ struct SolveProgram {
 // to the block's row accumulators in shared memory.  The block's equations are coloured so that one colour never
 // touches a row twice, and the colours are processed in order with a barrier in between: no atomics, a fixed
 // summation order.
+constexpr int COMPACT_TILE = 64;                 // frames per tile of the compact dgrad: K2 handles two frames per lane (packed fp32x2)
 constexpr int ASM_MAX_COLOURS = 32;
 constexpr int ASM_WARPS_PER_BLOCK = 8;
 constexpr int16_t ASM_SCHED_BARRIER = -1, ASM_SCHED_END = -2;
@@ -108,7 +109,7 @@ struct AssemblyPlan {
     std::vector<int32_t> warp_ptr;      // [blocks * ASM_WARPS_PER_BLOCK + 1] start of each walk in warp_sched
     int max_eq_per_block = 0, max_rows_per_block = 0;
     // Frame-tiled compact dgrad (what the decode kernel writes and the staged assembly reads):
-    // [tile of 32 frames][slot][32 frames]; active equation u (index into HostPlan::active_eq) owns the scale slots
+    // [tile of COMPACT_TILE frames][slot][COMPACT_TILE frames]; active equation u (index into HostPlan::active_eq) owns the scale slots
     // 6 u .. 6 u + 5 (s00,s01,s02,s11,s12,s22) and the rotation slots compact_s_rows + 3 u .. + 2 (r01,r02,r12);
     // both parts are padded to whole GEMM row tiles, so a decode GEMM row is simply its slot.
     std::vector<int32_t> eq_slot;       // per block-local equation: its u

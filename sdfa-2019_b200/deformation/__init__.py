@@ -249,13 +249,15 @@ class Reconstructor:
 
     def decode_compact(self, coeff_scale, coeff_rotat, stream=None):
         """Coefficients -> compact dgrad (torch.cuda; tcgen05 kernel).  The kernel writes the frame-tiled layout
-        [ceil(N/32), slots, 32] the assembly kernel reads; returned here as [N, slots] (slots as in compact_layout())."""
+        [ceil(N/T), slots, T] the assembly kernel reads (T = 64 frames per tile); returned here as [N, slots]
+        (slots as in compact_layout())."""
         import torch
         a = coeff_scale.contiguous().reshape(-1, self.k_scale)
         b = coeff_rotat.contiguous().reshape(-1, self.k_rotat)
         slots = lib.sdfa_compact_layout(self._h, None, 0)
         n = a.shape[0]
-        out = torch.zeros(((n + 31) // 32, slots, 32), dtype=torch.float32, device=a.device)
+        T = int(self.debug("compact_tile")[0])
+        out = torch.zeros(((n + T - 1) // T, slots, T), dtype=torch.float32, device=a.device)
         s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
         check(lib.sdfa_decode_compact_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), n, ptr(out.data_ptr()), ptr(s)))
         return out.permute(0, 2, 1).reshape(-1, slots)[:n]
