@@ -115,8 +115,8 @@ static int upload_eq_src(sdfa_handle *h) {
 static std::vector<int32_t> compact_map(const sdfa_handle *h) {
     const AssemblyPlan &ap = h->host.asmplan;
     std::vector<int32_t> map((size_t)ap.compact_stride, -1);
-    for (size_t g = 0; g < h->host.active_eq.size(); ++g) {
-        const int src = h->eq_src_host[h->host.active_eq[g]];
+    for (size_t g = 0; g < ap.slot_eq.size(); ++g) {
+        const int src = h->eq_src_host[ap.slot_eq[g]];
         if (src < 0) continue;
         for (int j = 0; j < 6; ++j) map[g * 6 + j] = src * 9 + j;
         for (int j = 0; j < 3; ++j) map[(size_t)ap.compact_s_rows + g * 3 + j] = src * 9 + 6 + j;
@@ -549,8 +549,8 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     {
         const AssemblyPlan &ap = h->host.asmplan;
         std::vector<int32_t> src_s, src_r;
-        for (size_t g = 0; g < h->host.active_eq.size(); ++g) {
-            const int src = h->eq_src_host[h->host.active_eq[g]];
+        for (size_t g = 0; g < ap.slot_eq.size(); ++g) {
+            const int src = h->eq_src_host[ap.slot_eq[g]];
             if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
             for (int j = 0; j < 6; ++j) src_s.push_back(src < 0 ? -1 : src * 6 + j);
             for (int j = 0; j < 3; ++j) src_r.push_back(src < 0 ? -1 : src * 3 + j);

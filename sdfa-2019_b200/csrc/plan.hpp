@@ -109,10 +109,11 @@ struct AssemblyPlan {
     std::vector<int32_t> warp_ptr;      // [blocks * ASM_WARPS_PER_BLOCK + 1] start of each walk in warp_sched
     int max_eq_per_block = 0, max_rows_per_block = 0;
     // Frame-tiled compact dgrad (what the decode kernel writes and the staged assembly reads):
-    // [tile of COMPACT_TILE frames][slot][COMPACT_TILE frames]; active equation u (index into HostPlan::active_eq) owns the scale slots
+    // [tile of COMPACT_TILE frames][slot][COMPACT_TILE frames]; active equation u (slot_eq[u]) owns the scale slots
     // 6 u .. 6 u + 5 (s00,s01,s02,s11,s12,s22) and the rotation slots compact_s_rows + 3 u .. + 2 (r01,r02,r12);
     // both parts are padded to whole GEMM row tiles, so a decode GEMM row is simply its slot.
     std::vector<int32_t> eq_slot;       // per block-local equation: its u
+    std::vector<int32_t> slot_eq;       // u -> equation block (the active equations in block-walk order)
     int compact_s_rows = 0;
     int compact_stride = 0;             // slots = floats per frame
 };

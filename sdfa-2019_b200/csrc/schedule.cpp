@@ -718,10 +718,14 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
     // frame-tiled compact dgrad: a scale part (6 slots per active equation) and a rotation part (3), each padded
     // to whole 256-row GEMM tiles of the decode kernel; an equation shared by two row blocks is decoded once
     {
+        // slots in the order the row blocks walk their equations, so that a block reads (mostly) one contiguous run
         std::vector<int> slot_of_eq(p.n_eq, -1);
-        for (size_t u = 0; u < p.active_eq.size(); ++u) slot_of_eq[p.active_eq[u]] = (int)u;
         ap.eq_slot.clear();
-        for (int k : ap.eq_id) ap.eq_slot.push_back(slot_of_eq[k]);
+        ap.slot_eq.clear();
+        for (int k : ap.eq_id) {
+            if (slot_of_eq[k] < 0) { slot_of_eq[k] = (int)ap.slot_eq.size(); ap.slot_eq.push_back(k); }
+            ap.eq_slot.push_back(slot_of_eq[k]);
+        }
         const int E = (int)p.active_eq.size();
         ap.compact_s_rows = (6 * E + 255) / 256 * 256;
         ap.compact_stride = ap.compact_s_rows + (3 * E + 255) / 256 * 256;
