@@ -32,6 +32,8 @@ constexpr int TC_BM = 256;          // basis rows per tile (UMMA N): 256 halves 
 constexpr int TC_BN = 128;          // frames per tile (UMMA M = TMEM lanes)
 constexpr int TC_BK = 32;           // floats per K-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 2;
+constexpr int TC_CLUSTER = 2;       // CTAs per cluster: they decode TC_CLUSTER neighbouring frame tiles against the same basis
+                                    // tile, each fetching 1 / TC_CLUSTER of it and multicasting it to all (L2 reads it once)
 constexpr int TC_W_BYTES = TC_BM * TC_BK * 4;                    // 32 KB: one half (hi or lo) of the basis tile
 constexpr int TC_X_BYTES = TC_BN * TC_BK * 4;                    // 16 KB: one half of the frames tile
 constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;  // W_hi, W_lo, X_hi, X_lo = 96 KB
@@ -124,11 +126,11 @@ struct GemmParams {
     long long out_stride;    // slots per frame (scale part + rotation part)
     int part_off[2];         // first slot of the part: GEMM row r is slot part_off + r (the bias rides in the GEMM)
     int m_tiles[2], kb[2];
-    int n_frames, n_tiles;
+    int n_frames, n_tiles;   // n_tiles = frame tiles, a multiple of TC_CLUSTER (the images are padded)
 };
 
 struct TileInfo { int part, m, n; };
-// tile t of the launch: frame tile n = t / (m_tiles[0] + m_tiles[1]); inside it scale, scale, rotation, ... while both last
+// unit t of a cluster: frame-tile group n = t / (m_tiles[0] + m_tiles[1]); inside it scale, scale, rotation, ... while both last
 __device__ __forceinline__ TileInfo tile_info(const GemmParams &P, int t) {
     const int per_n = P.m_tiles[0] + P.m_tiles[1];
     TileInfo ti;
@@ -150,8 +152,22 @@ __device__ __forceinline__ TileInfo tile_info(const GemmParams &P, int t) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 256 rows, M = 128 frames
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(TC_BN >> 4) << 24);
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
+    const uint32_t crank = blockIdx.x % TC_CLUSTER, cid = blockIdx.x / TC_CLUSTER, n_clusters = gridDim.x / TC_CLUSTER;
+    constexpr uint16_t CMASK = (uint16_t)((1u << TC_CLUSTER) - 1u);
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *stages = smem;
@@ -162,7 +178,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        // a stage is free once the MMAs of every CTA of the cluster have read it: the peers multicast into it
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_CLUSTER); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -174,24 +191,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    cluster_sync();                                // every CTA's barriers exist before a peer signals them
     const uint32_t tmem_base = *tmem_slot;
-    const int n_tiles_total = (P.m_tiles[0] + P.m_tiles[1]) * P.n_tiles;
+    const int n_tiles_total = (P.m_tiles[0] + P.m_tiles[1]) * (P.n_tiles / TC_CLUSTER);     // units per cluster walk
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+            constexpr uint32_t W_SLICE = 2 * TC_W_BYTES / TC_CLUSTER;     // this CTA's share of the basis tile (hi | lo images)
+            for (int tile = cid; tile < n_tiles_total; tile += n_clusters) {
                 const TileInfo ti = tile_info(P, tile);
                 const int kbs = P.kb[ti.part];
                 const float *w = P.w_img[ti.part] + (size_t)ti.m * kbs * (2 * TC_BM * TC_BK);
-                const float *x = P.x_img[ti.part] + (size_t)ti.n * kbs * (2 * TC_BN * TC_BK);
+                const float *x = P.x_img[ti.part] + (size_t)(ti.n * TC_CLUSTER + crank) * kbs * (2 * TC_BN * TC_BK);
                 for (int kb = 0; kb < kbs; ++kb, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);            // all CTAs of the cluster are done with stage s
                     mbar_arrive_expect_tx(bar_full + 8 * s, TC_STAGE_BYTES);
                     const uint32_t dst = smem_u32(stages + s * TC_STAGE_BYTES);
-                    tma_bulk_g2s(dst, w + (size_t)kb * (2 * TC_BM * TC_BK), 2 * TC_W_BYTES, bar_full + 8 * s);
+                    tma_bulk_g2s_multicast(dst + crank * W_SLICE, reinterpret_cast<const uint8_t *>(w + (size_t)kb * (2 * TC_BM * TC_BK)) + crank * W_SLICE,
+                                           W_SLICE, bar_full + 8 * s, CMASK);
                     tma_bulk_g2s(dst + 2 * TC_W_BYTES, x + (size_t)kb * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES, bar_full + 8 * s);
                 }
             }
@@ -200,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+            for (int tile = cid; tile < n_tiles_total; tile += n_clusters, ++tc) {
                 const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);         // epilogue has drained this accumulator
                 tc_fence_after();
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
                         umma_tf32(d_tmem, x_lo, w_hi, TC_IDESC, 1u);
                         umma_tf32(d_tmem, x_hi, w_lo, TC_IDESC, 1u);
                     }
-                    tc_commit(bar_empty + 8 * s);                  // stage reusable once these MMAs have read it
+                    tc_commit_multicast(bar_empty + 8 * s, CMASK);   // tell every CTA of the cluster: this one has read stage s
                 }
                 tc_commit(bar_tfull + 8 * acc);                    // accumulator complete
             }
@@ -230,9 +250,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
         const int lane_grp = warp & 3;                              // TMEM lanes = frames 32*lane_grp .. +31 of the 128-frame tile
         const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (basis rows) it drains
         uint32_t tc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+        for (int tile = cid; tile < n_tiles_total; tile += n_clusters, ++tc) {
             const TileInfo ti = tile_info(P, tile);
-            const int m = ti.m, n = ti.n;
+            const int m = ti.m, n = ti.n * TC_CLUSTER + (int)crank;
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
             // this warp's 32 frames inside the compact dgrad's tiles of COMPACT_TILE frames
             const int frame0 = n * TC_BN + lane_grp * 32;
@@ -260,6 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                                // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -287,8 +308,9 @@ __global__ void k_split_coeffs(const float *__restrict__ x, int K, int n_frames,
 }  // namespace
 
 int tc_kblocks(int K) { return (K + 1 + TC_BK - 1) / TC_BK; }   // + the bias column
+static int tc_frame_tiles(int n_frames) { return ((n_frames + TC_BN - 1) / TC_BN + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER; }
 size_t tc_ximg_floats(int n_frames, int K) {
-    return (size_t)((n_frames + TC_BN - 1) / TC_BN) * tc_kblocks(K) * 2 * TC_BN * TC_BK;
+    return (size_t)tc_frame_tiles(n_frames) * tc_kblocks(K) * 2 * TC_BN * TC_BK;
 }
 
 // Host: pre-split, pre-tiled basis images; GEMM row r = compact slot r of the basis' part, rows_src[r] = row of the
@@ -313,7 +335,7 @@ int tc_rows_per_tile() { return TC_BM; }
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    const int n_tiles = (n_frames + TC_BN - 1) / TC_BN;
+    const int n_tiles = tc_frame_tiles(n_frames);                  // padded to whole clusters
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 1024;
     {
         cudaError_t e = cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -332,6 +354,7 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
                  {d.tc_mt_scale, d.tc_mt_rotat}, {tc_kblocks(d.k_scale), tc_kblocks(d.k_rotat)}, n_frames, n_tiles};
     int grid = (P.m_tiles[0] + P.m_tiles[1]) * n_tiles;
     if (grid > d.sm_count) grid = d.sm_count;
+    grid = grid / TC_CLUSTER * TC_CLUSTER;
     k_decode_tc<<<grid, TC_THREADS, smem, stream>>>(P);
     count_launch();
     cudaError_t e = cudaGetLastError();
