@@ -135,6 +135,17 @@ int sdfa_get_deform_grad_host(const float *verts_a, const float *verts_b, int n_
 int sdfa_deform_grad_batch_dev(const float *verts_a_dev, const float *verts_b_dev, int n_verts, const uint32_t *tris_dev,
                                int n_tris, int n_frames, double eps, int as_matrix, float *out_dev, void *stream);
 
+/* ---- the step before the path: time interpolation of a sequence (saber.stream.seek) ------- */
+
+/* Batched saber.stream.seek (saber/data/stream/stream.py:20-46): for every query time the two bracketing rows of
+ * seq_dev [n_src, width] float32 are blended, out = a*seq[m] + (1-a)*seq[m+1] with a = (t[m+1]-ts)/(t[m+1]-t[m])
+ * evaluated in float64 like the reference and rounded to float32; a query outside [t[0], t[-1]] copies the row the
+ * reference's binary search stops at.  timestamps_host [n_src] (ascending) and query_host [n_query] are host
+ * float64; out_dev [n_query, width].  The decode is affine, so seeking PCA coefficients and decoding equals
+ * decoding and seeking the dgrad (model.py:201-212 does the latter on the host, one frame at a time). */
+int sdfa_seek_dev(const float *seq_dev, int n_src, long long width, const double *timestamps_host,
+                  const double *query_host, int n_query, float *out_dev, void *stream);
+
 /* ---- measurement / introspection -------------------------------------------------------- */
 
 /* Kernel launches issued by this library since process start (for bench.py's gpu_launches). */

@@ -684,6 +684,46 @@ int sdfa_deform_grad_batch_dev(const float *verts_a_dev, const float *verts_b_de
     return SDFA_OK;
 }
 
+int sdfa_seek_dev(const float *seq_dev, int n_src, long long width, const double *timestamps_host,
+                  const double *query_host, int n_query, float *out_dev, void *stream) {
+    if (!seq_dev || !timestamps_host || n_src <= 0 || width <= 0 || n_query < 0 || (n_query > 0 && (!query_host || !out_dev)))
+        return fail(SDFA_ERR_ARG, "sdfa_seek_dev: bad arguments");
+    if (n_query == 0) return SDFA_OK;
+    // saber.stream.seek's search and its two special cases (stream.py:23-46), per query
+    std::vector<int2> pairs(n_query);
+    std::vector<double> w(n_query, 1.0);
+    const double *t = timestamps_host;
+    for (int q = 0; q < n_query; ++q) {
+        const double ts = query_host[q];
+        int left = 0, right = n_src, m = (left + right) / 2;
+        while (left < right) {
+            m = (left + right) / 2;
+            const double tm = t[m], tn = m + 1 < n_src ? t[m + 1] : ts + 1;
+            if (tm <= ts && ts < tn) break;
+            else if (tm > ts) right = m;
+            else left = m + 1;
+        }
+        if (m >= n_src) m = n_src - 1;
+        if (ts < t[m] || ts > t[n_src - 1] || m + 1 >= n_src) pairs[q] = make_int2(m, m);
+        else {
+            pairs[q] = make_int2(m, m + 1);
+            w[q] = (t[m + 1] - ts) / (t[m + 1] - t[m]);
+        }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int2 *dp = nullptr;
+    double *dw = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&dp, sizeof(int2) * n_query, s));
+    CUDA_TRY(cudaMallocAsync((void **)&dw, sizeof(double) * n_query, s));
+    CUDA_TRY(cudaMemcpyAsync(dp, pairs.data(), sizeof(int2) * n_query, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dw, w.data(), sizeof(double) * n_query, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));                   // the pageable host tables above must outlive the copies
+    CUDA_TRY(launch_seek(seq_dev, width, dp, dw, n_query, out_dev, s));
+    CUDA_TRY(cudaFreeAsync(dp, s));
+    CUDA_TRY(cudaFreeAsync(dw, s));
+    return SDFA_OK;
+}
+
 long long sdfa_launch_count(void) { return launch_counter(); }
 
 int sdfa_set_timing(sdfa_handle *h, int enable) {

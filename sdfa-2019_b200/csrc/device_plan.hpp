@@ -83,6 +83,9 @@ cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, co
 cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, long long vb_stride, const uint32_t *tris,
                                int n_tris, int n_frames, double eps, int as_matrix, void *out, bool out_f64,
                                cudaStream_t stream);
+// inverse.cu: out[q] = (float)(a[q] * seq[lo[q]] + (1 - a[q]) * seq[hi[q]]) in float64, rows of `width` floats
+cudaError_t launch_seek(const float *seq, long long width, const int2 *pairs, const double *weights, int n_query, float *out,
+                        cudaStream_t stream);
 // decode_tc.cu
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);

@@ -11,6 +11,8 @@
 //     R     = T V diag(1/s1, 1/s2, d/s3) V^T    (= U Temp V^T,   impl.hpp:456)
 #include "device_plan.hpp"
 
+#include <algorithm>
+
 namespace sdfa {
 
 namespace {
@@ -220,6 +222,30 @@ cudaError_t launch_deform_grad(const float *verts_a, const float *verts_b, long 
         k_deform_grad<double><<<grid, 128, 0, stream>>>(verts_a, verts_b, vb_stride, tris, n_tris, n_frames, eps, as_matrix, (double *)out);
     else
         k_deform_grad<float><<<grid, 128, 0, stream>>>(verts_a, verts_b, vb_stride, tris, n_tris, n_frames, eps, as_matrix, (float *)out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched saber.stream.seek (saber/data/stream/stream.py:20-46): the bracketing rows and the weight come from
+// the host (api.cpp restates the reference's binary search); the blend is evaluated in float64 like numpy does
+// with a float64 weight, then rounded to float32 (what frame_to_mesh casts to, viewer/frame.py:112).
+__global__ void k_seek(const float *__restrict__ seq, long long width, const int2 *__restrict__ pairs,
+                       const double *__restrict__ weights, float *__restrict__ out) {
+    const int q = blockIdx.y;
+    const int2 pr = pairs[q];
+    const double a = weights[q];
+    const float *lo = seq + (long long)pr.x * width, *hi = seq + (long long)pr.y * width;
+    float *dst = out + (long long)q * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < width; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = pr.x == pr.y ? lo[i] : (float)__dadd_rn(__dmul_rn(a, (double)lo[i]), __dmul_rn(1.0 - a, (double)hi[i]));   // no FMA: numpy's rounding
+}
+
+cudaError_t launch_seek(const float *seq, long long width, const int2 *pairs, const double *weights, int n_query, float *out,
+                        cudaStream_t stream) {
+    if (n_query <= 0 || width <= 0) return cudaSuccess;
+    const unsigned bx = (unsigned)std::min<long long>((width + 255) / 256, 64);
+    k_seek<<<dim3(bx, (unsigned)n_query), 256, 0, stream>>>(seq, width, pairs, weights, out);
     count_launch();
     return cudaGetLastError();
 }

@@ -361,6 +361,28 @@ def get_deform_grad_batch(verts_a, verts_b, faces, eps=1e-6, as_matrix=False):
     return out
 
 
+def seek_batch(query_ts, timestamps, sequence, out=None, stream=None):
+    """Batched ``saber.stream.seek`` (saber/data/stream/stream.py:20-46) on the device: ``sequence`` is a
+    torch.cuda float32 tensor [n_src, ...] sampled at ``timestamps`` (ascending); returns [len(query_ts), ...] with
+    every row blended like the reference does for one timestamp.  Seeking PCA coefficients and then calling
+    ``decode_and_get_mesh`` equals decoding and seeking the dgrad (the decode is affine)."""
+    import torch
+    if not _is_torch(sequence) or not sequence.is_cuda:
+        raise SdfaError(_native.ERR_ARG, "seek_batch: sequence must be a torch.cuda tensor")
+    seq = sequence.contiguous().to(torch.float32)
+    t = np.ascontiguousarray(timestamps, dtype=np.float64).reshape(-1)
+    q = np.ascontiguousarray(query_ts, dtype=np.float64).reshape(-1)
+    if len(t) != seq.shape[0]:
+        raise SdfaError(_native.ERR_ARG, "seek_batch: one timestamp per row of the sequence")   # stream.py:22
+    width = int(np.prod(seq.shape[1:])) if seq.dim() > 1 else 1
+    if out is None:
+        out = torch.empty((len(q),) + tuple(seq.shape[1:]), dtype=torch.float32, device=seq.device)
+    s = torch.cuda.current_stream(seq.device).cuda_stream if stream is None else stream
+    with torch.cuda.device(seq.device):
+        check(lib.sdfa_seek_dev(ptr(seq.data_ptr()), seq.shape[0], width, ptr(t), ptr(q), len(q), ptr(out.data_ptr()), ptr(s)))
+    return out
+
+
 def get_mesh_batch(deform_grads, vert_cnsts=None, out=None):
     r = _need_target()
     r.set_constraint_positions(vert_cnsts)

@@ -50,6 +50,7 @@ def _load():
         "sdfa_compact_layout": ([vp, vp, ci], ci),
         "sdfa_get_deform_grad_host": ([vp, vp, ci, vp, ci, cd, ci, ci, vp], ci),
         "sdfa_deform_grad_batch_dev": ([vp, vp, ci, vp, ci, ci, cd, ci, vp, vp], ci),
+        "sdfa_seek_dev": ([vp, ci, cll, vp, vp, ci, vp, vp], ci),
         "sdfa_launch_count": ([], cll),
         "sdfa_set_timing": ([vp, ci], ci),
         "sdfa_last_timing": ([vp, vp], ci),
@@ -67,7 +68,7 @@ EXPORTS = ["sdfa_create", "sdfa_destroy", "sdfa_info", "sdfa_last_error", "sdfa_
            "sdfa_set_correspondences", "sdfa_reconstruct_dev", "sdfa_reconstruct_host", "sdfa_get_mesh_f64",
            "sdfa_get_mesh_from_dm_f64", "sdfa_set_pca", "sdfa_decode_reconstruct_dev",
            "sdfa_decode_reconstruct_host", "sdfa_decode_dgrad_dev", "sdfa_decode_compact_dev", "sdfa_compact_layout",
-           "sdfa_get_deform_grad_host", "sdfa_deform_grad_batch_dev",
+           "sdfa_get_deform_grad_host", "sdfa_deform_grad_batch_dev", "sdfa_seek_dev",
            "sdfa_launch_count", "sdfa_set_timing", "sdfa_last_timing", "sdfa_debug_get"]
 
 

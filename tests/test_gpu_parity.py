@@ -312,3 +312,32 @@ def test_config4_network_to_mesh_on_device(rec, chk, flame):
     for i in (0, 239, 240, 479):
         ref = chk.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[nfv])
         assert np.abs(out[i].cpu().numpy() - ref).max() <= tol, i
+
+
+def test_seek_batch_matches_stream_seek(rec, chk, flame):
+    """§8(f) rank 2: saber.stream.seek batched on the device -- bit-equal to the restated reference per timestamp
+    (in range, exact hits, before the first and after the last sample), and seeking coefficients then decoding
+    equals decoding then seeking the dgrad."""
+    import torch
+    from oracle.dgrad_oracle import seek
+    V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
+    rng = np.random.default_rng(5)
+    ts = np.cumsum(rng.uniform(0.01, 0.03, 50))                 # uneven sampling times
+    seq = rng.normal(size=(50, 7, 3)).astype(np.float32)
+    q = np.concatenate([rng.uniform(ts[0] - 0.05, ts[-1] + 0.05, 200), ts[[0, 17, 49]], [ts[0] - 1.0, ts[-1] + 1.0]])
+    got = D.seek_batch(q, ts, torch.from_numpy(seq).cuda()).cpu().numpy()
+    for i, t in enumerate(q):
+        assert np.array_equal(got[i], np.asarray(seek(t, ts, seq)).astype(np.float32)), (i, t)
+    # coefficients at 30 fps -> meshes at 60 fps render times
+    cs, ms, cr, mr = W.random_pca(len(F), seed=1)
+    rec.set_pca(cs, ms, cr, mr)
+    xs, xr = W.random_coeffs(20, seed=9)
+    t30 = np.arange(20) / 30.0
+    t60 = np.arange(39) / 60.0
+    xs_q = D.seek_batch(t60, t30, torch.from_numpy(xs).cuda())
+    xr_q = D.seek_batch(t60, t30, torch.from_numpy(xr).cuda())
+    out = rec.decode_and_get_mesh(xs_q, xr_q).cpu().numpy()
+    dg = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float32)  # [20, 89784]: what the reference interpolates
+    for i in (0, 1, 18, 37, 38):
+        ref = chk.get_mesh(np.asarray(seek(t60[i], t30, dg)).astype(np.float32).astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(out[i] - ref).max() <= tol, i
