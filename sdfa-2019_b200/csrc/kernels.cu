@@ -489,8 +489,19 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 // One task on one warp (lane = frame).  Entry lists are padded by the host to whole batches (4 sources of
 // kind B, 4 packed pairs of kind A), and the next batch's entries are fetched while the current batch's
 // state values are in flight, so a batch costs one shared-memory round trip instead of two.
+// With fewer than 32 frames per tile (large factors) the warp's 32 / F lane groups split a task's entry batches among
+// them and add their partial sums with shuffles, instead of mirroring each other.
+template <int COORD_STRIDE>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+    for (int off = COORD_STRIDE; off < 32; off <<= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    return x;
+}
+
 template <int COORD_STRIDE>
 __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state_lane) {
+    constexpr int G = 32 / COORD_STRIDE;                            // lane groups
+    const int grp = (threadIdx.x & 31) / COORD_STRIDE;
     const uint4 th = *reinterpret_cast<const uint4 *>(task);       // TaskHeader
     const int n = (int)(th.w & 0xFFFFFFu);
     const uint4 *e = reinterpret_cast<const uint4 *>(task + 16);
@@ -499,9 +510,10 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
         float a[3][3] = {};
         constexpr int BB = TASK_BATCH_B;
         uint4 p[BB];
+        const int k0 = grp * BB;
 #pragma unroll
-        for (int j = 0; j < BB; ++j) p[j] = e[j];
-        for (int k = 0; k < n; k += BB) {
+        for (int j = 0; j < BB; ++j) p[j] = e[min(k0, n - BB) + j];
+        for (int k = k0; k < n; k += G * BB) {
             float v[BB][3];
 #pragma unroll
             for (int j = 0; j < BB; ++j) {
@@ -509,7 +521,7 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
                 v[j][0] = s[0]; v[j][1] = s[COORD_STRIDE]; v[j][2] = s[2 * COORD_STRIDE];
             }
             uint4 q[BB];
-            const int kn = (k + BB < n) ? k + BB : k;               // last batch re-reads itself (harmless)
+            const int kn = (k + G * BB < n) ? k + G * BB : k;       // last batch re-reads itself (harmless)
 #pragma unroll
             for (int j = 0; j < BB; ++j) q[j] = e[kn + j];
 #pragma unroll
@@ -524,6 +536,12 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
             }
 #pragma unroll
             for (int j = 0; j < BB; ++j) p[j] = q[j];
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) a[r][d] = group_sum<COORD_STRIDE>(a[r][d]);
         }
         const uint32_t tg[3] = {th.x, th.y, th.z};
 #pragma unroll
@@ -540,9 +558,10 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
     }
     // kind A: one target row, two entries {coeff, src} per uint4, 4 uint4 (8 entries) per batch
     float a[3] = {}, b[3] = {};
-    uint4 p[4] = {e[0], e[1], e[2], e[3]};
     const int nq = n >> 1;                                          // number of uint4 pairs, multiple of 4
-    for (int k = 0; k < nq; k += 4) {
+    const int q0 = grp * 4, qs = min(q0, nq - 4);
+    uint4 p[4] = {e[qs], e[qs + 1], e[qs + 2], e[qs + 3]};
+    for (int k = q0; k < nq; k += G * 4) {
         float v[4][2][3];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -552,7 +571,7 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
             v[j][1][0] = s1[0]; v[j][1][1] = s1[COORD_STRIDE]; v[j][1][2] = s1[2 * COORD_STRIDE];
         }
         uint4 q[4];
-        const int kn = (k + 4 < nq) ? k + 4 : k;
+        const int kn = (k + G * 4 < nq) ? k + G * 4 : k;
 #pragma unroll
         for (int j = 0; j < 4; ++j) q[j] = e[kn + j];
 #pragma unroll
@@ -563,6 +582,10 @@ __device__ __forceinline__ void run_row_task(const uint8_t *task, uint8_t *state
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) p[j] = q[j];
+    }
+    if (G > 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { a[d] = group_sum<COORD_STRIDE>(a[d] + b[d]); b[d] = 0.f; }
     }
     float *t = reinterpret_cast<float *>(state_lane + th.x);
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
