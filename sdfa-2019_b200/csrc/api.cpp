@@ -46,6 +46,10 @@ struct sdfa_handle {
         float *io_in2 = nullptr; size_t io_in2_cap = 0;
         float *io_out = nullptr; size_t io_out_cap = 0;
         cudaStream_t stream = nullptr;
+        // chunk pipeline: the output kernel of chunk i runs on `side` under the kernels of chunk i + 1
+        float *rhs2 = nullptr; size_t rhs2_cap = 0;
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_solved[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     } ws[2];
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -328,8 +332,10 @@ void sdfa_destroy(sdfa_handle *h) {
         cudaSetDevice(h->dev.device);
         for (void *p : h->allocs) cudaFree(p);
         for (auto &w : h->ws) {
-            for (float *p : {w.rhs, w.dgrad_c, w.io_in, w.io_out, w.io_in2, w.ximg_s, w.ximg_r}) if (p) cudaFree(p);
+            for (float *p : {w.rhs, w.rhs2, w.dgrad_c, w.io_in, w.io_out, w.io_in2, w.ximg_s, w.ximg_r}) if (p) cudaFree(p);
             if (w.stream) cudaStreamDestroy(w.stream);
+            if (w.side) cudaStreamDestroy(w.side);
+            for (cudaEvent_t e : {w.ev_solved[0], w.ev_solved[1], w.ev_out[0], w.ev_out[1]}) if (e) cudaEventDestroy(e);
         }
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     }
@@ -419,25 +425,89 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
     return SDFA_OK;
 }
 
+// One pass over frames [0, n_frames): assembly, solve and -- on stream `so` -- the output kernel.
+static int reconstruct_pass(sdfa_handle *h, float *rhs, const float *dgrad_dev, long long stride, bool staged, int mode,
+                            int n_frames, float *out_dev, cudaStream_t s, cudaStream_t so, cudaEvent_t solved) {
+    int rc;
+    if ((rc = time_mark(h, 1, s))) return rc;
+    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, staged, n_frames, mode, rhs, s));
+    if ((rc = time_mark(h, 2, s))) return rc;
+    if (h->dev.use_tensor) CUDA_TRY(launch_solve_tc(h->dev, rhs, n_frames, s));
+    else CUDA_TRY(launch_solve(h->dev, rhs, n_frames, s));
+    if ((rc = time_mark(h, 3, s))) return rc;
+    if (so != s) {
+        CUDA_TRY(cudaEventRecord(solved, s));
+        CUDA_TRY(cudaStreamWaitEvent(so, solved, 0));
+    }
+    CUDA_TRY(launch_output(h->dev, rhs, n_frames, out_dev, so));
+    return time_mark(h, 4, s);
+}
+
+static int grow_scratch(sdfa_handle *h, float **buf, size_t *cap, int n_frames, cudaStream_t s) {
+    const size_t need = scratch_floats(h->dev, n_frames);
+    if (*cap >= need) return SDFA_OK;
+    int rc;
+    if ((rc = grow(buf, cap, need))) return rc;
+    // columns of a partially filled tensor tile that no frame owns are solved too: keep them finite
+    CUDA_TRY(cudaMemsetAsync(*buf, 0, need * sizeof(float), s));
+    return SDFA_OK;
+}
+
+// Frames per chunk of the device-resident entry points (0: no chunking): four waves of 128-frame solve tiles.  Larger
+// batches run chunk by chunk, which bounds the workspace (compact dgrad 94 KB + scratch 2 x 18 KB per frame of a chunk,
+// not of the batch); the output kernel of a chunk runs on a second stream under the next chunk's kernels.  Measured on
+// the 75 600-frame bench batch the overlap is worth nothing (one-wave chunks: 7.31 ms against 7.28 ms in one pass --
+// the persistent decode and solve kernels leave no room for a second resident CTA), so the chunk is sized for memory.
+// Per-kernel timing runs unchunked.
+static int pipe_chunk(const sdfa_handle *h, int n_frames) {
+    const char *e = getenv("SDFA_PIPE_CHUNK");        // read per call: the tests switch it
+    const int env = e ? atoi(e) : -1;
+    if (h->timing || env == 0) return 0;
+    int chunk = env > 0 ? (env + 127) / 128 * 128 : h->dev.sm_count * 128 * 4;
+    return n_frames > chunk ? chunk : 0;
+}
+
+static int pipe_setup(sdfa_handle::Workspace &w) {
+    if (!w.side) CUDA_TRY(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!w.ev_solved[i]) CUDA_TRY(cudaEventCreateWithFlags(&w.ev_solved[i], cudaEventDisableTiming));
+        if (!w.ev_out[i]) CUDA_TRY(cudaEventCreateWithFlags(&w.ev_out[i], cudaEventDisableTiming));
+    }
+    return SDFA_OK;
+}
+
+// Runs `decode(f0, nf)` (may be empty) and the reconstruction chunk by chunk; dgrad_of(f0) is the chunk's input.
+template <class Decode, class Input>
+static int reconstruct_chunks(sdfa_handle *h, sdfa_handle::Workspace &w, int chunk, Decode decode, Input dgrad_of,
+                              long long stride, bool staged, int mode, int n_frames, float *out_dev, cudaStream_t s) {
+    int rc;
+    if ((rc = pipe_setup(w))) return rc;
+    if ((rc = grow_scratch(h, &w.rhs, &w.rhs_cap, chunk, s))) return rc;
+    if ((rc = grow_scratch(h, &w.rhs2, &w.rhs2_cap, chunk, s))) return rc;
+    const size_t row_out = (size_t)h->dev.n_verts * 3;
+    int i = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++i) {
+        const int nf = std::min(chunk, n_frames - f0), b = i & 1;
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(s, w.ev_out[b], 0));      // the scratch buffer is free again
+        if ((rc = decode(f0, nf))) return rc;
+        if ((rc = reconstruct_pass(h, b ? w.rhs2 : w.rhs, dgrad_of(f0), stride, staged, mode, nf,
+                                   out_dev + (size_t)f0 * row_out, s, w.side, w.ev_solved[b]))) return rc;
+        CUDA_TRY(cudaEventRecord(w.ev_out[b], w.side));
+    }
+    for (int b = 0; b < std::min(i, 2); ++b) CUDA_TRY(cudaStreamWaitEvent(s, w.ev_out[b], 0));
+    return SDFA_OK;
+}
+
 static int reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const float *dgrad_dev, long long stride,
                             bool staged, int mode, int n_frames, float *out_dev, cudaStream_t s, bool decoded) {
     int rc;
-    {
-        const size_t need = scratch_floats(h->dev, n_frames);
-        if (w.rhs_cap < need) {
-            if ((rc = grow(&w.rhs, &w.rhs_cap, need))) return rc;
-            // columns of a partially filled tensor tile that no frame owns are solved too: keep them finite
-            CUDA_TRY(cudaMemsetAsync(w.rhs, 0, need * sizeof(float), s));
-        }
-    }
-    if ((rc = time_mark(h, 1, s))) return rc;
-    CUDA_TRY(launch_assembly(h->dev, dgrad_dev, stride, staged, n_frames, mode, w.rhs, s));
-    if ((rc = time_mark(h, 2, s))) return rc;
-    if (h->dev.use_tensor) CUDA_TRY(launch_solve_tc(h->dev, w.rhs, n_frames, s));
-    else CUDA_TRY(launch_solve(h->dev, w.rhs, n_frames, s));
-    if ((rc = time_mark(h, 3, s))) return rc;
-    CUDA_TRY(launch_output(h->dev, w.rhs, n_frames, out_dev, s));
-    if ((rc = time_mark(h, 4, s))) return rc;
+    const int chunk = staged ? 0 : pipe_chunk(h, n_frames);
+    if (chunk)
+        return reconstruct_chunks(h, w, chunk, [](int, int) { return (int)SDFA_OK; },
+                                  [&](int f0) { return dgrad_dev + (long long)f0 * stride; }, stride, false, mode,
+                                  n_frames, out_dev, s);
+    if ((rc = grow_scratch(h, &w.rhs, &w.rhs_cap, n_frames, s))) return rc;
+    if ((rc = reconstruct_pass(h, w.rhs, dgrad_dev, stride, staged, mode, n_frames, out_dev, s, s, nullptr))) return rc;
     return time_finish(h, s, decoded);
 }
 
@@ -574,11 +644,20 @@ static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, co
                                    int n_frames, float *out_dev, cudaStream_t s) {
     int rc;
     const long long stride = h->dev.compact_stride;
-    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, ((size_t)n_frames + COMPACT_TILE - 1) / COMPACT_TILE * COMPACT_TILE * stride))) return rc;
+    const int chunk = pipe_chunk(h, n_frames), cap = chunk ? chunk : n_frames;
+    if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, ((size_t)cap + COMPACT_TILE - 1) / COMPACT_TILE * COMPACT_TILE * stride))) return rc;
+    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(cap, h->dev.k_scale)))) return rc;
+    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(cap, h->dev.k_rotat)))) return rc;
+    auto decode = [&](int f0, int nf) -> int {
+        CUDA_TRY(launch_decode_tc(h->dev, cs_dev + (size_t)f0 * h->dev.k_scale, cr_dev + (size_t)f0 * h->dev.k_rotat, nf,
+                                  w.ximg_s, w.ximg_r, w.dgrad_c, s));
+        return SDFA_OK;
+    };
+    if (chunk)
+        return reconstruct_chunks(h, w, chunk, decode, [&](int) { return (const float *)w.dgrad_c; }, stride, true,
+                                  ASM_DGRAD, n_frames, out_dev, s);
     if ((rc = time_mark(h, 0, s))) return rc;
-    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
-    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
-    CUDA_TRY(launch_decode_tc(h->dev, cs_dev, cr_dev, n_frames, w.ximg_s, w.ximg_r, w.dgrad_c, s));
+    if ((rc = decode(0, n_frames))) return rc;
     return reconstruct_core(h, w, w.dgrad_c, stride, true, ASM_DGRAD, n_frames, out_dev, s, true);
 }
 

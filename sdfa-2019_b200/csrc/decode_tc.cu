@@ -31,12 +31,22 @@ namespace {
 constexpr int TC_BM = 256;          // basis rows per tile (UMMA N): 256 halves the frames-operand traffic per MMA
 constexpr int TC_BN = 128;          // frames per tile (UMMA M = TMEM lanes)
 constexpr int TC_BK = 32;           // floats per K-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 2;
-constexpr int TC_CLUSTER = 2;       // CTAs per cluster: they decode TC_CLUSTER neighbouring frame tiles against the same basis
-                                    // tile, each fetching 1 / TC_CLUSTER of it and multicasting it to all (L2 reads it once)
-constexpr int TC_W_BYTES = TC_BM * TC_BK * 4;                    // 32 KB: one half (hi or lo) of the basis tile
-constexpr int TC_X_BYTES = TC_BN * TC_BK * 4;                    // 16 KB: one half of the frames tile
-constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;  // W_hi, W_lo, X_hi, X_lo = 96 KB
+constexpr int TC_STAGES = 3;
+constexpr int TC_PAIR = 2;          // a CTA pair (cta_group::2): one 256-frame x 256-row UMMA spans both SMs; each CTA stages its
+                                    // own 128 frames and HALF of the basis tile, the tensor cores read the other half from the peer
+#ifndef TC_CLUSTER_SIZE
+#define TC_CLUSTER_SIZE 2
+#endif
+constexpr int TC_CLUSTER = TC_CLUSTER_SIZE;   // CTAs per cluster = TC_CLUSTER / 2 pairs decoding neighbouring frame tiles against the
+                                    // same basis tile: a CTA fetches 1 / pairs of its half and multicasts it to the same-rank CTAs
+                                    // of the other pairs.  Measured: 4 and 8 cut the L2 reads by 25 / 37 % but only 132 / 120 SMs
+                                    // can hold whole clusters -- 2.35 / 2.53 ms against 2.36 ms for plain pairs, so 2 it is
+constexpr int TC_PAIRS = TC_CLUSTER / TC_PAIR;
+constexpr int TC_W_BYTES = TC_BM * TC_BK * 4;                    // 32 KB: the hi (or lo) image of the whole basis tile
+constexpr int TC_WH_BYTES = TC_W_BYTES / TC_PAIR;                // 16 KB: this CTA's rows of it
+constexpr int TC_WQ_BYTES = TC_WH_BYTES / TC_PAIRS;              // the slice of them it fetches itself
+constexpr int TC_X_BYTES = TC_BN * TC_BK * 4;                    // 16 KB: hi (or lo) image of the CTA's frames tile
+constexpr int TC_STAGE_BYTES = 2 * TC_WH_BYTES + 2 * TC_X_BYTES; // W_hi, W_lo (this CTA's rows), X_hi, X_lo = 64 KB
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each drains half of the columns
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue warps
 constexpr int TC_TMEM_COLS = 512;   // two 256-column fp32 accumulators
@@ -66,9 +76,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -85,8 +92,31 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals come from the peer CTA
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// remote arrive, default (CTA-scope release) semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): the thread has no
+// memory operations of its own to publish, and a cluster-scope release costs a MEMBAR.GPU per stage
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the same without cluster-scope release: the accumulator hand-back orders tensor-memory reads (tcgen05.wait::ld has
+// completed them), not the thread's global stores -- a release fence here would wait for all 128 of them
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // leading byte offset 1 (unused for swizzled K-major), stride byte offset 1024 >> 4 between 8-row groups,
@@ -96,13 +126,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     const uint32_t hi = 64u | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M = 128, N = 128, K = 8
+// D[tmem of both CTAs] (+)= A[smem] * B[smem]^T, kind::tf32, M = 256 (128 per CTA), N = 256 (128 rows of B per CTA), K = 8;
+// issued by the pair's leader only, the descriptors name the same shared-memory offsets in both CTAs
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile(
@@ -149,14 +180,15 @@ __device__ __forceinline__ TileInfo tile_info(const GemmParams &P, int t) {
     return ti;
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 256 rows, M = 128 frames
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(TC_BN >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 256 rows, M = 256 frames (the pair)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) |
+                              ((uint32_t)((TC_BN * TC_PAIR) >> 4) << 24);
 
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask) {
@@ -167,26 +199,31 @@ __device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst, const void 
 __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t crank = blockIdx.x % TC_CLUSTER, cid = blockIdx.x / TC_CLUSTER, n_clusters = gridDim.x / TC_CLUSTER;
+    const uint32_t prank = crank & 1u, pair = crank >> 1;      // rank inside the CTA pair (0 = leader), pair inside the cluster
     constexpr uint16_t CMASK = (uint16_t)((1u << TC_CLUSTER) - 1u);
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+    uint16_t rank_mask = 0;                                    // the CTAs that hold the same rows of the basis tile
+    for (int q = 0; q < TC_PAIRS; ++q) rank_mask |= (uint16_t)(1u << (2 * q + prank));
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *stages = smem;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * TC_STAGES + 4);
+    // full: this CTA's stage has landed; peer (leader only): the follower's has; empty: the pair's MMAs have read the stage
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES), bar_peer = smem_u32(bars + 2 * TC_STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 3 * TC_STAGES), bar_tempty = smem_u32(bars + 3 * TC_STAGES + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        // a stage is free once the MMAs of every CTA of the cluster have read it: the peers multicast into it
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_CLUSTER); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_PAIRS); mbar_init(bar_peer + 8 * s, 1); }
+        // the leader's accumulator is free once the epilogue warps of BOTH CTAs have drained their halves
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, TC_PAIR * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {   // one warp allocates the tensor memory and later frees it
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {   // the same warp of both CTAs allocates the pair's tensor memory and later frees it
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -196,59 +233,75 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
     const int n_tiles_total = (P.m_tiles[0] + P.m_tiles[1]) * (P.n_tiles / TC_CLUSTER);     // units per cluster walk
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
         if (lane == 0) {
             uint32_t it = 0;
-            constexpr uint32_t W_SLICE = 2 * TC_W_BYTES / TC_CLUSTER;     // this CTA's share of the basis tile (hi | lo images)
             for (int tile = cid; tile < n_tiles_total; tile += n_clusters) {
                 const TileInfo ti = tile_info(P, tile);
                 const int kbs = P.kb[ti.part];
-                const float *w = P.w_img[ti.part] + (size_t)ti.m * kbs * (2 * TC_BM * TC_BK);
+                const uint8_t *w = reinterpret_cast<const uint8_t *>(P.w_img[ti.part] + (size_t)ti.m * kbs * (2 * TC_BM * TC_BK)) +
+                                   prank * TC_WH_BYTES + pair * TC_WQ_BYTES;
                 const float *x = P.x_img[ti.part] + (size_t)(ti.n * TC_CLUSTER + crank) * kbs * (2 * TC_BN * TC_BK);
                 for (int kb = 0; kb < kbs; ++kb, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);            // all CTAs of the cluster are done with stage s
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);            // the MMAs of every pair are done with stage s
                     mbar_arrive_expect_tx(bar_full + 8 * s, TC_STAGE_BYTES);
                     const uint32_t dst = smem_u32(stages + s * TC_STAGE_BYTES);
-                    tma_bulk_g2s_multicast(dst + crank * W_SLICE, reinterpret_cast<const uint8_t *>(w + (size_t)kb * (2 * TC_BM * TC_BK)) + crank * W_SLICE,
-                                           W_SLICE, bar_full + 8 * s, CMASK);
-                    tma_bulk_g2s(dst + 2 * TC_W_BYTES, x + (size_t)kb * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES, bar_full + 8 * s);
+                    const uint8_t *wk = w + (size_t)kb * (2 * TC_W_BYTES);
+                    // rows 128 prank .. of W_hi and W_lo: this CTA's slice of them, to every CTA of the same rank
+                    tma_bulk_g2s_multicast(dst + pair * TC_WQ_BYTES, wk, TC_WQ_BYTES, bar_full + 8 * s, rank_mask);
+                    tma_bulk_g2s_multicast(dst + TC_WH_BYTES + pair * TC_WQ_BYTES, wk + TC_W_BYTES, TC_WQ_BYTES, bar_full + 8 * s, rank_mask);
+                    tma_bulk_g2s(dst + 2 * TC_WH_BYTES, x + (size_t)kb * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES, bar_full + 8 * s);
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        if (lane == 0 && prank != 0) {
+            // ------------------------------------------------------------------ follower: tell the leader when a stage has landed
+            const uint32_t peer0 = mapa(bar_peer, 2 * pair);
+            uint32_t it = 0;
+            for (int tile = cid; tile < n_tiles_total; tile += n_clusters) {
+                const int kbs = P.kb[tile_info(P, tile).part];
+                for (int kb = 0; kb < kbs; ++kb, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    mbar_arrive_cluster(peer0 + 8 * s);
+                }
+            }
+        } else if (lane == 0) {
+            // ------------------------------------------------------------------ leader: MMA issuer of the pair (one thread)
             uint32_t it = 0, tc = 0;
             for (int tile = cid; tile < n_tiles_total; tile += n_clusters, ++tc) {
                 const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
-                mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);         // epilogue has drained this accumulator
+                mbar_wait_cluster(bar_tempty + 8 * acc, aph ^ 1u);   // both epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TC_BM;
                 const int kbs = P.kb[tile_info(P, tile).part];
                 for (int kb = 0; kb < kbs; ++kb, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
+                    mbar_wait_cluster(bar_peer + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t base = smem_u32(stages + s * TC_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {          // UMMA K = 8 floats = 32 bytes
-                        const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_W_BYTES + k * 32);
-                        const uint64_t x_hi = umma_desc(base + 2 * TC_W_BYTES + k * 32);
-                        const uint64_t x_lo = umma_desc(base + 2 * TC_W_BYTES + TC_X_BYTES + k * 32);
+                        const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_WH_BYTES + k * 32);
+                        const uint64_t x_hi = umma_desc(base + 2 * TC_WH_BYTES + k * 32);
+                        const uint64_t x_lo = umma_desc(base + 2 * TC_WH_BYTES + TC_X_BYTES + k * 32);
                         umma_tf32(d_tmem, x_hi, w_hi, TC_IDESC, (kb | k) != 0);      // A = frames (M), B = basis rows (N)
                         umma_tf32(d_tmem, x_lo, w_hi, TC_IDESC, 1u);
                         umma_tf32(d_tmem, x_hi, w_lo, TC_IDESC, 1u);
                     }
-                    tc_commit_multicast(bar_empty + 8 * s, CMASK);   // tell every CTA of the cluster: this one has read stage s
+                    tc_commit_multicast(bar_empty + 8 * s, CMASK);   // every producer of the cluster: this pair has read stage s
                 }
-                tc_commit(bar_tfull + 8 * acc);                    // accumulator complete
+                tc_commit_multicast(bar_tfull + 8 * acc, pair_mask); // both epilogues of the pair: accumulator complete
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
         const int lane_grp = warp & 3;                              // TMEM lanes = frames 32*lane_grp .. +31 of the 128-frame tile
         const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (basis rows) it drains
+        const uint32_t tempty0 = mapa(bar_tempty, 2 * pair);
         uint32_t tc = 0;
         for (int tile = cid; tile < n_tiles_total; tile += n_clusters, ++tc) {
             const TileInfo ti = tile_info(P, tile);
@@ -275,15 +328,15 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty0 + 8 * acc);
         }
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync();                                // no CTA leaves while a peer may still multicast into it or signal its barriers
+    cluster_sync();                                // no CTA leaves while the pair's MMAs may still read its shared memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -353,7 +406,24 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
     GemmParams P{{d.tc_w_scale, d.tc_w_rotat}, {ximg_scale, ximg_rotat}, dgrad_out, stride, {0, d.compact_s_rows},
                  {d.tc_mt_scale, d.tc_mt_rotat}, {tc_kblocks(d.k_scale), tc_kblocks(d.k_rotat)}, n_frames, n_tiles};
     int grid = (P.m_tiles[0] + P.m_tiles[1]) * n_tiles;
-    if (grid > d.sm_count) grid = d.sm_count;
+    {
+        // persistent: as many clusters as can be resident at once (a cluster must fit inside one GPC)
+        static int max_clusters = 0;
+        if (!max_clusters) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(d.sm_count / TC_CLUSTER * TC_CLUSTER));
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = TC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_decode_tc, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.sm_count / TC_CLUSTER; }
+            max_clusters = n;
+        }
+        if (grid > max_clusters * TC_CLUSTER) grid = max_clusters * TC_CLUSTER;
+    }
     grid = grid / TC_CLUSTER * TC_CLUSTER;
     k_decode_tc<<<grid, TC_THREADS, smem, stream>>>(P);
     count_launch();

@@ -26,7 +26,7 @@ namespace sdfa {
 namespace {
 
 constexpr int TS_RING = 3;                     // matrix ring stages (32 KB each)
-constexpr int TS_ROWRING = 3;                  // scratch-row ring stages (<= 64 rows x 128 columns each)
+constexpr int TS_ROWRING = 2;                  // scratch-row ring stages (<= 64 rows x 128 columns each)
 constexpr int TS_ROWSTAGE_BYTES = TS_MAX_NODE * TS_COLS * 4;
 constexpr int TS_EPI_WARPS = 8;                // two warps per tensor-memory lane quarter, each takes every other 8-column chunk
 constexpr int TS_THREADS = 32 * (4 + TS_EPI_WARPS);   // streamer, issuer, row loader, row storer, epilogue warps

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "..", "lib", "libsdfa_b200.so")
+LIB_PATH = os.environ.get("SDFA_LIB") or os.path.join(_HERE, "..", "lib", "libsdfa_b200.so")   # SDFA_LIB: A/B builds
 
 OK, ERR_ARG, ERR_FACTOR, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4, 5
 

@@ -289,6 +289,30 @@ def test_config3_batch_sizes_give_identical_frames(rec, flame):
         assert torch.equal(out[:64], ref) and torch.equal(out[n - 64:], ref), n
 
 
+def test_chunk_pipeline_is_bit_identical(rec, flame, monkeypatch):
+    """Large batches run chunk by chunk with the output kernel of a chunk on a second stream (api.cpp
+    reconstruct_chunks): forced to 256-frame chunks, both entry points return exactly what the single pass returns,
+    ragged last chunk included, and back-to-back calls do not race on the two scratch buffers."""
+    import torch
+    F = flame["F"]
+    n = 256 * 5 + 77
+    dg = torch.from_numpy(W.iid_dgrad(64, len(F), sigma=0.02, seed=33)).cuda().repeat((n + 63) // 64, 1)[:n].contiguous()
+    cs, ms, cr, mr = W.random_pca(len(F), seed=1)
+    rec.set_pca(cs, ms, cr, mr)
+    xs, xr = (torch.from_numpy(a).cuda() for a in W.random_coeffs(n, seed=8))
+    monkeypatch.setenv("SDFA_PIPE_CHUNK", "0")
+    ref_a, ref_b = rec.get_mesh_batch(dg), rec.decode_and_get_mesh(xs, xr)
+    monkeypatch.setenv("SDFA_PIPE_CHUNK", "256")
+    for _ in range(3):
+        out_a, out_b = rec.get_mesh_batch(dg), rec.decode_and_get_mesh(xs, xr)
+        assert torch.equal(out_a, ref_a) and torch.equal(out_b, ref_b)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        out_c = rec.decode_and_get_mesh(xs, xr, stream=side.cuda_stream)
+    side.synchronize()
+    assert torch.equal(out_c, ref_b)
+
+
 def test_config4_network_to_mesh_on_device(rec, chk, flame):
     """Config 4 in miniature: audio features -> random-init temporal network (plain torch, stands in for
     speech_anime's model, config/model/dgrad.py:60-86) -> PCA coefficients -> K1..K5, everything staying on the
