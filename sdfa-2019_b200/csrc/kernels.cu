@@ -266,7 +266,10 @@ __device__ __forceinline__ void eq_apply2(float *acc, int lane, int mode, int sr
 
 static_assert(COMPACT_TILE == 64, "k_assemble carries two frames per lane");
 
-__global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
+#ifndef ASM_MIN_BLOCKS
+#define ASM_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_BLOCKS) k_assemble(AsmParams P) {
     extern __shared__ __align__(16) float acc[];                     // [row][3][64]
     constexpr int CT = COMPACT_TILE;
     const int4 blk = P.blocks[blockIdx.x];
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
     for (int i = threadIdx.x; i < n_rows * 3 * CT; i += ASM_THREADS) acc[i] = 0.f;
     // this tile's lines (six scale lines and three rotation lines per equation); the lane's two frames are adjacent
     const float2 *in = reinterpret_cast<const float2 *>(P.dgrad + (long long)tile * P.frame_stride * CT) + lane;
-    // the block's eight walks go to shared memory first, so that an entry costs a shared-memory read and the only
+    // the block's walks (one per warp) go to shared memory first, so that an entry costs a shared-memory read and the only
     // long-latency loads are an equation's values and its record -- both issued one equation ahead
     int4 *walk_sh = reinterpret_cast<int4 *>(acc + P.max_rows * 3 * CT);
     {
@@ -333,9 +336,10 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(AsmParams P) {
 // [row*3+c][33] transpose buffer; one block barrier per frame.
 constexpr int ASM_GF = 16;                      // frames per CTA of the gather variant (smaller tile: more CTAs per SM)
 constexpr int ASM_GPAD = ASM_GF + 1;
-constexpr int ASM_KMAX = ASM_MAX_EQ / ASM_THREADS;
+constexpr int ASM_G_WARPS = 8, ASM_G_THREADS = 32 * ASM_G_WARPS;   // the gather variant keeps 8 warps: thread = equation
+constexpr int ASM_KMAX = ASM_MAX_EQ / ASM_G_THREADS;
 
-__global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
+__global__ void __launch_bounds__(ASM_G_THREADS) k_assemble_gather(AsmParams P) {
     extern __shared__ __align__(16) float sh[];
     const int plane = (3 * P.max_eq + 3) & ~3;
     float *stage = sh;                                              // [2][3 planes][plane]: the frame's values, planar
@@ -347,13 +351,13 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
     const int tile = blockIdx.y;
     const int frame0 = tile * ASM_GF;
     const int nvalid = max(0, min(ASM_GF, P.n_frames - frame0));    // 0: a tile past the batch only zero-fills its lanes
-    for (int e = threadIdx.x; e < n_eq; e += ASM_THREADS) src_sh[e] = P.eq_src_local[blk.x + e];
+    for (int e = threadIdx.x; e < n_eq; e += ASM_G_THREADS) src_sh[e] = P.eq_src_local[blk.x + e];
     __syncthreads();
     int src_k[ASM_KMAX];
     float4 m0_k[ASM_KMAX], m1_k[ASM_KMAX];
 #pragma unroll
     for (int k = 0; k < ASM_KMAX; ++k) {
-        const int e = threadIdx.x + k * ASM_THREADS;
+        const int e = threadIdx.x + k * ASM_G_THREADS;
         src_k[k] = -1;
         m0_k[k] = m1_k[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < n_eq) {
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
     auto gather = [&](int ft, int si) {
         const float *row = P.dgrad + (long long)(frame0 + ft) * P.frame_stride;
         float *dst = stage + si * 3 * plane;
-        for (int v = threadIdx.x; v < n_eq * 9; v += ASM_THREADS) {
+        for (int v = threadIdx.x; v < n_eq * 9; v += ASM_G_THREADS) {
             const int e = v / 9, j = v - 9 * e;
             const int sr = src_sh[e];
             if (sr < 0) continue;
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
         float *g_sh = g_sh0 + (f & 1) * P.max_eq * 9;
 #pragma unroll
         for (int k = 0; k < ASM_KMAX; ++k) {
-            const int e = threadIdx.x + k * ASM_THREADS;
+            const int e = threadIdx.x + k * ASM_G_THREADS;
             if (e >= n_eq || f >= nvalid) break;
             const int src = src_k[k];
             const float u0[3] = {m0_k[k].x, m0_k[k].y, m0_k[k].z}, u1[3] = {m0_k[k].w, m1_k[k].x, m1_k[k].y};
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
         if (f >= 1) {
             const float *gp = g_sh0 + ((f - 1) & 1) * P.max_eq * 9;
             // rows are dealt from the top thread ids down: the low threads carry the extra equations above
-            for (int r = ASM_THREADS - 1 - threadIdx.x; r < n_rows; r += ASM_THREADS) {
+            for (int r = ASM_G_THREADS - 1 - threadIdx.x; r < n_rows; r += ASM_G_THREADS) {
                 const int gr = blk.z + r;
                 const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_gather(AsmParams P) {
     const int fl = lane % ASM_GF, sub = lane / ASM_GF;
     const int fr = frame0 + fl;
     float *dst_tile = P.rhs + (long long)(fr / P.L.FL) * P.L.tile_stride + fr % P.L.FL;
-    for (int line = warp * LPW + sub; line < n_rows * 3; line += ASM_WARPS * LPW) {
+    for (int line = warp * LPW + sub; line < n_rows * 3; line += ASM_G_WARPS * LPW) {
         const int r = line / 3, c = line - 3 * r;
         dst_tile[(long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride] = fl < nvalid ? t_sh[line * ASM_GPAD + fl] : 0.f;
     }
@@ -453,7 +457,7 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
     else {
         // whole 32-frame groups are covered so that the scratch's idle lanes of a partial group hold zeros
         grid.y = (unsigned)((n_frames + 31) / 32 * (32 / ASM_GF));
-        k_assemble_gather<<<grid, ASM_THREADS, smem, stream>>>(P);
+        k_assemble_gather<<<grid, ASM_G_THREADS, smem, stream>>>(P);
     }
     g_launches++;
     return cudaGetLastError();

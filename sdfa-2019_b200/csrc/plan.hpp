@@ -87,7 +87,10 @@ struct SolveProgram {
 // summation order.
 constexpr int COMPACT_TILE = 64;                 // frames per tile of the compact dgrad: K2 handles two frames per lane (packed fp32x2)
 constexpr int ASM_MAX_COLOURS = 32;
-constexpr int ASM_WARPS_PER_BLOCK = 8;
+#ifndef ASM_WARPS_N
+#define ASM_WARPS_N 10
+#endif
+constexpr int ASM_WARPS_PER_BLOCK = ASM_WARPS_N;
 constexpr int16_t ASM_SCHED_BARRIER = -1, ASM_SCHED_END = -2;
 struct AssemblyBlock {
     int eq_begin, eq_end;       // range in eq_* arrays (block-local equations, duplicates across blocks allowed)
@@ -159,6 +162,7 @@ void solve_factored(const HostPlan &p, std::vector<double> &rhs_perm /* [n_free*
 // schedule.cpp
 void build_solve_program(HostPlan &p, int piece_cap, int supernode_cap, int subtree_cap, int frames_per_tile);
 void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block);
+constexpr int ASM_ROWS_MAX = 116; // vertices per row block of the assembly kernel (api.cpp splits evenly below this)
 constexpr int ASM_MAX_EQ = 512;   // equations per row block the assembly kernel keeps in registers/shared memory
 
 }  // namespace sdfa
