@@ -31,22 +31,22 @@ namespace {
 constexpr int TC_BM = 256;          // basis rows per tile (UMMA N): 256 halves the frames-operand traffic per MMA
 constexpr int TC_BN = 128;          // frames per tile (UMMA M = TMEM lanes)
 constexpr int TC_BK = 32;           // floats per K-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_PAIR = 2;          // a CTA pair (cta_group::2): one 256-frame x 256-row UMMA spans both SMs; each CTA stages its
-                                    // own 128 frames and HALF of the basis tile, the tensor cores read the other half from the peer
-#ifndef TC_CLUSTER_SIZE
-#define TC_CLUSTER_SIZE 2
-#endif
-constexpr int TC_CLUSTER = TC_CLUSTER_SIZE;   // CTAs per cluster = TC_CLUSTER / 2 pairs decoding neighbouring frame tiles against the
-                                    // same basis tile: a CTA fetches 1 / pairs of its half and multicasts it to the same-rank CTAs
-                                    // of the other pairs.  Measured: 4 and 8 cut the L2 reads by 25 / 37 % but only 132 / 120 SMs
-                                    // can hold whole clusters -- 2.35 / 2.53 ms against 2.36 ms for plain pairs, so 2 it is
-constexpr int TC_PAIRS = TC_CLUSTER / TC_PAIR;
+constexpr int TC_CLUSTER = 2;       // a CTA pair (cta_group::2): one 256-frame x 256-row UMMA spans both SMs; each CTA stages its
+                                    // own 128 frames and HALF of the basis tile, the tensor cores read the other half from the peer.
+                                    // (Measured: clusters of 2 or 4 pairs multicasting the basis tile cut the L2 reads by 25 / 37 %,
+                                    // but only 132 / 120 SMs can hold whole clusters -- 2.35 / 2.53 ms against 2.36 ms for one pair.)
 constexpr int TC_W_BYTES = TC_BM * TC_BK * 4;                    // 32 KB: the hi (or lo) image of the whole basis tile
-constexpr int TC_WH_BYTES = TC_W_BYTES / TC_PAIR;                // 16 KB: this CTA's rows of it
-constexpr int TC_WQ_BYTES = TC_WH_BYTES / TC_PAIRS;              // the slice of them it fetches itself
+constexpr int TC_WH_BYTES = TC_W_BYTES / TC_CLUSTER;             // 16 KB: this CTA's rows of it
 constexpr int TC_X_BYTES = TC_BN * TC_BK * 4;                    // 16 KB: hi (or lo) image of the CTA's frames tile
-constexpr int TC_STAGE_BYTES = 2 * TC_WH_BYTES + 2 * TC_X_BYTES; // W_hi, W_lo (this CTA's rows), X_hi, X_lo = 64 KB
+// Shared memory: a ring of 32 KB slots -- one K-block of the basis (this CTA's rows, hi | lo) or of the frames (hi | lo)
+// -- plus the RESIDENT frames operand of the scale part: its K = 85 + 1 is three K-blocks = 96 KB, loaded once per
+// 128-frame tile and reused by all 61 scale tiles, so a scale K-block streams 32 KB instead of 64 (the kernel is bound
+// by operand traffic from L2 plus its own 94 KB/frame of stores).  Rotation K-blocks (K = 180 + 1: six blocks, 192 KB
+// of frames) stream both operands.
+constexpr int TC_SLOT_BYTES = 2 * TC_WH_BYTES;                   // = 2 * TC_X_BYTES = 32 KB
+constexpr int TC_SLOTS = 4;
+constexpr int TC_XS_KB = 3;                                      // resident K-blocks of the scale part's frames operand
+static_assert(2 * TC_X_BYTES == TC_SLOT_BYTES, "one slot holds either operand's K-block");
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each drains half of the columns
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);   // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue warps
 constexpr int TC_TMEM_COLS = 512;   // two 256-column fp32 accumulators
@@ -161,7 +161,7 @@ struct GemmParams {
 };
 
 struct TileInfo { int part, m, n; };
-// unit t of a cluster: frame-tile group n = t / (m_tiles[0] + m_tiles[1]); inside it scale, scale, rotation, ... while both last
+// unit t of the walk: frame-tile group n = t / (m_tiles[0] + m_tiles[1]); inside it scale, scale, rotation, ... while both last
 __device__ __forceinline__ TileInfo tile_info(const GemmParams &P, int t) {
     const int per_n = P.m_tiles[0] + P.m_tiles[1];
     TileInfo ti;
@@ -182,7 +182,7 @@ __device__ __forceinline__ TileInfo tile_info(const GemmParams &P, int t) {
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 256 rows, M = 256 frames (the pair)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) |
-                              ((uint32_t)((TC_BN * TC_PAIR) >> 4) << 24);
+                              ((uint32_t)((TC_BN * TC_CLUSTER) >> 4) << 24);
 
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -191,33 +191,28 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
-
 __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1) k_decode_tc(GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t crank = blockIdx.x % TC_CLUSTER, cid = blockIdx.x / TC_CLUSTER, n_clusters = gridDim.x / TC_CLUSTER;
-    const uint32_t prank = crank & 1u, pair = crank >> 1;      // rank inside the CTA pair (0 = leader), pair inside the cluster
     constexpr uint16_t CMASK = (uint16_t)((1u << TC_CLUSTER) - 1u);
-    const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
-    uint16_t rank_mask = 0;                                    // the CTAs that hold the same rows of the basis tile
-    for (int q = 0; q < TC_PAIRS; ++q) rank_mask |= (uint16_t)(1u << (2 * q + prank));
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *stages = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * TC_STAGES + 4);
-    // full: this CTA's stage has landed; peer (leader only): the follower's has; empty: the pair's MMAs have read the stage
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES), bar_peer = smem_u32(bars + 2 * TC_STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 3 * TC_STAGES), bar_tempty = smem_u32(bars + 3 * TC_STAGES + 2);
+    uint8_t *slots = smem, *xs = smem + TC_SLOTS * TC_SLOT_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xs + TC_XS_KB * TC_SLOT_BYTES);
+    // per slot -- full: this CTA's copy has landed; peer (leader only): the follower's has; empty: the pair's MMAs have read it.
+    // The same three for the resident operand (index TC_SLOTS), then the two accumulators' full / empty.
+    constexpr int NB = TC_SLOTS + 1;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NB), bar_peer = smem_u32(bars + 2 * NB);
+    const uint32_t bar_tfull = smem_u32(bars + 3 * NB), bar_tempty = smem_u32(bars + 3 * NB + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * NB + 4);
+    const uint32_t xs_full = bar_full + 8 * TC_SLOTS, xs_empty = bar_empty + 8 * TC_SLOTS, xs_peer = bar_peer + 8 * TC_SLOTS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool resident = P.kb[0] <= TC_XS_KB;       // else the scale part streams its frames operand like the rotation part
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_PAIRS); mbar_init(bar_peer + 8 * s, 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_peer + 8 * s, 1); }
         // the leader's accumulator is free once the epilogue warps of BOTH CTAs have drained their halves
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, TC_PAIR * TC_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, TC_CLUSTER * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -230,80 +225,123 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
     tc_fence_after();
     cluster_sync();                                // every CTA's barriers exist before a peer signals them
     const uint32_t tmem_base = *tmem_slot;
-    const int n_tiles_total = (P.m_tiles[0] + P.m_tiles[1]) * (P.n_tiles / TC_CLUSTER);     // units per cluster walk
+    // a pair walks a CONTIGUOUS range of units (frame-tile pair n major, the basis tiles inside it scale, scale, rotation, ...)
+    // so that the resident frames operand changes once per m_tiles[0] + m_tiles[1] units
+    const long long n_units = (long long)(P.m_tiles[0] + P.m_tiles[1]) * (P.n_tiles / TC_CLUSTER);
+    const int t_begin = (int)(n_units * cid / n_clusters), t_end = (int)(n_units * (cid + 1) / n_clusters);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = cid; tile < n_tiles_total; tile += n_clusters) {
+            uint32_t it = 0, xit = 0;
+            int cur_n = -1;
+            auto slot_begin = [&]() -> uint32_t {
+                const uint32_t s = it % TC_SLOTS, ph = (it / TC_SLOTS) & 1u;
+                ++it;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);                // the pair's MMAs are done with the slot
+                mbar_arrive_expect_tx(bar_full + 8 * s, TC_SLOT_BYTES);
+                return s;
+            };
+            for (int tile = t_begin; tile < t_end; ++tile) {
                 const TileInfo ti = tile_info(P, tile);
                 const int kbs = P.kb[ti.part];
-                const uint8_t *w = reinterpret_cast<const uint8_t *>(P.w_img[ti.part] + (size_t)ti.m * kbs * (2 * TC_BM * TC_BK)) +
-                                   prank * TC_WH_BYTES + pair * TC_WQ_BYTES;
+                const uint8_t *w = reinterpret_cast<const uint8_t *>(P.w_img[ti.part] + (size_t)ti.m * kbs * (2 * TC_BM * TC_BK)) + crank * TC_WH_BYTES;
                 const float *x = P.x_img[ti.part] + (size_t)(ti.n * TC_CLUSTER + crank) * kbs * (2 * TC_BN * TC_BK);
-                for (int kb = 0; kb < kbs; ++kb, ++it) {
-                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);            // the MMAs of every pair are done with stage s
-                    mbar_arrive_expect_tx(bar_full + 8 * s, TC_STAGE_BYTES);
-                    const uint32_t dst = smem_u32(stages + s * TC_STAGE_BYTES);
+                const bool stream_x = ti.part == 1 || !resident;
+                if (!stream_x && ti.n != cur_n) {                     // new frame tile: reload the resident operand
+                    mbar_wait(xs_empty, (xit & 1u) ^ 1u);             // every MMA that read the old one has completed
+                    mbar_arrive_expect_tx(xs_full, (uint32_t)kbs * TC_SLOT_BYTES);
+                    for (int kb = 0; kb < kbs; ++kb)
+                        tma_bulk_g2s(smem_u32(xs + kb * TC_SLOT_BYTES), x + (size_t)kb * (2 * TC_BN * TC_BK), TC_SLOT_BYTES, xs_full);
+                    ++xit;
+                    cur_n = ti.n;
+                }
+                for (int kb = 0; kb < kbs; ++kb) {
                     const uint8_t *wk = w + (size_t)kb * (2 * TC_W_BYTES);
-                    // rows 128 prank .. of W_hi and W_lo: this CTA's slice of them, to every CTA of the same rank
-                    tma_bulk_g2s_multicast(dst + pair * TC_WQ_BYTES, wk, TC_WQ_BYTES, bar_full + 8 * s, rank_mask);
-                    tma_bulk_g2s_multicast(dst + TC_WH_BYTES + pair * TC_WQ_BYTES, wk + TC_W_BYTES, TC_WQ_BYTES, bar_full + 8 * s, rank_mask);
-                    tma_bulk_g2s(dst + 2 * TC_WH_BYTES, x + (size_t)kb * (2 * TC_BN * TC_BK), 2 * TC_X_BYTES, bar_full + 8 * s);
+                    const uint32_t s = slot_begin(), dst = smem_u32(slots + s * TC_SLOT_BYTES);
+                    tma_bulk_g2s(dst, wk, TC_WH_BYTES, bar_full + 8 * s);                              // rows 128 crank .. of W_hi
+                    tma_bulk_g2s(dst + TC_WH_BYTES, wk + TC_W_BYTES, TC_WH_BYTES, bar_full + 8 * s);   // the same rows of W_lo
+                    if (stream_x) {
+                        const uint32_t s2 = slot_begin();
+                        tma_bulk_g2s(smem_u32(slots + s2 * TC_SLOT_BYTES), x + (size_t)kb * (2 * TC_BN * TC_BK), TC_SLOT_BYTES, bar_full + 8 * s2);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && prank != 0) {
-            // ------------------------------------------------------------------ follower: tell the leader when a stage has landed
-            const uint32_t peer0 = mapa(bar_peer, 2 * pair);
-            uint32_t it = 0;
-            for (int tile = cid; tile < n_tiles_total; tile += n_clusters) {
-                const int kbs = P.kb[tile_info(P, tile).part];
-                for (int kb = 0; kb < kbs; ++kb, ++it) {
-                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+        if (lane == 0 && crank != 0) {
+            // ------------------------------------------------------------------ follower: tell the leader what has landed here
+            const uint32_t peer0 = mapa(bar_peer, 0), xs_peer0 = mapa(xs_peer, 0);
+            uint32_t it = 0, xit = 0;
+            int cur_n = -1;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const TileInfo ti = tile_info(P, tile);
+                const bool stream_x = ti.part == 1 || !resident;
+                if (!stream_x && ti.n != cur_n) {
+                    mbar_wait(xs_full, xit & 1u);
+                    mbar_arrive_cluster(xs_peer0);
+                    ++xit;
+                    cur_n = ti.n;
+                }
+                const int n_slots = P.kb[ti.part] * (stream_x ? 2 : 1);
+                for (int k = 0; k < n_slots; ++k, ++it) {
+                    const uint32_t s = it % TC_SLOTS, ph = (it / TC_SLOTS) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
                     mbar_arrive_cluster(peer0 + 8 * s);
                 }
             }
         } else if (lane == 0) {
             // ------------------------------------------------------------------ leader: MMA issuer of the pair (one thread)
-            uint32_t it = 0, tc = 0;
-            for (int tile = cid; tile < n_tiles_total; tile += n_clusters, ++tc) {
+            uint32_t it = 0, tc = 0, xit = 0;
+            int cur_n = -1;
+            auto slot_ready = [&]() -> uint32_t {
+                const uint32_t s = it % TC_SLOTS, ph = (it / TC_SLOTS) & 1u;
+                ++it;
+                mbar_wait(bar_full + 8 * s, ph);
+                mbar_wait_cluster(bar_peer + 8 * s, ph);
+                return s;
+            };
+            for (int tile = t_begin; tile < t_end; ++tile, ++tc) {
+                const TileInfo ti = tile_info(P, tile);
+                const bool stream_x = ti.part == 1 || !resident;
                 const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+                if (!stream_x && ti.n != cur_n) {
+                    if (cur_n >= 0) tc_commit_multicast(xs_empty, CMASK);   // both producers: the old resident operand has been read
+                    mbar_wait(xs_full, xit & 1u);
+                    mbar_wait_cluster(xs_peer, xit & 1u);
+                    ++xit;
+                    cur_n = ti.n;
+                }
                 mbar_wait_cluster(bar_tempty + 8 * acc, aph ^ 1u);   // both epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TC_BM;
-                const int kbs = P.kb[tile_info(P, tile).part];
-                for (int kb = 0; kb < kbs; ++kb, ++it) {
-                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    mbar_wait_cluster(bar_peer + 8 * s, ph);
+                const int kbs = P.kb[ti.part];
+                for (int kb = 0; kb < kbs; ++kb) {
+                    const uint32_t sw = slot_ready(), sx = stream_x ? slot_ready() : 0u;
                     tc_fence_after();
-                    const uint32_t base = smem_u32(stages + s * TC_STAGE_BYTES);
+                    const uint32_t wbase = smem_u32(slots + sw * TC_SLOT_BYTES);
+                    const uint32_t xbase = stream_x ? smem_u32(slots + sx * TC_SLOT_BYTES) : smem_u32(xs + kb * TC_SLOT_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {          // UMMA K = 8 floats = 32 bytes
-                        const uint64_t w_hi = umma_desc(base + k * 32), w_lo = umma_desc(base + TC_WH_BYTES + k * 32);
-                        const uint64_t x_hi = umma_desc(base + 2 * TC_WH_BYTES + k * 32);
-                        const uint64_t x_lo = umma_desc(base + 2 * TC_WH_BYTES + TC_X_BYTES + k * 32);
+                        const uint64_t w_hi = umma_desc(wbase + k * 32), w_lo = umma_desc(wbase + TC_WH_BYTES + k * 32);
+                        const uint64_t x_hi = umma_desc(xbase + k * 32), x_lo = umma_desc(xbase + TC_X_BYTES + k * 32);
                         umma_tf32(d_tmem, x_hi, w_hi, TC_IDESC, (kb | k) != 0);      // A = frames (M), B = basis rows (N)
                         umma_tf32(d_tmem, x_lo, w_hi, TC_IDESC, 1u);
                         umma_tf32(d_tmem, x_hi, w_lo, TC_IDESC, 1u);
                     }
-                    tc_commit_multicast(bar_empty + 8 * s, CMASK);   // every producer of the cluster: this pair has read stage s
+                    tc_commit_multicast(bar_empty + 8 * sw, CMASK);  // both producers: the slot has been read
+                    if (stream_x) tc_commit_multicast(bar_empty + 8 * sx, CMASK);
                 }
-                tc_commit_multicast(bar_tfull + 8 * acc, pair_mask); // both epilogues of the pair: accumulator complete
+                tc_commit_multicast(bar_tfull + 8 * acc, CMASK);     // both epilogues: accumulator complete
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
         const int lane_grp = warp & 3;                              // TMEM lanes = frames 32*lane_grp .. +31 of the 128-frame tile
         const int col_half = (warp - 2) >> 2;                       // which 64 of the 128 columns (basis rows) it drains
-        const uint32_t tempty0 = mapa(bar_tempty, 2 * pair);
+        const uint32_t tempty0 = mapa(bar_tempty, 0);
         uint32_t tc = 0;
-        for (int tile = cid; tile < n_tiles_total; tile += n_clusters, ++tc) {
+        for (int tile = t_begin; tile < t_end; ++tile, ++tc) {
             const TileInfo ti = tile_info(P, tile);
             const int m = ti.m, n = ti.n * TC_CLUSTER + (int)crank;
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
@@ -389,7 +427,7 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     const int n_tiles = tc_frame_tiles(n_frames);                  // padded to whole clusters
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 1024;
+    const size_t smem = (size_t)(TC_SLOTS + TC_XS_KB) * TC_SLOT_BYTES + 256 + 1024;
     {
         cudaError_t e = cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
