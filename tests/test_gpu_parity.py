@@ -182,6 +182,27 @@ def test_tensor_core_decode_matches_fp64(rec, flame):
         assert err <= 5e-7, (n, err, err32)
 
 
+def test_tensor_core_decode_other_basis_sizes(flame):
+    """K1 with bases of other widths than the reference's 85 + 180: a scale basis wider than three K-blocks (its frames
+    operand is then streamed instead of resident in shared memory), a one-block rotation basis, and widths that
+    are exact multiples of the 32-float K-block (the means' column opens a new block).  Several frame tiles, so that
+    CTA pairs change tiles mid-walk."""
+    import torch
+    V, F, nfv = flame["V"], flame["F"], flame["nfv"]
+    r = D.Reconstructor(V, F, cnsts=nfv, device=0)
+    for ks, kr in ((120, 20), (96, 31), (32, 64), (5, 200)):
+        cs, ms, cr, mr = W.random_pca(len(F), seed=3, k_scale=ks, k_rotat=kr)
+        r.set_pca(cs, ms, cr, mr)
+        n = 700
+        xs, xr = W.random_coeffs(n, seed=ks, k_scale=ks, k_rotat=kr)
+        got = r.decode_compact(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda()).cpu().numpy()
+        lay = r.compact_layout()
+        used = lay >= 0
+        dg64 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float64)[:, lay[used]]
+        assert np.abs(got[:, used] - dg64).max() <= 5e-7, (ks, kr)
+    r.close()
+
+
 def test_decode_and_reconstruct_config2(rec, chk, flame):
     """Config 2: 240 frames of PCA coefficients -> vertices; oracle = fp32 F.linear + cat + reference get_mesh."""
     import torch
