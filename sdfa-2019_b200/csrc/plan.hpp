@@ -88,7 +88,7 @@ struct SolveProgram {
 constexpr int COMPACT_TILE = 64;                 // frames per tile of the compact dgrad: K2 handles two frames per lane (packed fp32x2)
 constexpr int ASM_MAX_COLOURS = 32;
 #ifndef ASM_WARPS_N
-#define ASM_WARPS_N 10
+#define ASM_WARPS_N 16
 #endif
 constexpr int ASM_WARPS_PER_BLOCK = ASM_WARPS_N;
 constexpr int16_t ASM_SCHED_BARRIER = -1, ASM_SCHED_END = -2;

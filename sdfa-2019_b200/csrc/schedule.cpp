@@ -650,7 +650,10 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
                 for (int q = 0; q < limit; ++q) {
                     if (used >> q & 1u) continue;
                     if (pass == 0) { c = q; break; }
-                    if (c < 0 || load[q] < load[c]) c = q;
+                    // a colour whose last round of ASM_WARPS_PER_BLOCK equations is still open comes first (its warps
+                    // would idle otherwise), then the emptiest
+                    auto key = [&](int x) { return (load[x] % ASM_WARPS_PER_BLOCK == 0 ? (1 << 20) : 0) + load[x]; };
+                    if (c < 0 || key(q) < key(c)) c = q;
                 }
                 if (c < 0) {
                     for (int q = limit; q < ASM_MAX_COLOURS && c < 0; ++q) if (!(used >> q & 1u)) c = q;
@@ -661,6 +664,53 @@ void build_assembly_plan(HostPlan &p, int rows_per_block, int max_eq_per_block) 
                 n_colours = std::max(n_colours, c + 1);
                 for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) row_colours[local_row[g]] |= 1u << c;
             }
+        }
+        // A colour costs ceil(load / warps) rounds (one equation per warp and round, a barrier at its end): empty the
+        // last, partly filled round of a colour into the open rounds of the others where the rows allow it, cheapest
+        // colour first, until nothing moves.
+        {
+            constexpr int W = ASM_WARPS_PER_BLOCK;
+            std::vector<int> load(ASM_MAX_COLOURS, 0);
+            for (int c : colour) ++load[c];
+            for (bool moved = true; moved;) {
+                moved = false;
+                std::vector<int> by_rest;
+                for (int c = 0; c < n_colours; ++c) if (load[c] % W) by_rest.push_back(c);
+                std::sort(by_rest.begin(), by_rest.end(), [&](int a, int b) { return load[a] % W < load[b] % W; });
+                for (int c : by_rest) {
+                    // only worth it if the whole rest of the colour finds room
+                    std::vector<std::pair<size_t, int>> plan_moves;
+                    std::vector<int> room(ASM_MAX_COLOURS, 0);
+                    for (int q = 0; q < n_colours; ++q) if (q != c && load[q] % W) room[q] = W - load[q] % W;
+                    int need = load[c] % W;
+                    std::vector<uint32_t> rc = row_colours;        // tentative
+                    for (size_t i = 0; i < eqs.size() && need > 0; ++i) {
+                        if (colour[i] != c) continue;
+                        uint32_t used = 0;
+                        for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) used |= rc[local_row[g]];
+                        used &= ~(1u << c);
+                        int best = -1;
+                        for (int q = 0; q < n_colours; ++q)
+                            if (room[q] > 0 && !(used >> q & 1u) && (best < 0 || room[q] < room[best])) best = q;
+                        if (best < 0) continue;
+                        plan_moves.push_back({i, best});
+                        --room[best];
+                        --need;
+                        for (int g : rows_of_eq[eqs[i]]) if (local_row[g] >= 0) rc[local_row[g]] = (rc[local_row[g]] & ~(1u << c)) | (1u << best);
+                    }
+                    if (need > 0) continue;
+                    for (auto &mv : plan_moves) { colour[mv.first] = mv.second; --load[c]; ++load[mv.second]; }
+                    row_colours.swap(rc);
+                    moved = !plan_moves.empty();
+                    if (moved) break;
+                }
+            }
+            // colours emptied on the way are closed up
+            std::vector<int> remap(ASM_MAX_COLOURS, -1);
+            int nc = 0;
+            for (int c = 0; c < n_colours; ++c) if (load[c] > 0) remap[c] = nc++;
+            for (int &c : colour) c = remap[c];
+            n_colours = nc;
         }
         std::vector<int> order(eqs.size());
         std::iota(order.begin(), order.end(), 0);
