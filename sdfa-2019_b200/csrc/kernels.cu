@@ -383,16 +383,25 @@ __global__ void __launch_bounds__(ASM_G_THREADS) k_assemble_gather(AsmParams P) 
     }
     // consecutive threads copy consecutive (equation, component) values, so that a warp's copy touches the few
     // cache lines of three or four triangles instead of 32; one commit group per frame and thread
+    // The (source, destination) offsets of the thread's copies do not depend on the frame: computed once.
+    constexpr int ASM_GCOPIES = (ASM_MAX_EQ * 9 + ASM_G_THREADS - 1) / ASM_G_THREADS;
+    int g_src[ASM_GCOPIES], g_dst[ASM_GCOPIES];
+#pragma unroll
+    for (int i = 0; i < ASM_GCOPIES; ++i) {
+        const int v = threadIdx.x + i * ASM_G_THREADS;
+        g_src[i] = -1; g_dst[i] = 0;
+        if (v < n_eq * 9) {
+            const int e = v / 9, j = v - 9 * e, sr = src_sh[e];
+            if (sr >= 0) { g_src[i] = sr * 9 + j; g_dst[i] = (j / 3) * plane + e * 3 + (j % 3); }
+        }
+    }
     auto gather = [&](int ft, int si) {
         const float *row = P.dgrad + (long long)(frame0 + ft) * P.frame_stride;
-        float *dst = stage + si * 3 * plane;
-        for (int v = threadIdx.x; v < n_eq * 9; v += ASM_G_THREADS) {
-            const int e = v / 9, j = v - 9 * e;
-            const int sr = src_sh[e];
-            if (sr < 0) continue;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (j / 3) * plane + e * 3 + (j % 3))),
-                         "l"(row + (long long)sr * 9 + j) : "memory");
-        }
+        const uint32_t dst = smem_u32(stage + si * 3 * plane);
+#pragma unroll
+        for (int i = 0; i < ASM_GCOPIES; ++i)
+            if (g_src[i] >= 0)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * g_dst[i]), "l"(row + g_src[i]) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (nvalid > 0) gather(0, 0);
