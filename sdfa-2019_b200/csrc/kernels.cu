@@ -830,6 +830,8 @@ struct OutParams {
     long long tile_stride;
 };
 
+constexpr int OUT_L2_AHEAD = 16;
+
 __global__ void __launch_bounds__(OUT_THREADS) k_output(OutParams P) {
     extern __shared__ float t_sh[];              // [line][FC + 1]
     const int chunk = blockIdx.x, grp = blockIdx.y;
@@ -839,6 +841,15 @@ __global__ void __launch_bounds__(OUT_THREADS) k_output(OutParams P) {
     const int l0 = P.line_ptr[chunk], nl = P.line_ptr[chunk + 1] - l0;
     const int pitch = P.FC + 1;
     const float *src_tile = P.scratch + (long long)(frame0 / P.FR) * P.tile_stride + frame0 % P.FR;
+    {   // pull the lines of the CTA OUT_L2_AHEAD frame groups further on (same chunk: about one wave of CTAs later) into
+        // L2, one 128-byte line per thread: its staging loop then waits for L2 instead of DRAM (1.50 -> 1.44 ms; 6 ... 32
+        // groups ahead measure the same)
+        const int f2 = frame0 + OUT_L2_AHEAD * P.FC;
+        if (f2 < P.n_frames) {
+            const float *t2 = P.scratch + (long long)(f2 / P.FR) * P.tile_stride + f2 % P.FR;
+            for (int i = threadIdx.x; i < nl; i += OUT_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(t2 + P.line_off[l0 + i]));
+        }
+    }
     if (lane < P.FC) {
 #pragma unroll 4
         for (int i = warp; i < nl; i += OUT_THREADS / 32)
