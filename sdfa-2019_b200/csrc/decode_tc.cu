@@ -8,8 +8,10 @@
 //      D[n, m] = sum_k X[n, k] * W[m, k]       n = frame, m = basis row (output value = "slot")
 // i.e. the frames are the MMA M dimension (TMEM lanes) and the basis rows the N dimension (TMEM columns): an
 // epilogue warp owns 32 consecutive frames (lane = frame), holds one output value per register, and every
-// store instruction writes one full 128-byte line of the frame-tiled compact dgrad [tile of 32 frames][slot][32]
-// -- the layout the assembly kernel (lane = frame as well) reads back with coalesced lines.
+// store instruction writes one full 128-byte line of the frame-tiled compact dgrad [tile of 64 frames][slot][64]
+// (its half of the slot's 64 frames) -- the layout the assembly kernel (lane = two frames) reads back with coalesced
+// 256-byte lines.  Two CTAs form a pair (cta_group::2): ONE instruction stream, issued by the pair's leader, drives the
+// tensor cores of both SMs on a 256-frame x 256-row tile, each CTA staging its own 128 frames and half of the basis rows.
 //
 // fp32 accuracy from TF32 tensor cores: both operands are split x = hi + lo with hi = x truncated to
 // TF32 (the 19 bits the tensor core reads) and lo = x - hi (exact), and every K-step issues three MMAs
@@ -17,7 +19,7 @@
 // into the same fp32 accumulator.  The basis is split and pre-tiled once on the host (sdfa_set_pca); the
 // coefficients are split per call by k_split_coeffs.  Tiles are stored in global memory as exact images
 // of the 128-byte-swizzled K-major shared-memory layout the UMMA descriptors expect, so one
-// cp.async.bulk per operand and K-block fills a stage (no tensor maps needed).
+// cp.async.bulk per operand half and K-block fills a ring slot (no tensor maps needed).
 #include "device_plan.hpp"
 
 #include <cstring>
