@@ -277,6 +277,29 @@ def test_config5_subdivided_template():
     assert np.abs(z[0] - V).max() <= 1e-8
 
 
+def test_decode_path_on_other_templates():
+    """The staged path (K1 -> k_assemble -> solve -> output) on templates other than FLAME -- a 63-vertex grid (row
+    blocks with fewer equations than warps, tensor plan of a tiny system) and the subdivided FLAME of config 5 (179 row
+    blocks, SIMT solve) -- against the gather path fed with the same decoded dgrad, which the tests above pin to the
+    reference."""
+    import torch
+    Vg, Fg, border = W.grid_mesh()
+    Vs, Fs, cs_ = W.flame_sub2()
+    for V, F, c in ((Vg, Fg, border), (Vs, Fs, cs_)):
+        tol = 1e-6 * W.bbox_diag(V)
+        r = D.Reconstructor(V, F, cnsts=c, device=0)
+        cs, ms, cr, mr = W.random_pca(len(F), seed=4, k_scale=20, k_rotat=30)
+        r.set_pca(cs, ms, cr, mr)
+        xs, xr = (torch.from_numpy(a).cuda() for a in W.random_coeffs(70, seed=6, k_scale=20, k_rotat=30))
+        out = r.decode_and_get_mesh(xs, xr)
+        ref = r.get_mesh_batch(r.decode_dgrad(xs, xr))
+        assert out.shape == (70, len(V), 3)
+        assert float((out - ref).abs().max()) <= 0.25 * tol, len(V)
+        assert torch.equal(out[:, torch.as_tensor(np.asarray(c), device="cuda").long()],
+                           torch.from_numpy(V[np.asarray(c)]).cuda().expand(70, -1, -1))
+        r.close()
+
+
 def test_tensor_and_simt_solvers_agree(chk, flame):
     """K3T (tcgen05 block products, operands in tensor memory) and K3 (SIMT sweeps) on the same frames, against each
     other and the checker; frame counts around the 128-column tile boundaries of K3T."""
