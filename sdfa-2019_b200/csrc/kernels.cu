@@ -361,12 +361,19 @@ __global__ void __launch_bounds__(ASM_G_THREADS) k_assemble_gather(AsmParams P) 
     float *g_sh0 = sh + 6 * plane;                                  // [2][max_eq][9]: corner vectors, double buffered
     float *t_sh = g_sh0 + 2 * P.max_eq * 9;                         // [rows*3][33]
     int *src_sh = reinterpret_cast<int *>(t_sh + P.max_rows * 3 * ASM_GPAD);   // [max_eq]
+    uint16_t *inc_sh = reinterpret_cast<uint16_t *>(src_sh + P.max_eq);        // [3 * max_eq]: the block's row incidences (CSR payload)
     const int4 blk = P.blocks[blockIdx.x];
     const int n_eq = blk.y - blk.x, n_rows = blk.w - blk.z;
     const int tile = blockIdx.y;
     const int frame0 = tile * ASM_GF;
     const int nvalid = max(0, min(ASM_GF, P.n_frames - frame0));    // 0: a tile past the batch only zero-fills its lanes
     for (int e = threadIdx.x; e < n_eq; e += ASM_G_THREADS) src_sh[e] = P.eq_src_local[blk.x + e];
+    // the CSR of the block's rows does not depend on the frame either: payload to shared memory, the thread's row range
+    // to registers
+    const int inc0 = P.row_ptr[blk.z];
+    for (int q = inc0 + threadIdx.x; q < P.row_ptr[blk.w]; q += ASM_G_THREADS) inc_sh[q - inc0] = P.inc[q];
+    const int my_row = ASM_G_THREADS - 1 - threadIdx.x;       // rows are dealt from the top thread ids down (see below)
+    const int my_q0 = my_row < n_rows ? P.row_ptr[blk.z + my_row] - inc0 : 0, my_q1 = my_row < n_rows ? P.row_ptr[blk.z + my_row + 1] - inc0 : 0;
     __syncthreads();
     int src_k[ASM_KMAX];
     float4 m0_k[ASM_KMAX], m1_k[ASM_KMAX];
@@ -437,12 +444,12 @@ __global__ void __launch_bounds__(ASM_G_THREADS) k_assemble_gather(AsmParams P) 
         if (f >= 1) {
             const float *gp = g_sh0 + ((f - 1) & 1) * P.max_eq * 9;
             // rows are dealt from the top thread ids down: the low threads carry the extra equations above
-            for (int r = ASM_G_THREADS - 1 - threadIdx.x; r < n_rows; r += ASM_G_THREADS) {
-                const int gr = blk.z + r;
-                const int q0 = P.row_ptr[gr], q1 = P.row_ptr[gr + 1];
+            for (int r = my_row; r < n_rows; r += ASM_G_THREADS) {
+                const bool first = r == my_row;
+                const int q0 = first ? my_q0 : P.row_ptr[blk.z + r] - inc0, q1 = first ? my_q1 : P.row_ptr[blk.z + r + 1] - inc0;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;
                 for (int q = q0; q < q1; ++q) {
-                    const float *g = gp + 3 * (int)P.inc[q];
+                    const float *g = gp + 3 * (int)inc_sh[q];
                     s0 += g[0]; s1 += g[1]; s2 += g[2];
                 }
                 float *t = t_sh + (3 * r) * ASM_GPAD + (f - 1);
@@ -472,7 +479,8 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
                 d.asm_max_eq, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.asm_max_walk, d.layout};
     const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
     const size_t smem = staged ? (size_t)d.asm_max_rows * 3 * COMPACT_TILE * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4)
-                               : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * ASM_GPAD + d.asm_max_eq) * sizeof(float);
+                               : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * ASM_GPAD + d.asm_max_eq) * sizeof(float) +
+                                 (((size_t)d.asm_max_eq * 3 * sizeof(uint16_t) + 15) & ~(size_t)15);
     cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
