@@ -470,6 +470,12 @@ static int pipe_chunk(const sdfa_handle *h, int n_frames) {
     const int env = e ? atoi(e) : -1;
     if (h->timing || env == 0) return 0;
     int chunk = env > 0 ? (env + 127) / 128 * 128 : h->dev.sm_count * 128 * 4;
+    if (env <= 0) {
+        // large templates: keep each of the two scratch buffers under 2 GiB (config 5: 248 KB per frame -> 8448 frames)
+        const size_t per_128 = scratch_floats(h->dev, 128) * sizeof(float);
+        const size_t fit = ((size_t)2 << 30) / std::max<size_t>(per_128, 1);
+        if ((size_t)chunk / 128 > fit) chunk = (int)std::max<size_t>(fit, 1) * 128;
+    }
     return n_frames > chunk ? chunk : 0;
 }
 
