@@ -349,7 +349,10 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_BLOCKS) k_assemble(AsmPar
 // gathered with 4-byte cp.async copies two frames ahead into a double-buffered stage, corner vectors into shared
 // memory, then thread = row sums the incident corner vectors (CSR, fixed order, no atomics) into a
 // [row*3+c][33] transpose buffer; one block barrier per frame.
-constexpr int ASM_GF = 16;                      // frames per CTA of the gather variant (smaller tile: more CTAs per SM)
+#ifndef ASM_GF_N
+#define ASM_GF_N 16
+#endif
+constexpr int ASM_GF = ASM_GF_N;                      // frames per CTA of the gather variant (smaller tile: more CTAs per SM)
 constexpr int ASM_GPAD = ASM_GF + 1;
 constexpr int ASM_G_WARPS = 8, ASM_G_THREADS = 32 * ASM_G_WARPS;   // the gather variant keeps 8 warps: thread = equation
 constexpr int ASM_KMAX = ASM_MAX_EQ / ASM_G_THREADS;
