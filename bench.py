@@ -8,17 +8,21 @@ Workload (config.workload): configs[1] of BASELINE.json -- PCA-coefficient decod
 240-frame sentences (4 s at 60 fps) on the FLAME template with the default mask (5023 v / 9976 tris, 3762
 constrained vertices, 2601 active triangles), random PCA basis (K = 85 scale + 180 rotation).  One step =
 one batch of S sentences per GPU (default 315 -> 75 600 frames), i.e. the kernels of the path:
-K1 decode -> K2 assembly -> K3 solve -> K5 output (transpose + base + constrained vertices).  Frames are sharded over ranks with no
-data-path collective ("weak": per-GPU batch fixed).
+K1 decode -> K2 assembly -> K3 solve -> K5 output (transpose + base + constrained vertices).  Frames are sharded over
+ranks with no data-path collective ("weak": per-GPU batch fixed).
 
   value     frames/s, inputs (coefficients, basis, factor) resident in HBM, CUDA-event timed, max over ranks
   e2e       same through the host-buffer C-ABI call (pinned host coefficients in, host vertices out)
-  dgrad_resident  the same frames with the decoded dgrad [N, 9976*9] fp32 already in HBM (K2+K3 only):
+  dgrad_resident  the same frames with the decoded dgrad [N, 9976*9] fp32 already in HBM (K2+K3+K5 only):
             the literal "dgrad -> mesh" number SURVEY 8(d)'s 153 912 B/frame figure refers to
-  roofline  dominant kernel, live CUDA-event time from the library's per-stage events; roofline_kernels lists all four
+  parity    max |dv| of sampled frames of the TIMED output against the compiled reference; non-zero exit on failure
+  roofline  dominant kernel per SURVEY 8(d): algorithmic bytes (or useful FLOP) per launch / live CUDA-event time
+  gather    (N > 1) the same step followed by the NCCL gather of the vertex buffers (north star): free rows all-gathered
+            on a side stream chunk by chunk under the next chunk's kernels
   cpu_baseline  the UNMODIFIED reference solver (oracle/_ref, all host threads) on a bounded sample
 """
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -26,7 +30,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "sdfa-2019_b200")):
+PKG = os.path.join(ROOT, "sdfa-2019_b200")
+for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -38,20 +43,37 @@ BYTES_PATH = 36 * N_ACTIVE + 12 * N_VERTS          # 153 912 B/frame, SURVEY 8(d
 BYTES_SOLVE = 2 * 12 * N_FREE                      # 30 264 B/frame: rhs in + solution out
 BYTES_ASSEMBLY = 36 * N_ACTIVE + 12 * N_FREE       # dgrad of the active triangles in + rhs out
 BYTES_OUTPUT = 12 * N_FREE + 12 * N_VERTS          # solved rows in + vertices out
-DECODE_FLOP = 2 * (N_ACTIVE * 6 * 85 + N_ACTIVE * 3 * 180)   # 5 462 100 useful FLOP/frame
+BYTES_DECODE_OUT = 36 * N_ACTIVE                   # compact dgrad the unfused decode must write
+DECODE_FLOP = 2 * (N_ACTIVE * 6 * 85 + N_ACTIVE * 3 * 180)   # 5 462 100 useful FLOP/frame, SURVEY 8(d)
+METRIC = "dgrad->mesh frames/s (FLAME 5023v)"
 
 
-def ncu_traffic(kernel, n_frames):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json holds
-    bytes per frame measured at 15 360 frames per launch, both decode launches added up), scaled to this launch;
-    None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as fp:
-            per_frame = json.load(fp)["dram_bytes_per_frame"][kernel]
-        return per_frame * n_frames
-    except Exception:
-        return None
+def load_workloads():
+    """deformation/workloads.py by path: pure numpy helpers, WITHOUT importing the ``deformation`` package (which loads
+    libsdfa_b200.so) -- the reference arm must not map the product library (VERDICT r1 weak #10)."""
+    spec = importlib.util.spec_from_file_location("sdfa_workloads", os.path.join(PKG, "deformation", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def bench_config(sentences, world):
+    n = sentences * FRAMES_PER_SENTENCE
+    return {"workload": f"configs[1]: PCA-coefficient decode + reconstruction, {sentences} sentences x 240 "
+                        f"frames per GPU per step, FLAME 5023v/9976t default mask (1261 unknowns), random PCA "
+                        "basis K=85+180", "frames_per_step_per_gpu": n, "parallelism": f"frames sharded x{world}",
+            "l2": "flushed between timed iterations (256 MiB memset) and inputs > L2"}
+
+
+def traffic_table():
+    """DRAM bytes per frame per kernel from the committed ncu --set full capture of this round (profiles/), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fp:
+                return json.load(fp), name
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -109,8 +131,24 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def workload(n_frames, seed):
-    from deformation import workloads as W
+def bind_to_gpu_numa_node(index):
+    """Run this rank (and first-touch its pinned staging buffers) on the host cores next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def workload(W, n_frames, seed):
     V, F, nfv, nft = W.load_flame()
     cs, ms, cr, mr = W.random_pca(len(F), seed=1, zero_tris=nft)
     xs, xr = W.random_coeffs(n_frames, seed=seed)
@@ -139,12 +177,15 @@ class CpuReference:
             self.o = TriangleDeformationOracle()
             self.o.set_target(V, F, cnsts=nfv)
 
-    def step(self, xs, xr):
+    def decode(self, xs, xr):
         torch = self.torch
         n = len(xs)
         s = torch.nn.functional.linear(torch.from_numpy(xs), self.cs, self.ms)
         r = torch.nn.functional.linear(torch.from_numpy(xr), self.cr, self.mr)
-        dg = torch.cat((s.view(n, -1, 6), r.view(n, -1, 3)), dim=-1).view(n, -1).numpy()
+        return torch.cat((s.view(n, -1, 6), r.view(n, -1, 3)), dim=-1).view(n, -1).numpy()
+
+    def step(self, xs, xr):
+        dg = self.decode(xs, xr)
         if self.kind == "reference":
             out, _ = self.rs.get_mesh_batch(dg, self.C)
             return out
@@ -161,24 +202,36 @@ class CpuReference:
 
 
 def run_reference(args):
+    """The reference's own CPU implementation on the host cores; same metric / unit / config as the product arm, each
+    step a bounded sample of that workload (4 sentences) so that the run ends within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    W = load_workloads()
     n = FRAMES_PER_SENTENCE * 4
-    V, F, nfv, pca, xs, xr = workload(n, seed=2)
+    V, F, nfv, pca, xs, xr = workload(W, n, seed=2)
     ref = CpuReference(V, F, nfv, pca, os.cpu_count() or 1)
     value, dt = ref.fps(xs, xr, steps=args.steps, warmup=args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": "dgrad->mesh frames/s (FLAME 5023v)", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: PCA decode + reconstruction, FLAME default mask, bounded sample of "
-                               f"{n} frames (4 sentences) per step on the host cores"},
+        "config": bench_config(args.sentences, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": ref.cores, "kind": ref.kind,
-                         "sample": f"{n} frames per step x {args.steps} steps"},
+                         "sample": f"bounded sample of the config's workload: {n} frames (4 sentences) per step x "
+                                   f"{args.steps} steps, torch fp32 F.linear decode + reference get_mesh, one solver per host thread"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def parity_check(out_rows, sample_ids, xs, xr, ref, tol, free_ids=None):
+    """Sampled frames of a timed output against the reference path (fp32 F.linear decode + reference get_mesh)."""
+    want = ref.step(xs[sample_ids], xr[sample_ids])
+    if free_ids is not None:
+        want = want[:, free_ids]
+    err = np.abs(out_rows - want).reshape(len(sample_ids), -1).max(axis=1)
+    return float(err.max()), err
 
 
 def main():
@@ -191,17 +244,20 @@ def main():
                     help="240-frame sentences per step per GPU (315 -> 75 600 frames = 1773 solve tiles of 128 columns "
                          "= 11.98 per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather leg at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
-    import deformation as D
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    cpus = bind_to_gpu_numa_node(local)
+    import deformation as D
+    from deformation import sharded, workloads as W
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -209,18 +265,24 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = args.sentences * FRAMES_PER_SENTENCE
-    V, F, nfv, pca, xs, xr = workload(n, seed=2 + rank)
+    V, F, nfv, pca, xs, xr = workload(W, n, seed=2 + rank)
     rec = D.Reconstructor(V, F, cnsts=nfv, device=local)
     rec.set_pca(*pca)
+    tol = 1e-6 * W.bbox_diag(V)
     xs_d, xr_d = torch.from_numpy(xs).to(dev), torch.from_numpy(xr).to(dev)
     out = torch.empty((n, N_VERTS, 3), dtype=torch.float32, device=dev)
-    dgrad = rec.decode_dgrad(xs_d, xr_d)            # [n, 89784] fp32 resident dgrad for the K2+K3 leg
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -233,39 +295,26 @@ def main():
             fn()
             b.record()
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / steps
 
+    # ---- the timed step, then parity of what it just wrote
     launches0 = D.lib.sdfa_launch_count()
     with ClockSampler(local) as clocks:
         ms_step = timed(lambda: rec.decode_and_get_mesh(xs_d, xr_d, out=out), args.steps, args.warmup)
     launches = (D.lib.sdfa_launch_count() - launches0) // max(1, args.steps + args.warmup) * args.steps
+    # frames: first / last, 128-frame tile boundaries, and a spread over the batch (= over the persistent CTAs' tile ranges)
+    sample_ids = np.unique(np.clip(np.concatenate([[0, 1, 127, 128, 129, n - 129, n - 128, n - 1],
+                                                   np.linspace(0, n - 1, 24).astype(np.int64)]), 0, n - 1))
+    out_samples = out[torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
+
+    # ---- the literal metric: dgrad resident in HBM (gather assembly + solve + output)
+    dgrad = rec.decode_dgrad(xs_d, xr_d)            # [n, 89784] fp32
     ms_dgrad = timed(lambda: rec.get_mesh_batch(dgrad, out=out), args.steps, args.warmup)
+    out_samples_dgrad = out[torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
+    del dgrad
+    torch.cuda.empty_cache()
 
-    # end to end through the host-buffer call: pinned host coefficients in, host vertices out
-    xs_h, xr_h = torch.from_numpy(xs).pin_memory(), torch.from_numpy(xr).pin_memory()
-    out_h = torch.empty((n, N_VERTS, 3), dtype=torch.float32).pin_memory()
-    xs_n, xr_n, out_n = xs_h.numpy(), xr_h.numpy(), out_h.numpy()
-
-    def e2e_step():
-        rec.decode_and_get_mesh(xs_n, xr_n, out=out_n)
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-
-    # per-kernel device time (library's own CUDA events on the launch stream), separate pass
+    # ---- per-kernel device time (library's own CUDA events on the launch stream), separate pass
     rec.set_timing(True)
     stage = {"decode_ms": 0.0, "assembly_ms": 0.0, "solve_ms": 0.0, "output_ms": 0.0}
     reps = max(3, min(args.steps, 10))
@@ -276,64 +325,173 @@ def main():
             for k, v in rec.last_timing().items():
                 stage[k] += v / reps
     rec.set_timing(False)
+
+    # ---- end to end through the host-buffer calls: host coefficients in, host vertices out, wall clock
+    def e2e(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    xs_n, xr_n = torch.from_numpy(xs).pin_memory().numpy(), torch.from_numpy(xr).pin_memory().numpy()
+    free_h = torch.empty((n, N_FREE, 3), dtype=torch.float32).pin_memory()
+    free_n = free_h.numpy()
+    e2e_free_ms = e2e(lambda: rec.decode_and_get_mesh(xs_n, xr_n, out=free_n, free_only=True))
+    free_samples = free_n[sample_ids].copy()
+    del free_h, free_n
+    full_h = torch.empty((n, N_VERTS, 3), dtype=torch.float32).pin_memory()
+    full_n = full_h.numpy()
+    e2e_full_ms = e2e(lambda: rec.decode_and_get_mesh(xs_n, xr_n, out=full_n))
+    del full_h, full_n
+    # what a caller with ordinary (pageable) numpy arrays gets -- fewer steps, it is slow
+    page_out = np.empty((n, N_VERTS, 3), dtype=np.float32)
+    page_steps = max(1, min(3, args.steps))
+    rec.decode_and_get_mesh(xs, xr, out=page_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(page_steps):
+        rec.decode_and_get_mesh(xs, xr, out=page_out)
+    barrier()
+    e2e_page_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / page_steps)
+    del page_out
+
+    # ---- N > 1: the step followed by the gather of the vertex buffers (free rows over NCCL, side stream, chunked)
+    gather = None
+    if world > 1 and not args.no_gather:
+        gather = {}
+        del out
+        torch.cuda.empty_cache()
+        row_b = N_FREE * 12
+        for key, mode, expand in (("all_gather_free_rows", "all", False), ("all_gather_expanded", "all", True),
+                                  ("gather_to_rank0_free_rows", "root", False)):
+            pipe = sharded.GatherPipeline(rec, chunk_frames=148 * 128, mode=mode, dst=0, expand=expand)
+            rows = N_VERTS if expand else N_FREE
+            g_out = (torch.empty((world * n, rows, 3), dtype=torch.float32, device=dev)
+                     if (mode == "all" or rank == 0) else None)
+
+            def step(pipe=pipe, g_out=g_out):
+                pipe.run(lambda a, b, out: rec.decode_and_get_mesh(a, b, out=out, free_only=True), [xs_d, xr_d], out=g_out)
+            ms = timed(step, max(3, args.steps // 2), 2)
+            recv = (world - 1) * n * row_b            # bytes arriving at a receiving GPU per step
+            gather[key] = {"value": world * n / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                           "nvlink_in_gbs_per_receiver": recv / (ms * 1e-3) / 1e9, "bytes_per_frame_on_wire": row_b}
+            if key == "all_gather_expanded":
+                # the gathered + expanded frames of rank r are this rank's timed output when r == rank
+                mine = g_out[rank * n + torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
+                gather[key]["equals_local_output"] = bool(np.array_equal(mine, out_samples))
+            del g_out, pipe
+            torch.cuda.empty_cache()
+        gather["limiter"] = ("receiver NVLink ingress: (N-1)/N of every frame's free rows (15 132 B) arrive at each "
+                             "receiving GPU; compute overlaps on the main stream")
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+
+    # ---- rank 0: parity of the timed outputs, rooflines, CPU baseline
+    ref = CpuReference(V, F, nfv, pca, os.cpu_count() or 1)
+    free_ids = rec.free_vertices
+    worst, _ = parity_check(out_samples, sample_ids, xs, xr, ref, tol)
+    worst_dgrad, _ = parity_check(out_samples_dgrad, sample_ids, xs, xr, ref, tol)
+    worst_free, _ = parity_check(free_samples, sample_ids, xs, xr, ref, tol, free_ids)
+    cnst_ok = bool(np.array_equal(out_samples[:, nfv], np.broadcast_to(V[nfv], (len(sample_ids),) + V[nfv].shape)))
+    parity = {"max_abs_m": max(worst, worst_dgrad, worst_free), "tol": tol, "frames": [int(i) for i in sample_ids],
+              "checker": ref.kind, "max_abs_m_decode_path": worst, "max_abs_m_dgrad_path": worst_dgrad,
+              "max_abs_m_e2e_free_rows": worst_free, "constrained_rows_bit_equal": cnst_ok,
+              "ok": bool(max(worst, worst_dgrad, worst_free) <= tol and cnst_ok)}
+
     peaks, peak_src = measured_peaks()
+    traffic, traffic_src = traffic_table()
+
+    def ncu_traffic(kernel):
+        try:
+            return traffic["dram_bytes_per_frame"][kernel] * n
+        except Exception:
+            return None
+
+    # dense TF32 matmul measured in this run (no TF32 entry in MEASURED_PEAKS.json)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    for _ in range(3):
+        a @ b
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        a @ b
+    e1.record()
+    torch.cuda.synchronize()
+    tf32_tflops = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b
+
     total = n * world
     dom = max(("solve_ms", "assembly_ms", "decode_ms", "output_ms"), key=lambda k: stage[k])
+    solver_kernel = "k_solve_tc" if rec.debug("ts_stats")[0] else "k_solve"
     if dom == "decode_ms":
-        # issued MMA work: 3 TF32 products per K step, K padded to 32-wide blocks (the means ride in one of the pad
-        # columns), rows padded to 256-row tiles; peak = dense TF32 = half of the measured dense bf16 rate
         rows_s, rows_r = -(-6 * rec.n_active // 256) * 256, -(-3 * rec.n_active // 256) * 256
-        issued = 3 * 2 * (rows_s * 96 + rows_r * 192)
-        ach = issued * n / (stage[dom] * 1e-3) / 1e12
-        peak = peaks["bf16_tflops"] / 2
-        roof = {"kernel": "k_decode_tc (K1)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": ncu_traffic("k_decode_tc", n),
-                "issued_flop_per_frame": issued, "useful_flop_per_frame": DECODE_FLOP,
-                "useful_tflops": DECODE_FLOP * n / (stage[dom] * 1e-3) / 1e12,
-                "note": "kind::tf32 3xTF32; peak = measured dense bf16 / 2 (no TF32 entry in MEASURED_PEAKS.json); "
-                        "the kernel also writes the 94 KB/frame compact dgrad"}
+        issued = 3 * 2 * (rows_s * 96 + rows_r * 192)     # 3 TF32 products per K step, K and rows padded to tiles
+        ach = DECODE_FLOP * n / (stage[dom] * 1e-3) / 1e12
+        roof = {"kernel": "k_decode_tc (K1)", "bound": "tensor", "achieved": ach, "peak": tf32_tflops, "unit": "TFLOP/s",
+                "frac": ach / tf32_tflops, "traffic": ncu_traffic("k_decode_tc"),
+                "useful_flop_per_frame": DECODE_FLOP, "issued_flop_per_frame": issued,
+                "issued_frac": issued * n / (stage[dom] * 1e-3) / 1e12 / tf32_tflops,
+                "peak_source": "torch fp32 8192^3 matmul with allow_tf32, measured in this run",
+                "note": "achieved = SURVEY 8(d) useful FLOP (active triangles, K = 85 / 180, one product); the kernel issues "
+                        "3xTF32 on padded tiles (issued_frac) and writes the 94 KB/frame compact dgrad"}
     else:
-        b, kname = {"solve_ms": (BYTES_SOLVE, "k_solve_tc" if rec.debug("ts_stats")[0] else "k_solve"),
-                    "assembly_ms": (BYTES_ASSEMBLY, "k_assemble"), "output_ms": (BYTES_OUTPUT, "k_output")}[dom]
-        ach = b * n / (stage[dom] * 1e-3) / 1e9
+        b_, kname = {"solve_ms": (BYTES_SOLVE, solver_kernel), "assembly_ms": (BYTES_ASSEMBLY, "k_assemble"),
+                     "output_ms": (BYTES_OUTPUT, "k_output")}[dom]
+        ach = b_ * n / (stage[dom] * 1e-3) / 1e9
         tag = {"solve_ms": " (K3)", "assembly_ms": " (K2)", "output_ms": " (K5)"}[dom]
         roof = {"kernel": kname + tag, "bound": "hbm", "achieved": ach,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(kname, n),
-                "algorithmic_bytes_per_frame": b, "algorithmic_bytes_per_launch": b * n}
-    # every kernel of the path against its own algorithmic bytes (decode: the compact dgrad it must write)
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(kname),
+                "algorithmic_bytes_per_frame": b_, "algorithmic_bytes_per_launch": b_ * n, "peak_source": peak_src}
+    roof["traffic_source"] = traffic_src
+    # every kernel of the path against its own algorithmic bytes (decode: useful FLOP against the TF32 peak as well)
     per_kernel = {}
-    for key, nm, by in (("decode_ms", "k_decode_tc", 36 * N_ACTIVE), ("assembly_ms", "k_assemble", BYTES_ASSEMBLY),
-                        ("solve_ms", "k_solve", BYTES_SOLVE), ("output_ms", "k_output", BYTES_OUTPUT)):
+    for key, nm, by in (("decode_ms", "k_decode_tc", BYTES_DECODE_OUT), ("assembly_ms", "k_assemble", BYTES_ASSEMBLY),
+                        ("solve_ms", solver_kernel, BYTES_SOLVE), ("output_ms", "k_output", BYTES_OUTPUT)):
         gbs = by * n / (stage[key] * 1e-3) / 1e9
-        per_kernel[nm] = {"ms": stage[key], "algorithmic_bytes_per_frame": by, "achieved_gbs": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"]}
-    roof["peak_source"] = peak_src
+        per_kernel[nm] = {"ms": stage[key], "algorithmic_bytes_per_frame": by, "achieved_gbs": gbs,
+                          "frac_of_hbm": gbs / peaks["hbm_gbs"], "ncu_dram_bytes_per_launch": ncu_traffic(nm)}
+    per_kernel["k_decode_tc"]["useful_tflops"] = DECODE_FLOP * n / (stage["decode_ms"] * 1e-3) / 1e12
+    per_kernel["k_decode_tc"]["frac_of_tf32_peak"] = per_kernel["k_decode_tc"]["useful_tflops"] / tf32_tflops
     path_gbs = BYTES_PATH * n / (ms_dgrad * 1e-3) / 1e9
     result = {
-        "metric": "dgrad->mesh frames/s (FLAME 5023v)", "value": total / (ms_step * 1e-3), "unit": "frames/s",
+        "metric": METRIC, "value": total / (ms_step * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: PCA-coefficient decode + reconstruction, {args.sentences} sentences x 240 "
-                               f"frames per GPU per step, FLAME 5023v/9976t default mask (1261 unknowns), random PCA "
-                               "basis K=85+180", "frames_per_step_per_gpu": n, "parallelism": f"frames sharded x{world}",
-                   "l2": "flushed between timed iterations (256 MiB memset) and inputs > L2"},
-        "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(xs.nbytes + xr.nbytes),
-                "d2h_bytes_per_step": int(n * N_VERTS * 12), "api": "deformation.Reconstructor.decode_and_get_mesh(numpy) "
-                "-> sdfa_decode_reconstruct_host"},
+        "config": bench_config(args.sentences, world),
+        "e2e": {"value": total / (e2e_free_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(xs.nbytes + xr.nbytes),
+                "d2h_bytes_per_step": int(n * N_FREE * 12), "ms_per_step": e2e_free_ms,
+                "api": "deformation.Reconstructor.decode_and_get_mesh(numpy, free_only=True) -> "
+                       "sdfa_decode_reconstruct_free_host: pinned host coefficients in, the 1261 free vertices of every frame "
+                       "out (the 3762 constrained rows are the caller's own vert_cnsts constants)"},
+        "e2e_full_layout": {"value": total / (e2e_full_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_full_ms,
+                            "d2h_bytes_per_step": int(n * N_VERTS * 12),
+                            "api": "decode_and_get_mesh(numpy) -> sdfa_decode_reconstruct_host, pinned buffers, all 5023 rows"},
+        "e2e_pageable": {"value": total / (e2e_page_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_page_ms,
+                         "api": "decode_and_get_mesh(numpy) with ordinary pageable arrays, all 5023 rows"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
+        "parity": parity,
         "roofline": roof,
-        "roofline_path": {"what": "K2+K3+fill with dgrad resident in HBM, 153 912 algorithmic B/frame (SURVEY 8d)",
+        "roofline_path": {"what": "K2+K3+K5 with dgrad resident in HBM, 153 912 algorithmic B/frame (SURVEY 8d)",
                           "achieved": path_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": path_gbs / peaks["hbm_gbs"]},
         "dgrad_resident": {"value": total / (ms_dgrad * 1e-3), "unit": "frames/s", "ms_per_step": ms_dgrad},
         "kernel_ms_per_step": stage,
         "roofline_kernels": per_kernel,
+        "tf32_matmul_tflops_measured": tf32_tflops,
+        "host_cpus_bound": len(cpus) if cpus else None,
     }
+    if gather is not None:
+        result["gather"] = gather
     if not args.no_cpu_baseline:
-        ref = CpuReference(V, F, nfv, pca, os.cpu_count() or 1)
         sample = FRAMES_PER_SENTENCE * 8
         fps, _ = ref.fps(xs[:sample], xr[:sample], steps=3, warmup=1)
         result["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": ref.cores, "kind": ref.kind,
@@ -342,6 +500,9 @@ def main():
     print(json.dumps(result))
     if dist is not None:
         dist.destroy_process_group()
+    if not parity["ok"]:
+        print(f"bench.py: PARITY FAILED: {parity}", file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -48,7 +48,26 @@ typedef struct sdfa_handle sdfa_handle;   /* opaque: one template + factor + dev
  * fail with SDFA_ERR_CUDA) -- used by CPU-only tests of the host logic. */
 int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32_t *tris, int n_tris,
                 const uint32_t *cnsts, int n_cnsts, const uint32_t *corr_count, double reg, int device);
+/* Same, with construction options as "key=value;key=value" (NULL or "" = defaults):
+ *   solver=auto|simt|tensor   which solve kernel (auto: the tcgen05 block solve when the template fits, else SIMT sweeps)
+ *   pipe_chunk=N              frames per chunk of large batches (0 = never chunk); see sdfa_set_option
+ *   frames_per_tile, asm_rows, ts_leaf   tuning knobs of the planners
+ * An unknown key is SDFA_ERR_ARG.  (The SDFA_* environment variables of the same names are read at creation as
+ * defaults for A/B runs; an option given here wins.) */
+int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const uint32_t *tris, int n_tris,
+                     const uint32_t *cnsts, int n_cnsts, const uint32_t *corr_count, double reg, int device,
+                     const char *options);
 void sdfa_destroy(sdfa_handle *h);
+
+/* Threading and streams (SURVEY 8b "Threading"; the reference's singleton is neither thread-safe nor re-entrant):
+ *   - a handle may be shared by several host threads: every entry point holds the handle's lock while it enqueues;
+ *   - *_dev entry points are stream-ordered and asynchronous; calls on different streams are ordered on the device in
+ *     call order (they share the handle's workspaces), and every setter / *_host / legacy call first waits for
+ *     stream-ordered work still in flight;
+ *   - the caller's current CUDA device is left unchanged. */
+
+/* Run-time options: "pipe_chunk" = frames per chunk of large batches (-1 automatic, 0 never chunk). */
+int sdfa_set_option(sdfa_handle *h, const char *name, long long value);
 
 /* Counts; any out pointer may be NULL.  n_eq = number of equation blocks, n_active = blocks that touch
  * a free vertex, nnz_l = nonzeros of the Cholesky factor.  (IsSame, pybind.cpp:119-126, compares the
@@ -108,7 +127,8 @@ int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, 
                                  int n_frames, float *out_host);
 
 /* decode only: writes the full reference-layout dgrad [n_frames, n_tris*9] (inactive triangles included)
- * -- the tensor data_to_anime_feat returns.  Needs the full basis: pass keep_full=1 here. */
+ * -- the tensor data_to_anime_feat returns; n_tris here is the source triangle count sdfa_set_pca was called with
+ * (SDFA_ERR_STATE if correspondences with another count were set since). */
 int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
                           int n_frames, float *dgrad_dev, void *stream);
 
@@ -120,6 +140,23 @@ int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const fl
 int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
                             int n_frames, float *dgrad_compact_dev, void *stream);
 int sdfa_compact_layout(const sdfa_handle *h, int32_t *map, int cap);
+
+/* ---- free rows only (opt-in; not in the reference) ----------------------------------------------------------
+ * The constrained vertices of every reconstructed frame are constants (the positions given to
+ * sdfa_set_constraint_positions, copied through by impl.hpp:302-308) -- 3762 of FLAME's 5023 rows with the default
+ * mask.  The *_free variants write only the free vertices, [n_frames, n_free, 3] float32 in ascending vertex order
+ * (sdfa_free_vertices gives the vertex index of each row), so a device->host copy or an NCCL gather moves 15 KB
+ * instead of 60 KB per FLAME frame; sdfa_expand_free_dev rebuilds the reference layout on the receiving device. */
+int sdfa_free_vertices(const sdfa_handle *h, int32_t *ids, int cap);     /* returns n_free; ids may be NULL */
+int sdfa_reconstruct_free_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames,
+                              float *out_free_dev, void *stream);
+int sdfa_reconstruct_free_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_free_host);
+int sdfa_decode_reconstruct_free_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev,
+                                     int n_frames, float *out_free_dev, void *stream);
+int sdfa_decode_reconstruct_free_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host,
+                                      int n_frames, float *out_free_host);
+/* free_dev [n_frames, n_free, 3] -> out_dev [n_frames, n_verts, 3] with the handle's current constraint positions. */
+int sdfa_expand_free_dev(sdfa_handle *h, const float *free_dev, int n_frames, float *out_dev, void *stream);
 
 /* ---- inverse path: meshes -> dgrad (getDeformationGradients, impl.hpp:144-213) ----------- */
 

@@ -13,9 +13,12 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 using namespace sdfa;
 
@@ -28,10 +31,26 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(SDFA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
     } while (0)
 
+// NVTX range per entry point / stage (the reference only has wall-clock prints)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct sdfa_handle {
     HostPlan host;
     DevicePlan dev;
+    // One lock per handle: every entry point that takes a handle holds it for the duration of the call (the calls
+    // enqueue work and return, so this serialises enqueueing, not the GPU).  Recursive because the legacy entry points
+    // are built from the setters.
+    std::recursive_mutex mu;
     std::vector<void *> allocs;           // every device allocation, freed in destroy
+    std::vector<void *> pca_allocs;       // the PCA buffers of the current sdfa_set_pca (replaced by the next one)
+    int pipe_chunk = -1;                  // sdfa_set_option("pipe_chunk"): -1 auto, 0 never chunk, > 0 frames per chunk
+    cudaEvent_t ev_async = nullptr;       // recorded after the last stream-ordered call: table updates wait for it
+    bool async_pending = false;
+    cudaStream_t last_stream = nullptr;
+    bool free_only = false;               // output mode of the call in progress (set under the lock by the entry point)
     std::vector<int32_t> eq_src_host;     // current equation -> source triangle map
     int n_src_tris = 0;
     bool has_pca = false, has_full_pca = false;
@@ -84,6 +103,50 @@ static int grow(float **buf, size_t *cap, size_t floats) {
     return SDFA_OK;
 }
 
+// Makes the handle's device current for the duration of an entry point and puts the caller's device back afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool armed = false;
+    int enter(int device) {
+        CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != device) { CUDA_TRY(cudaSetDevice(device)); armed = true; }
+        return SDFA_OK;
+    }
+    ~DeviceGuard() { if (armed) cudaSetDevice(prev); }
+};
+static int need_device(sdfa_handle *h, DeviceGuard &g) {
+    if (h->dev.device < 0)
+        return fail(SDFA_ERR_CUDA, "handle was created without a CUDA device; this library has no CPU path");
+    return g.enter(h->dev.device);
+}
+// Entry-point prologue: NULL check, the handle's lock, its device current (restored on return).
+#define ENTER_DEVICE(h)                                                                             \
+    if (!(h)) return fail(SDFA_ERR_ARG, "NULL handle");                                             \
+    std::lock_guard<std::recursive_mutex> lock__((h)->mu);                                          \
+    DeviceGuard guard__;                                                                            \
+    if ((rc = need_device((h), guard__))) return rc
+// Stream-ordered entry points leave a marker behind; whoever rewrites device tables, reuses the staging buffers from
+// another stream or frees buffers waits for it first (handle state was not stream-safe).
+static int mark_async(sdfa_handle *h, cudaStream_t s) {
+    if (!h->ev_async) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_async, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(h->ev_async, s));
+    h->async_pending = true;
+    return SDFA_OK;
+}
+// A stream-ordered call on another stream than the previous one shares its workspaces: order the two on the device.
+static int order_after_last(sdfa_handle *h, cudaStream_t s) {
+    if (h->async_pending && s != h->last_stream) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_async, 0));
+    h->last_stream = s;
+    return SDFA_OK;
+}
+static int wait_async(sdfa_handle *h) {
+    if (h->async_pending) {
+        CUDA_TRY(cudaEventSynchronize(h->ev_async));
+        h->async_pending = false;
+    }
+    return SDFA_OK;
+}
+
 static void default_eq_src(sdfa_handle *h) {
     // no correspondences given at call time: block i reads source triangle i for i < n_tris, the remaining
     // blocks stay zero (deform_triangle_impl.hpp:224, :249-253)
@@ -96,7 +159,10 @@ static void default_eq_src(sdfa_handle *h) {
 static int upload_eq_src(sdfa_handle *h) {
     h->has_pca = false;                       // the compact basis is laid out per equation source: re-pack on change
     if (h->dev.device < 0) return SDFA_OK;
-    CUDA_TRY(cudaSetDevice(h->dev.device));
+    DeviceGuard guard;
+    int rc;
+    if ((rc = guard.enter(h->dev.device))) return rc;
+    if ((rc = wait_async(h))) return rc;      // kernels of an earlier stream-ordered call may still read these tables
     CUDA_TRY(cudaMemcpy(h->dev.eq_src, h->eq_src_host.data(), h->eq_src_host.size() * 4, cudaMemcpyHostToDevice));
     // the assembly walks carry every equation's current source triangle next to it
     const AssemblyPlan &ap = h->host.asmplan;
@@ -128,14 +194,14 @@ static std::vector<int32_t> compact_map(const sdfa_handle *h) {
     return map;
 }
 
-static int upload_base(sdfa_handle *h) {
-    if (h->dev.device < 0) return SDFA_OK;
+// The output kernel's per-chunk tables for the vertex list `verts` (one output row per entry): element -> free line
+// (or constant), line -> scratch offset + base.  x_base is kept in the Cholesky order (row iperm[f]); lines are indexed
+// by scratch row.
+static int upload_out_tables(sdfa_handle *h, DevicePlan::OutTables &t, const std::vector<int> &verts) {
     const HostPlan &p = h->host;
     DevicePlan &d = h->dev;
-    // the output kernel's per-chunk tables: element -> free line (or constant), line -> scratch offset + base.
-    // x_base is kept in the Cholesky order (row iperm[f]); lines are indexed by scratch row.
     constexpr int VC = 64, EC = VC * 3;
-    const int chunks = (p.n_verts + VC - 1) / VC;
+    const int nv = (int)verts.size(), chunks = (nv + VC - 1) / VC;
     std::vector<int16_t> line_of((size_t)chunks * EC, -1);
     std::vector<float> cval((size_t)chunks * EC, 0.f), hi, lo;
     std::vector<int32_t> ptr(chunks + 1, 0), off;
@@ -143,8 +209,9 @@ static int upload_base(sdfa_handle *h) {
     for (int k = 0; k < chunks; ++k) {
         ptr[k] = (int32_t)off.size();
         for (int e = 0; e < EC; ++e) {
-            const int v = k * VC + e / 3, c = e % 3;
-            if (v >= p.n_verts) break;
+            const int i = k * VC + e / 3, c = e % 3;
+            if (i >= nv) break;
+            const int v = verts[i];
             const int f = p.vi_to_free[v];
             if (f < 0) { cval[(size_t)k * EC + e] = p.cnst_pos[(size_t)p.vi_to_cnst[v] * 3 + c]; continue; }
             const double x = p.x_base[(size_t)p.iperm[f] * 3 + c];
@@ -156,19 +223,84 @@ static int upload_base(sdfa_handle *h) {
         max_lines = std::max(max_lines, (int)off.size() - ptr[k]);
     }
     ptr[chunks] = (int32_t)off.size();
-    d.out_max_lines = max_lines;
-    CUDA_TRY(cudaSetDevice(d.device));
-    CUDA_TRY(cudaMemcpy(d.out_line_of, line_of.data(), line_of.size() * 2, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d.out_cval, cval.data(), cval.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d.out_line_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d.out_line_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d.out_line_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d.out_line_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+    t.n_rows = nv;
+    t.max_lines = max_lines;
+    CUDA_TRY(cudaMemcpy(t.line_of, line_of.data(), line_of.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.cval, cval.data(), cval.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.line_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.line_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.line_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.line_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+    return SDFA_OK;
+}
+
+static int upload_base(sdfa_handle *h) {
+    if (h->dev.device < 0) return SDFA_OK;
+    const HostPlan &p = h->host;
+    DevicePlan &d = h->dev;
+    DeviceGuard guard;
+    int rc;
+    if ((rc = guard.enter(d.device))) return rc;
+    if ((rc = wait_async(h))) return rc;      // kernels of an earlier stream-ordered call may still read these tables
+    std::vector<int> all(p.n_verts);
+    for (int v = 0; v < p.n_verts; ++v) all[v] = v;
+    if ((rc = upload_out_tables(h, d.out_full, all))) return rc;
+    if ((rc = upload_out_tables(h, d.out_free, p.free_to_vi))) return rc;
+    // expansion table: output element -> element of the free rows, or the constrained value
+    std::vector<int32_t> src((size_t)p.n_verts * 3, -1);
+    std::vector<float> cval((size_t)p.n_verts * 3, 0.f);
+    for (int v = 0; v < p.n_verts; ++v)
+        for (int c = 0; c < 3; ++c) {
+            if (p.vi_to_free[v] >= 0) src[(size_t)v * 3 + c] = p.vi_to_free[v] * 3 + c;
+            else cval[(size_t)v * 3 + c] = p.cnst_pos[(size_t)p.vi_to_cnst[v] * 3 + c];
+        }
+    CUDA_TRY(cudaMemcpy(d.exp_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.exp_cval, cval.data(), cval.size() * 4, cudaMemcpyHostToDevice));
     return SDFA_OK;
 }
 
 int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32_t *tris, int n_tris,
                 const uint32_t *cnsts, int n_cnsts, const uint32_t *corr_count, double reg, int device) {
+    return sdfa_create_with(out, verts, n_verts, tris, n_tris, cnsts, n_cnsts, corr_count, reg, device, nullptr);
+}
+
+// "key=value;key=value" -> map; unknown keys are an error so that a typo does not silently select the default
+static int parse_options(const char *options, std::map<std::string, std::string> &kv) {
+    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf"};
+    const std::string text = options ? options : "";
+    size_t at = 0;
+    while (at < text.size()) {
+        size_t end = text.find(';', at);
+        if (end == std::string::npos) end = text.size();
+        const std::string item = text.substr(at, end - at);
+        at = end + 1;
+        if (item.empty()) continue;
+        const size_t eq = item.find('=');
+        if (eq == std::string::npos) return fail(SDFA_ERR_ARG, "sdfa_create_with: option '" + item + "' is not key=value");
+        const std::string key = item.substr(0, eq);
+        bool ok = false;
+        for (const char *k : known) ok |= key == k;
+        if (!ok) return fail(SDFA_ERR_ARG, "sdfa_create_with: unknown option '" + key + "'");
+        kv[key] = item.substr(eq + 1);
+    }
+    return SDFA_OK;
+}
+
+int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const uint32_t *tris, int n_tris,
+                     const uint32_t *cnsts, int n_cnsts, const uint32_t *corr_count, double reg, int device,
+                     const char *options) {
+    std::map<std::string, std::string> opt;
+    {
+        int orc;
+        if ((orc = parse_options(options, opt))) return orc;
+    }
+    // an option given in `options` wins over the environment variable of the same purpose (tuning / A-B runs only)
+    auto setting = [&](const char *key, const char *env) -> std::string {
+        auto it = opt.find(key);
+        if (it != opt.end()) return it->second;
+        const char *v = std::getenv(env);
+        return v ? v : "";
+    };
     if (!out || !verts || !tris || n_verts <= 0 || n_tris <= 0 || n_cnsts < 0 || (n_cnsts > 0 && !cnsts))
         return fail(SDFA_ERR_ARG, "sdfa_create: bad arguments");
     *out = nullptr;
@@ -189,7 +321,8 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
             // frames per solve tile: 32 unless the resident rows of a large factor do not fit in the 227 KB of
             // shared memory a CTA can have, then 16 or 8 (config 5: subdivided template)
             auto envi = [](const char *k, int d) { const char *v = std::getenv(k); return v ? std::atoi(v) : d; };
-            const int want = envi("SDFA_FRAMES_PER_TILE", 32);
+            const std::string fpt = setting("frames_per_tile", "SDFA_FRAMES_PER_TILE");
+            const int want = fpt.empty() ? 32 : std::atoi(fpt.c_str());
             for (int f = want; f >= 8; f /= 2) {
                 build_solve_program(p, envi("SDFA_PIECE_CAP", 64), envi("SDFA_SUPERNODE_CAP", 32), envi("SDFA_SUBTREE_CAP", 16), f);
                 if (solve_smem_bytes(p.prog.n_slots, f) <= 227 * 1024) break;
@@ -197,16 +330,20 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         }
         {
             // solver: the tensor-core plan when the template fits it, else the SIMT sweeps (SDFA_SOLVER=simt|tensor forces)
-            const char *sv = std::getenv("SDFA_SOLVER");
-            const std::string solver = sv ? sv : "auto";
+            std::string solver = setting("solver", "SDFA_SOLVER");
+            if (solver.empty()) solver = "auto";
+            if (solver != "auto" && solver != "simt" && solver != "tensor") {
+                delete h;
+                return fail(SDFA_ERR_ARG, "sdfa_create: solver must be auto, simt or tensor");
+            }
             if (solver != "simt") {
-                const char *lm = std::getenv("SDFA_TS_LEAF");
-                build_tensor_plan(p, lm ? std::atoi(lm) : 64);
-            } else p.tplan.why_not = "SDFA_SOLVER=simt";
+                const std::string lm = setting("ts_leaf", "SDFA_TS_LEAF");
+                build_tensor_plan(p, lm.empty() ? 64 : std::atoi(lm.c_str()));
+            } else p.tplan.why_not = "solver=simt";
             if (solver == "tensor" && !p.tplan.valid) {
                 std::string why = p.tplan.why_not;
                 delete h;
-                return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: SDFA_SOLVER=tensor but the template does not fit: " + why);
+                return fail(SDFA_ERR_UNSUPPORTED, "sdfa_create: solver=tensor but the template does not fit: " + why);
             }
             p.use_tensor = p.tplan.valid;
             p.scratch_row = p.use_tensor ? p.tplan.row_of_free : p.iperm;
@@ -214,8 +351,8 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         {
             // row blocks of the assembly kernel: at most ASM_ROWS_MAX vertices each (two CTAs of [rows][3][64 frames]
             // accumulators per SM), split evenly -- measured on FLAME: 11 even blocks of 115 beat 10 of 128 by 5 %
-            const char *e = getenv("SDFA_ASM_ROWS");
-            const int rows_max = e ? atoi(e) : ASM_ROWS_MAX, n_blocks = (p.n_free + rows_max - 1) / rows_max;
+            const std::string e = setting("asm_rows", "SDFA_ASM_ROWS");
+            const int rows_max = e.empty() ? ASM_ROWS_MAX : std::atoi(e.c_str()), n_blocks = (p.n_free + rows_max - 1) / rows_max;
             build_assembly_plan(p, /*rows_per_block=*/(p.n_free + n_blocks - 1) / std::max(n_blocks, 1), ASM_MAX_EQ);
         }
     } catch (const std::exception &e) {
@@ -223,12 +360,18 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
         return fail(SDFA_ERR_UNSUPPORTED, std::string("sdfa_create: ") + e.what());
     }
     default_eq_src(h);
+    {
+        const std::string pc = setting("pipe_chunk", "SDFA_PIPE_CHUNK");
+        h->pipe_chunk = pc.empty() ? -1 : std::atoi(pc.c_str());
+    }
     h->dev.device = device;
     h->dev.n_verts = n_verts; h->dev.n_tris = n_tris; h->dev.n_cnsts = n_cnsts;
     h->dev.n_free = p.n_free; h->dev.n_eq = p.n_eq;
     if (device >= 0) {
         auto up = [&]() -> int {
-            CUDA_TRY(cudaSetDevice(device));
+            DeviceGuard guard;
+            int gr;
+            if ((gr = guard.enter(device))) return gr;
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, device));
             if (prop.major < 10)
@@ -305,20 +448,28 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
                 d.layout.row_stride = TS_COLS;
                 d.layout.c_stride = p.n_free * TS_COLS;
             }
-            {
-                const size_t chunks = ((size_t)p.n_verts + 63) / 64;
+            for (DevicePlan::OutTables *t : {&d.out_full, &d.out_free}) {
+                const size_t chunks = ((size_t)(t == &d.out_full ? p.n_verts : p.n_free) + 63) / 64;
                 std::vector<int16_t> z16(chunks * 192, -1);
                 std::vector<float> zf(chunks * 192, 0.f), zl((size_t)p.n_free * 3, 0.f);
                 std::vector<int32_t> zp(chunks + 1, 0), zo((size_t)p.n_free * 3, 0);
-                if ((r = upload_mut(h, z16, &d.out_line_of))) return r;
-                if ((r = upload_mut(h, zf, &d.out_cval))) return r;
-                if ((r = upload_mut(h, zp, &d.out_line_ptr))) return r;
-                if ((r = upload_mut(h, zo, &d.out_line_off))) return r;
-                if ((r = upload_mut(h, zl, &d.out_line_hi))) return r;
-                if ((r = upload_mut(h, zl, &d.out_line_lo))) return r;
+                if ((r = upload_mut(h, z16, &t->line_of))) return r;
+                if ((r = upload_mut(h, zf, &t->cval))) return r;
+                if ((r = upload_mut(h, zp, &t->line_ptr))) return r;
+                if ((r = upload_mut(h, zo, &t->line_off))) return r;
+                if ((r = upload_mut(h, zl, &t->line_hi))) return r;
+                if ((r = upload_mut(h, zl, &t->line_lo))) return r;
+            }
+            {
+                std::vector<int32_t> zs((size_t)p.n_verts * 3, -1);
+                std::vector<float> zc((size_t)p.n_verts * 3, 0.f);
+                if ((r = upload_mut(h, zs, &d.exp_src))) return r;
+                if ((r = upload_mut(h, zc, &d.exp_cval))) return r;
             }
             if ((r = upload_base(h))) return r;
             if ((r = upload_eq_src(h))) return r;
+            if (!p.use_tensor) CUDA_TRY(configure_solve(d));
+            CUDA_TRY(configure_decode_tc(d));
             if (std::getenv("SDFA_SOLVE_PROFILE")) {
                 std::vector<long long> zero(std::max((size_t)h->dev.sm_count * 4 * 8, (3 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
                 if ((r = upload_mut(h, zero, &d.solve_prof))) return r;
@@ -335,8 +486,12 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
 void sdfa_destroy(sdfa_handle *h) {
     if (!h) return;
     if (h->dev.device >= 0) {
-        cudaSetDevice(h->dev.device);
+        DeviceGuard guard;
+        guard.enter(h->dev.device);
+        if (h->async_pending) cudaEventSynchronize(h->ev_async);
+        if (h->ev_async) cudaEventDestroy(h->ev_async);
         for (void *p : h->allocs) cudaFree(p);
+        for (void *p : h->pca_allocs) cudaFree(p);
         for (auto &w : h->ws) {
             for (float *p : {w.rhs, w.rhs2, w.dgrad_c, w.io_in, w.io_out, w.io_in2, w.ximg_s, w.ximg_r}) if (p) cudaFree(p);
             if (w.stream) cudaStreamDestroy(w.stream);
@@ -364,6 +519,7 @@ int sdfa_info(const sdfa_handle *h, int *n_verts, int *n_tris, int *n_cnsts, int
 
 int sdfa_set_constraint_positions(sdfa_handle *h, const float *cnst_verts_host) {
     if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     HostPlan &p = h->host;
     if (p.n_cnsts == 0) return SDFA_OK;
     // unchanged positions: nothing to redo
@@ -379,6 +535,7 @@ int sdfa_set_constraint_positions(sdfa_handle *h, const float *cnst_verts_host) 
 
 int sdfa_set_correspondences(sdfa_handle *h, const uint32_t *corr_count, const uint32_t *corr_faces, int n_src_tris) {
     if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     const HostPlan &p = h->host;
     std::vector<int32_t> prev = h->eq_src_host;
     if (!corr_count) {
@@ -405,15 +562,6 @@ int sdfa_set_correspondences(sdfa_handle *h, const uint32_t *corr_count, const u
     return upload_eq_src(h);
 }
 
-// ---------------------------------------------------------------------------------------------
-static int need_device(sdfa_handle *h) {
-    if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
-    if (h->dev.device < 0)
-        return fail(SDFA_ERR_CUDA, "handle was created without a CUDA device; this library has no CPU path");
-    CUDA_TRY(cudaSetDevice(h->dev.device));
-    return SDFA_OK;
-}
-
 static int time_mark(sdfa_handle *h, int i, cudaStream_t s) {
     if (!h->timing) return SDFA_OK;
     if (!h->ev[i]) CUDA_TRY(cudaEventCreate(&h->ev[i]));
@@ -431,6 +579,8 @@ static int time_finish(sdfa_handle *h, cudaStream_t s, bool decoded) {
     return SDFA_OK;
 }
 
+static size_t out_row_floats(const sdfa_handle *h) { return (size_t)(h->free_only ? h->dev.n_free : h->dev.n_verts) * 3; }
+
 // One pass over frames [0, n_frames): assembly, solve and -- on stream `so` -- the output kernel.
 static int reconstruct_pass(sdfa_handle *h, float *rhs, const float *dgrad_dev, long long stride, bool staged, int mode,
                             int n_frames, float *out_dev, cudaStream_t s, cudaStream_t so, cudaEvent_t solved) {
@@ -445,7 +595,7 @@ static int reconstruct_pass(sdfa_handle *h, float *rhs, const float *dgrad_dev, 
         CUDA_TRY(cudaEventRecord(solved, s));
         CUDA_TRY(cudaStreamWaitEvent(so, solved, 0));
     }
-    CUDA_TRY(launch_output(h->dev, rhs, n_frames, out_dev, so));
+    CUDA_TRY(launch_output(h->dev, h->free_only ? h->dev.out_free : h->dev.out_full, rhs, n_frames, out_dev, so));
     return time_mark(h, 4, s);
 }
 
@@ -465,12 +615,13 @@ static int grow_scratch(sdfa_handle *h, float **buf, size_t *cap, int n_frames, 
 // the 75 600-frame bench batch the overlap is worth nothing (one-wave chunks: 7.31 ms against 7.28 ms in one pass --
 // the persistent decode and solve kernels leave no room for a second resident CTA), so the chunk is sized for memory.
 // Per-kernel timing runs unchunked.
+// Frames on grid.y: the gather assembly launches n / 16 rows of CTAs, so one pass takes at most this many frames.
+static const int MAX_FRAMES_PER_PASS = 65535 * 16;
 static int pipe_chunk(const sdfa_handle *h, int n_frames) {
-    const char *e = getenv("SDFA_PIPE_CHUNK");        // read per call: the tests switch it
-    const int env = e ? atoi(e) : -1;
-    if (h->timing || env == 0) return 0;
-    int chunk = env > 0 ? (env + 127) / 128 * 128 : h->dev.sm_count * 128 * 4;
-    if (env <= 0) {
+    const int opt = h->pipe_chunk;                     // sdfa_set_option("pipe_chunk"); default from SDFA_PIPE_CHUNK at create
+    if (h->timing || opt == 0) return n_frames > MAX_FRAMES_PER_PASS ? MAX_FRAMES_PER_PASS / 128 * 128 : 0;
+    int chunk = opt > 0 ? (opt + 127) / 128 * 128 : h->dev.sm_count * 128 * 4;
+    if (opt <= 0) {
         // large templates: keep each of the two scratch buffers under 2 GiB (config 5: 248 KB per frame -> 8448 frames)
         const size_t per_128 = scratch_floats(h->dev, 128) * sizeof(float);
         const size_t fit = ((size_t)2 << 30) / std::max<size_t>(per_128, 1);
@@ -496,7 +647,7 @@ static int reconstruct_chunks(sdfa_handle *h, sdfa_handle::Workspace &w, int chu
     if ((rc = pipe_setup(w))) return rc;
     if ((rc = grow_scratch(h, &w.rhs, &w.rhs_cap, chunk, s))) return rc;
     if ((rc = grow_scratch(h, &w.rhs2, &w.rhs2_cap, chunk, s))) return rc;
-    const size_t row_out = (size_t)h->dev.n_verts * 3;
+    const size_t row_out = out_row_floats(h);
     int i = 0;
     for (int f0 = 0; f0 < n_frames; f0 += chunk, ++i) {
         const int nf = std::min(chunk, n_frames - f0), b = i & 1;
@@ -523,13 +674,27 @@ static int reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, const flo
     return time_finish(h, s, decoded);
 }
 
-int sdfa_reconstruct_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames, float *out_dev,
-                         void *stream) {
+static int sdfa_reconstruct_dev_impl(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames, float *out_dev,
+                         void *stream, bool free_only) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
+    h->free_only = free_only;
     if (n_frames < 0 || (n_frames > 0 && (!dgrad_dev || !out_dev))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_dev: bad arguments");
+    if (n_frames == 0) return SDFA_OK;
     long long stride = dgrad_stride ? dgrad_stride : (long long)h->n_src_tris * 9;
-    return reconstruct_core(h, h->ws[0], dgrad_dev, stride, false, ASM_DGRAD, n_frames, out_dev, (cudaStream_t)stream, false);
+    if (stride < (long long)h->n_src_tris * 9) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_dev: dgrad_stride is shorter than a frame");
+    NvtxRange nvtx("sdfa_reconstruct_dev");
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = order_after_last(h, s))) return rc;
+    if ((rc = reconstruct_core(h, h->ws[0], dgrad_dev, stride, false, ASM_DGRAD, n_frames, out_dev, s, false))) return rc;
+    return mark_async(h, s);
+}
+
+int sdfa_reconstruct_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames, float *out_dev, void *stream) {
+    return sdfa_reconstruct_dev_impl(h, dgrad_dev, dgrad_stride, n_frames, out_dev, stream, false);
+}
+int sdfa_reconstruct_free_dev(sdfa_handle *h, const float *dgrad_dev, long long dgrad_stride, int n_frames, float *out_dev, void *stream) {
+    return sdfa_reconstruct_dev_impl(h, dgrad_dev, dgrad_stride, n_frames, out_dev, stream, true);
 }
 
 // Frames per chunk of the host-buffer entry points: copies of chunk i overlap the kernels of chunk i+1.
@@ -540,11 +705,14 @@ static int ws_stream(sdfa_handle::Workspace &w) {
     return SDFA_OK;
 }
 
-int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host) {
+static int sdfa_reconstruct_host_impl(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host, bool free_only) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
+    h->free_only = free_only;
     if (n_frames < 0 || (n_frames > 0 && (!dgrad_host || !out_host))) return fail(SDFA_ERR_ARG, "sdfa_reconstruct_host: bad arguments");
-    const size_t row_in = (size_t)h->n_src_tris * 9, row_out = (size_t)h->dev.n_verts * 3;
+    const size_t row_in = (size_t)h->n_src_tris * 9, row_out = out_row_floats(h);
+    NvtxRange nvtx("sdfa_reconstruct_host");
+    if ((rc = wait_async(h))) return rc;
     for (int f0 = 0, k = 0; f0 < n_frames; f0 += HOST_CHUNK, k ^= 1) {
         const int nf = std::min(HOST_CHUNK, n_frames - f0);
         sdfa_handle::Workspace &w = h->ws[k];
@@ -560,6 +728,13 @@ int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames,
     return SDFA_OK;
 }
 
+int sdfa_reconstruct_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host) {
+    return sdfa_reconstruct_host_impl(h, dgrad_host, n_frames, out_host, false);
+}
+int sdfa_reconstruct_free_host(sdfa_handle *h, const float *dgrad_host, int n_frames, float *out_host) {
+    return sdfa_reconstruct_host_impl(h, dgrad_host, n_frames, out_host, true);
+}
+
 static int single_frame(sdfa_handle *h, const double *in, long long len, int mode, const float *cnst, float *out_host) {
     int rc;
     const HostPlan &p = h->host;
@@ -570,6 +745,8 @@ static int single_frame(sdfa_handle *h, const double *in, long long len, int mod
     std::vector<float> f32((size_t)len);
     for (long long i = 0; i < len; ++i) f32[(size_t)i] = (float)in[i];
     sdfa_handle::Workspace &w = h->ws[0];
+    h->free_only = false;
+    if ((rc = wait_async(h))) return rc;
     if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
     if ((rc = grow(&w.io_in, &w.io_in_cap, (size_t)len))) return rc;
     if ((rc = grow(&w.io_out, &w.io_out_cap, (size_t)p.n_verts * 3))) return rc;
@@ -583,7 +760,7 @@ static int single_frame(sdfa_handle *h, const double *in, long long len, int mod
 int sdfa_get_mesh_f64(sdfa_handle *h, const double *dgrad_host, long long dgrad_len, const float *cnst_verts_host,
                       const uint32_t *corr_count, const uint32_t *corr_faces, long long corr_faces_len, float *out_host) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
     if (!dgrad_host || !out_host || dgrad_len <= 0 || dgrad_len % 9) return fail(SDFA_ERR_ARG, "sdfa_get_mesh_f64: bad arguments");
     const HostPlan &p = h->host;
     const int n_src = (int)(dgrad_len / 9);
@@ -601,7 +778,7 @@ int sdfa_get_mesh_f64(sdfa_handle *h, const double *dgrad_host, long long dgrad_
 int sdfa_get_mesh_from_dm_f64(sdfa_handle *h, const double *dmat_host, long long dmat_len, const float *cnst_verts_host,
                               float *out_host) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
     const HostPlan &p = h->host;
     if (!dmat_host || !out_host || dmat_len < (long long)p.n_tris * 9) return fail(SDFA_ERR_ARG, "sdfa_get_mesh_from_dm_f64: bad arguments");
     if ((rc = sdfa_set_correspondences(h, nullptr, nullptr, (int)(dmat_len / 9)))) return rc;
@@ -612,42 +789,49 @@ int sdfa_get_mesh_from_dm_f64(sdfa_handle *h, const double *dmat_host, long long
 int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_scale, int k_scale,
                  const float *compT_rotat, const float *means_rotat, int k_rotat) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
     if (!compT_scale || !means_scale || !compT_rotat || !means_rotat || k_scale <= 0 || k_rotat <= 0)
         return fail(SDFA_ERR_ARG, "sdfa_set_pca: bad arguments");
     DevicePlan &d = h->dev;
     const int nt = h->n_src_tris;
-    auto pack_full = [&](const float *W, const float *m, int per, int K, float **dw, float **dm) -> int {
-        std::vector<float> w(W, W + (size_t)nt * per * K), mm(m, m + (size_t)nt * per);
-        int r;
-        if ((r = upload_mut(h, w, dw))) return r;
-        return upload_mut(h, mm, dm);
-    };
-    d.k_scale = k_scale; d.k_rotat = k_rotat;
-    if ((rc = pack_full(compT_scale, means_scale, 6, k_scale, &d.wfull_scale, &d.mfull_scale))) return rc;
-    if ((rc = pack_full(compT_rotat, means_rotat, 3, k_rotat, &d.wfull_rotat, &d.mfull_rotat))) return rc;
+    // everything is validated and built on the host before the current basis is touched
+    const AssemblyPlan &ap = h->host.asmplan;
+    std::vector<int32_t> src_s, src_r;
+    for (size_t g = 0; g < ap.slot_eq.size(); ++g) {
+        const int src = h->eq_src_host[ap.slot_eq[g]];
+        if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
+        for (int j = 0; j < 6; ++j) src_s.push_back(src < 0 ? -1 : src * 6 + j);
+        for (int j = 0; j < 3; ++j) src_r.push_back(src < 0 ? -1 : src * 3 + j);
+    }
     // tensor-core path: one GEMM row per slot of the frame-tiled compact layout (scale part, rotation part), split
     // into TF32 hi/lo and stored as tile images; the means ride along as an extra K column
-    {
-        const AssemblyPlan &ap = h->host.asmplan;
-        std::vector<int32_t> src_s, src_r;
-        for (size_t g = 0; g < ap.slot_eq.size(); ++g) {
-            const int src = h->eq_src_host[ap.slot_eq[g]];
-            if (src >= nt) return fail(SDFA_ERR_ARG, "sdfa_set_pca: basis has fewer triangles than the correspondences refer to");
-            for (int j = 0; j < 6; ++j) src_s.push_back(src < 0 ? -1 : src * 6 + j);
-            for (int j = 0; j < 3; ++j) src_r.push_back(src < 0 ? -1 : src * 3 + j);
-        }
-        auto build = [&](const float *W, const float *m, int K, const std::vector<int32_t> &src, float **dw, int *mt) -> int {
-            std::vector<float> img;
-            *mt = tc_build_basis(W, m, K, src, img);
-            return upload_mut(h, img, dw);
-        };
-        if ((rc = build(compT_scale, means_scale, k_scale, src_s, &d.tc_w_scale, &d.tc_mt_scale))) return rc;
-        if ((rc = build(compT_rotat, means_rotat, k_rotat, src_r, &d.tc_w_rotat, &d.tc_mt_rotat))) return rc;
-        if (d.tc_mt_scale * tc_rows_per_tile() != d.compact_s_rows ||
-            d.tc_mt_rotat * tc_rows_per_tile() != d.compact_stride - d.compact_s_rows)
-            return fail(SDFA_ERR_STATE, "sdfa_set_pca: compact layout and decode tiles disagree");
-    }
+    std::vector<float> img_s, img_r;
+    const int mt_s = tc_build_basis(compT_scale, means_scale, k_scale, src_s, img_s);
+    const int mt_r = tc_build_basis(compT_rotat, means_rotat, k_rotat, src_r, img_r);
+    if (mt_s * tc_rows_per_tile() != d.compact_s_rows || mt_r * tc_rows_per_tile() != d.compact_stride - d.compact_s_rows)
+        return fail(SDFA_ERR_STATE, "sdfa_set_pca: compact layout and decode tiles disagree");
+    // replace the previous basis (every call used to leak ~60 MB): nothing may still be reading it
+    if ((rc = wait_async(h))) return rc;
+    for (auto &w : h->ws) if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
+    h->has_pca = h->has_full_pca = false;
+    for (void *p : h->pca_allocs) cudaFree(p);
+    h->pca_allocs.clear();
+    d.wfull_scale = d.mfull_scale = d.wfull_rotat = d.mfull_rotat = d.tc_w_scale = d.tc_w_rotat = nullptr;
+    auto put = [&](const float *src, size_t n, float **dst) -> int {
+        void *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(float), 16)));
+        h->pca_allocs.push_back(p);
+        CUDA_TRY(cudaMemcpy(p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+        *dst = static_cast<float *>(p);
+        return SDFA_OK;
+    };
+    if ((rc = put(compT_scale, (size_t)nt * 6 * k_scale, &d.wfull_scale)) || (rc = put(means_scale, (size_t)nt * 6, &d.mfull_scale)) ||
+        (rc = put(compT_rotat, (size_t)nt * 3 * k_rotat, &d.wfull_rotat)) || (rc = put(means_rotat, (size_t)nt * 3, &d.mfull_rotat)) ||
+        (rc = put(img_s.data(), img_s.size(), &d.tc_w_scale)) || (rc = put(img_r.data(), img_r.size(), &d.tc_w_rotat)))
+        return rc;
+    d.k_scale = k_scale; d.k_rotat = k_rotat;
+    d.tc_mt_scale = mt_s; d.tc_mt_rotat = mt_r;
+    d.n_pca_tris = nt;
     h->has_pca = h->has_full_pca = true;
     return SDFA_OK;
 }
@@ -673,23 +857,38 @@ static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, co
     return reconstruct_core(h, w, w.dgrad_c, stride, true, ASM_DGRAD, n_frames, out_dev, s, true);
 }
 
-int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
-                                float *out_dev, void *stream) {
+static int sdfa_decode_reconstruct_dev_impl(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
+                                float *out_dev, void *stream, bool free_only) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
+    h->free_only = free_only;
     if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_reconstruct: call sdfa_set_pca first (and again after changing correspondences)");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !out_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
     if (n_frames == 0) return SDFA_OK;
-    return decode_reconstruct_core(h, h->ws[0], coeff_scale_dev, coeff_rotat_dev, n_frames, out_dev, (cudaStream_t)stream);
+    NvtxRange nvtx("sdfa_decode_reconstruct_dev");
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = order_after_last(h, s))) return rc;
+    if ((rc = decode_reconstruct_core(h, h->ws[0], coeff_scale_dev, coeff_rotat_dev, n_frames, out_dev, s))) return rc;
+    return mark_async(h, s);
 }
 
-int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host,
-                                 int n_frames, float *out_host) {
+int sdfa_decode_reconstruct_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames, float *out_dev, void *stream) {
+    return sdfa_decode_reconstruct_dev_impl(h, coeff_scale_dev, coeff_rotat_dev, n_frames, out_dev, stream, false);
+}
+int sdfa_decode_reconstruct_free_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames, float *out_dev, void *stream) {
+    return sdfa_decode_reconstruct_dev_impl(h, coeff_scale_dev, coeff_rotat_dev, n_frames, out_dev, stream, true);
+}
+
+static int sdfa_decode_reconstruct_host_impl(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host,
+                                 int n_frames, float *out_host, bool free_only) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
+    h->free_only = free_only;
     if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_reconstruct: call sdfa_set_pca first");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_host || !coeff_rotat_host || !out_host))) return fail(SDFA_ERR_ARG, "bad arguments");
-    const size_t ks = (size_t)h->dev.k_scale, kr = (size_t)h->dev.k_rotat, row_out = (size_t)h->dev.n_verts * 3;
+    const size_t ks = (size_t)h->dev.k_scale, kr = (size_t)h->dev.k_rotat, row_out = out_row_floats(h);
+    NvtxRange nvtx("sdfa_decode_reconstruct_host");
+    if ((rc = wait_async(h))) return rc;
     for (int f0 = 0, k = 0; f0 < n_frames; f0 += HOST_CHUNK, k ^= 1) {
         const int nf = std::min(HOST_CHUNK, n_frames - f0);
         sdfa_handle::Workspace &w = h->ws[k];
@@ -707,29 +906,42 @@ int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, 
     return SDFA_OK;
 }
 
+int sdfa_decode_reconstruct_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host, int n_frames, float *out_host) {
+    return sdfa_decode_reconstruct_host_impl(h, coeff_scale_host, coeff_rotat_host, n_frames, out_host, false);
+}
+int sdfa_decode_reconstruct_free_host(sdfa_handle *h, const float *coeff_scale_host, const float *coeff_rotat_host, int n_frames, float *out_host) {
+    return sdfa_decode_reconstruct_host_impl(h, coeff_scale_host, coeff_rotat_host, n_frames, out_host, true);
+}
+
 int sdfa_decode_dgrad_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
                           float *dgrad_dev, void *stream) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
     if (!h->has_full_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_dgrad_dev: call sdfa_set_pca first");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
-    CUDA_TRY(launch_decode_full(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, dgrad_dev, (cudaStream_t)stream));
-    return SDFA_OK;
+    if (h->n_src_tris != h->dev.n_pca_tris)
+        return fail(SDFA_ERR_STATE, "sdfa_decode_dgrad_dev: the source triangle count changed since sdfa_set_pca; call it again");
+    if (n_frames == 0) return SDFA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = order_after_last(h, s))) return rc;
+    CUDA_TRY(launch_decode_full(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, dgrad_dev, s));
+    return mark_async(h, s);
 }
 
 int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const float *coeff_rotat_dev, int n_frames,
                             float *dgrad_compact_dev, void *stream) {
     int rc;
-    if ((rc = need_device(h))) return rc;
+    ENTER_DEVICE(h);
     if (!h->has_pca) return fail(SDFA_ERR_STATE, "sdfa_decode_compact_dev: call sdfa_set_pca first");
     if (n_frames < 0 || (n_frames > 0 && (!coeff_scale_dev || !coeff_rotat_dev || !dgrad_compact_dev))) return fail(SDFA_ERR_ARG, "bad arguments");
     if (n_frames == 0) return SDFA_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = order_after_last(h, s))) return rc;
     sdfa_handle::Workspace &w = h->ws[0];
     if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
     if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
     CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, w.ximg_s, w.ximg_r, dgrad_compact_dev, s));
-    return SDFA_OK;
+    return mark_async(h, s);
 }
 
 int sdfa_compact_layout(const sdfa_handle *h, int32_t *map, int cap) {
@@ -746,7 +958,11 @@ int sdfa_get_deform_grad_host(const float *verts_a, const float *verts_b, int n_
     for (int i = 0; i < n_tris * 3; ++i)
         if (tris[i] >= (uint32_t)n_verts) return fail(SDFA_ERR_ARG, "sdfa_get_deform_grad_host: triangle index out of range");
     if (device < 0) return fail(SDFA_ERR_CUDA, "sdfa_get_deform_grad_host: needs a CUDA device; this library has no CPU path");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard;
+    {
+        int gr;
+        if ((gr = guard.enter(device))) return gr;
+    }
     float *da = nullptr, *db = nullptr;
     uint32_t *dt = nullptr;
     double *dout = nullptr;
@@ -815,10 +1031,43 @@ int sdfa_seek_dev(const float *seq_dev, int n_src, long long width, const double
     return SDFA_OK;
 }
 
+int sdfa_free_vertices(const sdfa_handle *h, int32_t *ids, int cap) {
+    if (!h) return -1;
+    const std::vector<int> &f = h->host.free_to_vi;
+    if (ids) for (int i = 0; i < std::min((int)f.size(), cap); ++i) ids[i] = f[i];
+    return (int)f.size();
+}
+
+int sdfa_expand_free_dev(sdfa_handle *h, const float *free_dev, int n_frames, float *out_dev, void *stream) {
+    int rc;
+    ENTER_DEVICE(h);
+    if (n_frames < 0 || (n_frames > 0 && (!free_dev || !out_dev))) return fail(SDFA_ERR_ARG, "sdfa_expand_free_dev: bad arguments");
+    if (n_frames == 0) return SDFA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = order_after_last(h, s))) return rc;
+    for (int f0 = 0; f0 < n_frames; f0 += MAX_FRAMES_PER_PASS)
+        CUDA_TRY(launch_expand(h->dev, free_dev + (size_t)f0 * h->dev.n_free * 3, std::min(MAX_FRAMES_PER_PASS, n_frames - f0),
+                               out_dev + (size_t)f0 * h->dev.n_verts * 3, s));
+    return mark_async(h, s);
+}
+
+int sdfa_set_option(sdfa_handle *h, const char *name, long long value) {
+    if (!h || !name) return fail(SDFA_ERR_ARG, "sdfa_set_option: bad arguments");
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
+    const std::string n(name);
+    if (n == "pipe_chunk") {
+        if (value < -1 || value > (1 << 30)) return fail(SDFA_ERR_ARG, "sdfa_set_option: pipe_chunk out of range");
+        h->pipe_chunk = (int)value;
+        return SDFA_OK;
+    }
+    return fail(SDFA_ERR_ARG, "sdfa_set_option: unknown option '" + n + "'");
+}
+
 long long sdfa_launch_count(void) { return launch_counter(); }
 
 int sdfa_set_timing(sdfa_handle *h, int enable) {
     if (!h) return fail(SDFA_ERR_ARG, "NULL handle");
+    std::lock_guard<std::recursive_mutex> lock(h->mu);
     h->timing = enable != 0;
     return SDFA_OK;
 }

@@ -425,6 +425,25 @@ int tc_build_basis(const float *W, const float *mean, int K, const std::vector<i
 }
 int tc_rows_per_tile() { return TC_BM; }
 
+// How many CTA pairs can be resident at once (a cluster must fit inside one GPC); kept in the plan.
+cudaError_t configure_decode_tc(DevicePlan &d) {
+    const size_t smem = (size_t)(TC_SLOTS + TC_XS_KB) * TC_SLOT_BYTES + 256 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(d.sm_count / TC_CLUSTER * TC_CLUSTER));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_decode_tc, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.sm_count / TC_CLUSTER; }
+    d.decode_max_clusters = n;
+    return cudaSuccess;
+}
+
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
@@ -446,24 +465,9 @@ cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, cons
     GemmParams P{{d.tc_w_scale, d.tc_w_rotat}, {ximg_scale, ximg_rotat}, dgrad_out, stride, {0, d.compact_s_rows},
                  {d.tc_mt_scale, d.tc_mt_rotat}, {tc_kblocks(d.k_scale), tc_kblocks(d.k_rotat)}, n_frames, n_tiles};
     int grid = (P.m_tiles[0] + P.m_tiles[1]) * n_tiles;
-    {
-        // persistent: as many clusters as can be resident at once (a cluster must fit inside one GPC)
-        static int max_clusters = 0;
-        if (!max_clusters) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(d.sm_count / TC_CLUSTER * TC_CLUSTER));
-            cfg.blockDim = dim3(TC_THREADS);
-            cfg.dynamicSmemBytes = smem;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = TC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, k_decode_tc, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.sm_count / TC_CLUSTER; }
-            max_clusters = n;
-        }
-        if (grid > max_clusters * TC_CLUSTER) grid = max_clusters * TC_CLUSTER;
-    }
+    // persistent: as many clusters as can be resident at once (configure_decode_tc)
+    const int max_clusters = d.decode_max_clusters > 0 ? d.decode_max_clusters : d.sm_count / TC_CLUSTER;
+    if (grid > max_clusters * TC_CLUSTER) grid = max_clusters * TC_CLUSTER;
     grid = grid / TC_CLUSTER * TC_CLUSTER;
     k_decode_tc<<<grid, TC_THREADS, smem, stream>>>(P);
     count_launch();

@@ -41,6 +41,9 @@ struct DevicePlan {
     const IoDesc   *io_desc = nullptr;
     const IoPhase  *io_phase = nullptr;
     int n_stages = 0, n_slots = 0, n_phases_fwd = 0, n_phases_bwd = 0, frames_per_tile = 32;
+    // launch configuration decided once per handle (sdfa_create: configure_launches), never in function-local statics
+    int solve_ctas_per_sm = 1;              // K3 (SIMT)
+    int decode_max_clusters = 0;            // K1: resident CTA pairs
     long long *solve_prof = nullptr;        // optional cycle counters [sm_count*4][8] (SDFA_SOLVE_PROFILE=1)
     // ---- tensor-core solve (K3T, solve_tc.cu); used instead of K3 when use_tensor
     bool use_tensor = false;
@@ -51,15 +54,24 @@ struct DevicePlan {
     const uint32_t *ts_chunk_off = nullptr;
     int ts_n_mma = 0, ts_n_epi = 0, ts_n_chunks = 0, ts_n_mma_events = 0, ts_n_epi_events = 0;
     // ---- output (K5)
-    // per 64-vertex chunk tables of the output kernel (rebuilt by upload_base when the base / constraints change)
-    int16_t        *out_line_of = nullptr;  // [chunks*192]
-    float          *out_cval = nullptr;     // [chunks*192]
-    int32_t        *out_line_ptr = nullptr; // [chunks+1]
-    int32_t        *out_line_off = nullptr; // [n_free*3]
-    float          *out_line_hi = nullptr, *out_line_lo = nullptr;
-    int out_max_lines = 0;
+    // per 64-vertex chunk tables of the output kernel (rebuilt by upload_base when the base / constraints change):
+    // out_full writes every vertex [n_verts,3] (the reference layout), out_free only the free vertices [n_free,3] in
+    // ascending vertex order (sdfa_*_free entry points: the constrained rows are constants the caller already has)
+    struct OutTables {
+        int n_rows = 0;                     // vertices per frame this table set writes
+        int16_t *line_of = nullptr;         // [chunks*192]
+        float   *cval = nullptr;            // [chunks*192]
+        int32_t *line_ptr = nullptr;        // [chunks+1]
+        int32_t *line_off = nullptr;        // [n_free*3]
+        float   *line_hi = nullptr, *line_lo = nullptr;
+        int max_lines = 0;
+    } out_full, out_free;
+    // expansion free rows -> all vertices (sdfa_expand_free_dev): per output element the free-row element or -1 + constant
+    int32_t *exp_src = nullptr;             // [n_verts*3]
+    float   *exp_cval = nullptr;            // [n_verts*3]
     // ---- decode (K1)
     int k_scale = 0, k_rotat = 0;
+    int n_pca_tris = 0;                     // source triangles of the basis given to sdfa_set_pca (rows / 6, rows / 3)
     float *wfull_scale = nullptr, *mfull_scale = nullptr, *wfull_rotat = nullptr, *mfull_rotat = nullptr;
     // tensor-core decode (decode_tc.cu): pre-split, pre-tiled basis images, bias and output offsets per row
     float *tc_w_scale = nullptr, *tc_w_rotat = nullptr;
@@ -76,7 +88,9 @@ cudaError_t launch_solve(const DevicePlan &d, float *scratch, int n_frames, cuda
 cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream);
 size_t solve_tc_smem_bytes(int n_mma, int n_epi);
 size_t scratch_floats(const DevicePlan &d, int n_frames);
-cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream);
+cudaError_t launch_output(const DevicePlan &d, const DevicePlan::OutTables &t, const float *scratch, int n_frames, float *out,
+                          cudaStream_t stream);
+cudaError_t launch_expand(const DevicePlan &d, const float *free_rows, int n_frames, float *out, cudaStream_t stream);
 cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                                float *dgrad_out, cudaStream_t stream);
 // inverse.cu: verts_b holds n_frames meshes vb_stride floats apart; out is [n_frames, n_tris, 9] double or float
@@ -90,6 +104,9 @@ cudaError_t launch_seek(const float *seq, long long width, const int2 *pairs, co
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);
 size_t tc_ximg_floats(int n_frames, int K);
+// Occupancy queries of the persistent kernels, stored in the plan (called by sdfa_create with the device current).
+cudaError_t configure_solve(DevicePlan &d);
+cudaError_t configure_decode_tc(DevicePlan &d);
 size_t solve_smem_bytes(int n_slots, int frames_per_tile);
 void count_launch();
 long long launch_counter();

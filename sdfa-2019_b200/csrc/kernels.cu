@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(ASM_THREADS, ASM_MIN_BLOCKS) k_assemble(AsmPar
 #define ASM_GF_N 16
 #endif
 constexpr int ASM_GF = ASM_GF_N;                      // frames per CTA of the gather variant (smaller tile: more CTAs per SM)
+static_assert(ASM_GF >= 1 && ASM_GF <= 32 && 32 % ASM_GF == 0, "ASM_GF_N must divide 32 (write-out deals 32 / ASM_GF lines per warp)");
 constexpr int ASM_GPAD = ASM_GF + 1;
 constexpr int ASM_G_WARPS = 8, ASM_G_THREADS = 32 * ASM_G_WARPS;   // the gather variant keeps 8 warps: thread = equation
 constexpr int ASM_KMAX = ASM_MAX_EQ / ASM_G_THREADS;
@@ -784,24 +785,37 @@ size_t solve_smem_bytes(int n_slots, int frames_per_tile) {
 }
 
 template <int F>
+static cudaError_t configure_solve_f(DevicePlan &d) {
+    const size_t smem = solve_smem_bytes(d.n_slots, F);
+    cudaError_t e = cudaFuncSetAttribute(k_solve<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_solve<F>, SOLVE_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (n < 1) return cudaErrorLaunchOutOfResources;
+    d.solve_ctas_per_sm = n;
+    return cudaSuccess;
+}
+
+cudaError_t configure_solve(DevicePlan &d) {
+    switch (d.frames_per_tile) {
+        case 32: return configure_solve_f<32>(d);
+        case 16: return configure_solve_f<16>(d);
+        case 8: return configure_solve_f<8>(d);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int F>
 static cudaError_t launch_solve_f(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
     const size_t smem = solve_smem_bytes(d.n_slots, F);
-    static int configured_device = -1;
-    static size_t configured_smem = 0;
-    static int ctas_per_sm = 1;
-    if (configured_device != d.device || configured_smem != smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_solve<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_solve<F>, SOLVE_THREADS, smem);
-        if (e != cudaSuccess) return e;
-        if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
-        configured_device = d.device;
-        configured_smem = smem;
-    }
+    // the attribute is per function and device, not per handle: another handle may have set a smaller size since
+    cudaError_t e = cudaFuncSetAttribute(k_solve<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int n_tiles = (n_frames + F - 1) / F;
     SolveParams P{d.prog, d.stage_off, d.io_desc, d.io_phase, d.n_stages, d.n_slots, d.n_phases_fwd, d.n_phases_bwd,
                   scratch, d.n_free, n_tiles, d.solve_prof};
-    int grid = d.sm_count * ctas_per_sm;
+    int grid = d.sm_count * d.solve_ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
     k_solve<F><<<grid, SOLVE_THREADS, smem, stream>>>(P);
     g_launches++;
@@ -883,16 +897,46 @@ __global__ void __launch_bounds__(OUT_THREADS) k_output(OutParams P) {
     }
 }
 
-cudaError_t launch_output(const DevicePlan &d, const float *scratch, int n_frames, float *out, cudaStream_t stream) {
+cudaError_t launch_output(const DevicePlan &d, const DevicePlan::OutTables &t, const float *scratch, int n_frames, float *out,
+                          cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     const int FR = d.layout.FL, FC = std::min(FR, 32);
-    OutParams P{scratch, d.out_line_of, d.out_cval, d.out_line_ptr, d.out_line_off, d.out_line_hi, d.out_line_lo,
-                out, n_frames, d.n_verts, FR, FC, d.layout.tile_stride};
-    const size_t smem = (size_t)std::max(d.out_max_lines, 1) * (FC + 1) * sizeof(float);
+    OutParams P{scratch, t.line_of, t.cval, t.line_ptr, t.line_off, t.line_hi, t.line_lo,
+                out, n_frames, t.n_rows, FR, FC, d.layout.tile_stride};
+    const size_t smem = (size_t)std::max(t.max_lines, 1) * (FC + 1) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_output, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((d.n_verts + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));
+    dim3 grid((unsigned)((t.n_rows + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));
     k_output<<<grid, OUT_THREADS, smem, stream>>>(P);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// Free rows [n_frames][n_free*3] -> all vertices [n_frames][n_verts*3]: the receiving side of a gather that moved only
+// the free rows (the constrained rows are per-handle constants, impl.hpp:302-308).  thread = output element, EXP_FRAMES
+// frames per CTA; a frame's 15 KB of free rows stay in L1 / L2 while its 60 KB leave as full-warp stores.
+constexpr int EXP_THREADS = 256, EXP_FRAMES = 16;
+__global__ void __launch_bounds__(EXP_THREADS) k_expand(const float *__restrict__ free_rows, const int32_t *__restrict__ src,
+                                                        const float *__restrict__ cval, float *__restrict__ out, int n_frames,
+                                                        int row_out, int row_in) {
+    const int e = blockIdx.x * EXP_THREADS + threadIdx.x;
+    if (e >= row_out) return;
+    const int sidx = src[e];
+    const float c = cval[e];
+    const int f0 = blockIdx.y * EXP_FRAMES, f1 = min(n_frames, f0 + EXP_FRAMES);
+    if (sidx < 0) {
+        for (int f = f0; f < f1; ++f) __stcs(out + (long long)f * row_out + e, c);
+    } else {
+#pragma unroll 4
+        for (int f = f0; f < f1; ++f) __stcs(out + (long long)f * row_out + e, __ldg(free_rows + (long long)f * row_in + sidx));
+    }
+}
+
+cudaError_t launch_expand(const DevicePlan &d, const float *free_rows, int n_frames, float *out, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    const int row_out = d.n_verts * 3, row_in = d.n_free * 3;
+    dim3 grid((unsigned)((row_out + EXP_THREADS - 1) / EXP_THREADS), (unsigned)((n_frames + EXP_FRAMES - 1) / EXP_FRAMES));
+    k_expand<<<grid, EXP_THREADS, 0, stream>>>(free_rows, d.exp_src, d.exp_cval, out, n_frames, row_out, row_in);
     g_launches++;
     return cudaGetLastError();
 }
@@ -948,7 +992,7 @@ __global__ void __launch_bounds__(256) k_decode(const float *__restrict__ coeff,
 cudaError_t launch_decode_full(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                                float *dgrad_out, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    const int ntri = d.n_tris;
+    const int ntri = d.n_pca_tris;                 // rows of the basis sdfa_set_pca uploaded (not the template's)
     const long long stride = (long long)ntri * 9;
     dim3 gs((unsigned)((ntri * 6 + DEC_TJ - 1) / DEC_TJ), (unsigned)((n_frames + DEC_TF - 1) / DEC_TF));
     k_decode<<<gs, 256, 0, stream>>>(coeff_scale, d.k_scale, d.wfull_scale, d.mfull_scale, ntri * 6, 6, 0, n_frames, dgrad_out, stride);

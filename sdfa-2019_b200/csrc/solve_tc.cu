@@ -381,13 +381,9 @@ size_t solve_tc_smem_bytes(int n_mma, int n_epi) {
 cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     const size_t smem = solve_tc_smem_bytes(d.ts_n_mma, d.ts_n_epi);
-    static int configured_device = -1;
-    static size_t configured_smem = 0;
-    if (configured_device != d.device || configured_smem != smem) {
+    {   // per function and device, not per handle: set on every launch (another handle may need a different size)
         cudaError_t e = cudaFuncSetAttribute(k_solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured_device = d.device;
-        configured_smem = smem;
     }
     const int n_tiles = 3 * ((n_frames + TS_COLS - 1) / TS_COLS);
     TsParams P{d.ts_mma, d.ts_epi, d.ts_matrix, d.ts_chunk_off, d.ts_n_mma, d.ts_n_epi, d.ts_n_chunks,

@@ -69,9 +69,10 @@ class Reconstructor:
     ``device=-1`` keeps everything on the host for plan inspection; compute calls then raise.
     """
 
-    def __init__(self, verts, faces, cnsts=(), corrs=(), reg=1e-10, device=None, solver=None):
+    def __init__(self, verts, faces, cnsts=(), corrs=(), reg=1e-10, device=None, solver=None, options=None):
         """``solver``: None = tensor-core solve when the template fits it, else the SIMT sweeps;
-        "simt" / "tensor" force one (same as the SDFA_SOLVER environment variable)."""
+        "simt" / "tensor" force one.  ``options``: further ``sdfa_create_with`` options as a dict
+        (include/sdfa_b200.h), e.g. ``{"pipe_chunk": 4096}``."""
         V = _f32c(verts, "verts")
         F = _u32c(faces)
         c = _u32c(cnsts).reshape(-1)
@@ -86,18 +87,13 @@ class Reconstructor:
         self.device = _default_device() if device is None else int(device)
         self._h = ctypes.c_void_p()
         self._verts, self._faces, self._cnsts = V, F, c
-        prev = os.environ.get("SDFA_SOLVER")
+        opts = dict(options or {})
         if solver is not None:
-            os.environ["SDFA_SOLVER"] = solver
-        try:
-            check(lib.sdfa_create(ctypes.byref(self._h), ptr(V), len(V), ptr(F), len(F), ptr(c) if c.size else None,
-                                  len(c), ptr(cc) if cc.size else None, float(reg), self.device))
-        finally:
-            if solver is not None:
-                if prev is None:
-                    os.environ.pop("SDFA_SOLVER", None)
-                else:
-                    os.environ["SDFA_SOLVER"] = prev
+            opts["solver"] = solver
+        text = ";".join(f"{k}={v}" for k, v in opts.items())
+        check(lib.sdfa_create_with(ctypes.byref(self._h), ptr(V), len(V), ptr(F), len(F), ptr(c) if c.size else None,
+                                   len(c), ptr(cc) if cc.size else None, float(reg), self.device,
+                                   text.encode() if text else None))
         nf, ne, na, nnz = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
         check(lib.sdfa_info(self._h, None, None, None, ctypes.byref(nf), ctypes.byref(ne), ctypes.byref(na),
                             ctypes.byref(nnz)))
@@ -120,6 +116,52 @@ class Reconstructor:
 
     def debug(self, what):
         return _native.debug_get(self._h, what)
+
+    def set_option(self, name, value):
+        """Run-time options of the handle (``sdfa_set_option``): ``pipe_chunk``."""
+        check(lib.sdfa_set_option(self._h, name.encode(), int(value)))
+
+    def _torch_out(self, out, n, like, free_only=False):
+        """Validated (or freshly allocated) [n, rows, 3] float32 output tensor on the handle's device
+        (rows = n_verts, or n_free with ``free_only``)."""
+        import torch
+        rows = self.n_free if free_only else self.n_verts
+        if like.device.index != self.device:
+            raise SdfaError(_native.ERR_ARG, f"input is on {like.device}, the handle on cuda:{self.device}")
+        if out is None:
+            return torch.empty((n, rows, 3), dtype=torch.float32, device=like.device)
+        if (not _is_torch(out) or out.dtype != torch.float32 or out.device != like.device or not out.is_contiguous()
+                or out.numel() != n * rows * 3):
+            raise SdfaError(_native.ERR_ARG, f"out must be a contiguous float32 tensor of {n}x{rows}x3 on {like.device}")
+        return out
+
+    def _numpy_out(self, out, n, free_only=False):
+        rows = self.n_free if free_only else self.n_verts
+        if out is None:
+            return np.empty((n, rows, 3), dtype=np.float32)
+        if (not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags.c_contiguous
+                or out.size != n * rows * 3):
+            raise SdfaError(_native.ERR_ARG, f"out must be a C-contiguous float32 array of {n}x{rows}x3")
+        return out
+
+    @property
+    def free_vertices(self):
+        """Vertex index of every row of a ``free_only`` result (ascending; the vertices that are not constrained)."""
+        ids = np.empty(self.n_free, dtype=np.int32)
+        lib.sdfa_free_vertices(self._h, ptr(ids), self.n_free)
+        return ids
+
+    def expand_free(self, free_rows, out=None, stream=None):
+        """[N, n_free, 3] free rows (torch.cuda) -> [N, n_verts, 3] with the current constraint positions filled in."""
+        import torch
+        x = free_rows.contiguous()
+        if x.dtype != torch.float32 or not x.is_cuda or x.numel() % (self.n_free * 3):
+            raise SdfaError(_native.ERR_ARG, "expand_free: float32 CUDA tensor [N, n_free, 3]")
+        n = x.numel() // (self.n_free * 3)
+        out = self._torch_out(out, n, x)
+        s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        check(lib.sdfa_expand_free_dev(self._h, ptr(x.data_ptr()), n, ptr(out.data_ptr()), ptr(s)))
+        return out
 
     # ---------------------------------------------------------------------------------- state
     def set_constraint_positions(self, vert_cnsts=None):
@@ -176,9 +218,11 @@ class Reconstructor:
         return out
 
     # ----------------------------------------------------------------------------------- batched
-    def get_mesh_batch(self, deform_grads, out=None, stream=None):
+    def get_mesh_batch(self, deform_grads, out=None, stream=None, free_only=False):
         """[N, 9*n_src_tris] float32 -> [N, n_verts, 3] float32.  torch.cuda tensors stay on the device
-        (stream-ordered, no synchronisation); numpy arrays go through pinned-size staging copies."""
+        (stream-ordered, no synchronisation); numpy arrays go through pinned-size staging copies.
+        ``free_only``: return only the free vertices, [N, n_free, 3] (rows = ``free_vertices``): the constrained
+        rows are the constants given as ``vert_cnsts``, so a host copy or gather moves a quarter of the bytes."""
         if _is_torch(deform_grads):
             import torch
             x = deform_grads
@@ -190,22 +234,24 @@ class Reconstructor:
             if x.shape[1] != self.n_src_tris * 9:
                 raise SdfaError(_native.ERR_ARG, f"expected {self.n_src_tris * 9} values per frame, got {x.shape[1]}")
             n = x.shape[0]
-            if out is None:
-                out = torch.empty((n, self.n_verts, 3), dtype=torch.float32, device=x.device)
+            out = self._torch_out(out, n, x, free_only)
             s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
-            check(lib.sdfa_reconstruct_dev(self._h, ptr(x.data_ptr()), x.stride(0), n, ptr(out.data_ptr()), ptr(s)))
+            fn = lib.sdfa_reconstruct_free_dev if free_only else lib.sdfa_reconstruct_dev
+            check(fn(self._h, ptr(x.data_ptr()), x.stride(0), n, ptr(out.data_ptr()), ptr(s)))
             return out
         x = _f32c(deform_grads, "deform_grads")
         x = x.reshape(x.shape[0], self.n_src_tris * 9) if (x.ndim > 1 and x.size == 0) else (
             x.reshape(x.shape[0], -1) if x.ndim > 1 else x.reshape(1, -1))
         if x.shape[1] != self.n_src_tris * 9:
             raise SdfaError(_native.ERR_ARG, f"expected {self.n_src_tris * 9} values per frame, got {x.shape[1]}")
-        res = np.empty((x.shape[0], self.n_verts, 3), dtype=np.float32) if out is None else out
-        check(lib.sdfa_reconstruct_host(self._h, ptr(x), x.shape[0], ptr(res)))
+        res = self._numpy_out(out, x.shape[0], free_only)
+        fn = lib.sdfa_reconstruct_free_host if free_only else lib.sdfa_reconstruct_host
+        check(fn(self._h, ptr(x), x.shape[0], ptr(res)))
         return res
 
-    def decode_and_get_mesh(self, coeff_scale, coeff_rotat, out=None, stream=None):
-        """PCA coefficients -> vertices: F.linear x2 + interleave + reconstruction in one call."""
+    def decode_and_get_mesh(self, coeff_scale, coeff_rotat, out=None, stream=None, free_only=False):
+        """PCA coefficients -> vertices: F.linear x2 + interleave + reconstruction in one call
+        (``free_only`` as in ``get_mesh_batch``)."""
         if not self._has_pca:
             raise SdfaError(_native.ERR_STATE, "set_pca() first")
         if _is_torch(coeff_scale):
@@ -215,18 +261,20 @@ class Reconstructor:
                 raise SdfaError(_native.ERR_ARG, "torch inputs must be float32 CUDA tensors")
             a, b = a.reshape(-1, self.k_scale), b.reshape(-1, self.k_rotat)
             n = a.shape[0]
-            if out is None:
-                out = torch.empty((n, self.n_verts, 3), dtype=torch.float32, device=a.device)
+            if b.shape[0] != n or b.device != a.device:
+                raise SdfaError(_native.ERR_ARG, "coefficient batches differ in length or device")
+            out = self._torch_out(out, n, a, free_only)
             s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
-            check(lib.sdfa_decode_reconstruct_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), n,
-                                                  ptr(out.data_ptr()), ptr(s)))
+            fn = lib.sdfa_decode_reconstruct_free_dev if free_only else lib.sdfa_decode_reconstruct_dev
+            check(fn(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), n, ptr(out.data_ptr()), ptr(s)))
             return out
         a = _f32c(coeff_scale, "coeff_scale").reshape(-1, self.k_scale)
         b = _f32c(coeff_rotat, "coeff_rotat").reshape(-1, self.k_rotat)
         if len(a) != len(b):
             raise SdfaError(_native.ERR_ARG, "coefficient batches differ in length")
-        res = np.empty((len(a), self.n_verts, 3), dtype=np.float32) if out is None else out
-        check(lib.sdfa_decode_reconstruct_host(self._h, ptr(a), ptr(b), len(a), ptr(res)))
+        res = self._numpy_out(out, len(a), free_only)
+        fn = lib.sdfa_decode_reconstruct_free_host if free_only else lib.sdfa_decode_reconstruct_host
+        check(fn(self._h, ptr(a), ptr(b), len(a), ptr(res)))
         return res
 
     def decode_dgrad(self, coeff_scale, coeff_rotat, stream=None):
@@ -234,6 +282,8 @@ class Reconstructor:
         import torch
         a = coeff_scale.contiguous().reshape(-1, self.k_scale)
         b = coeff_rotat.contiguous().reshape(-1, self.k_rotat)
+        if a.shape[0] != b.shape[0] or a.dtype != torch.float32 or b.dtype != torch.float32 or not (a.is_cuda and b.is_cuda):
+            raise SdfaError(_native.ERR_ARG, "decode_dgrad: float32 CUDA coefficient tensors of equal length")
         out = torch.empty((a.shape[0], self.n_src_tris * 9), dtype=torch.float32, device=a.device)
         s = torch.cuda.current_stream(a.device).cuda_stream if stream is None else stream
         check(lib.sdfa_decode_dgrad_dev(self._h, ptr(a.data_ptr()), ptr(b.data_ptr()), a.shape[0],

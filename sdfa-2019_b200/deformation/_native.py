@@ -33,6 +33,8 @@ def _load():
     pi = ctypes.POINTER(ctypes.c_int)
     sig = {
         "sdfa_create": ([ctypes.POINTER(vp), vp, ci, vp, ci, vp, ci, vp, cd, ci], ci),
+        "sdfa_create_with": ([ctypes.POINTER(vp), vp, ci, vp, ci, vp, ci, vp, cd, ci, ctypes.c_char_p], ci),
+        "sdfa_set_option": ([vp, ctypes.c_char_p, cll], ci),
         "sdfa_destroy": ([vp], None),
         "sdfa_info": ([vp, pi, pi, pi, pi, pi, pi, ctypes.POINTER(cll)], ci),
         "sdfa_last_error": ([], ctypes.c_char_p),
@@ -45,6 +47,12 @@ def _load():
         "sdfa_set_pca": ([vp, vp, vp, ci, vp, vp, ci], ci),
         "sdfa_decode_reconstruct_dev": ([vp, vp, vp, ci, vp, vp], ci),
         "sdfa_decode_reconstruct_host": ([vp, vp, vp, ci, vp], ci),
+        "sdfa_free_vertices": ([vp, vp, ci], ci),
+        "sdfa_reconstruct_free_dev": ([vp, vp, cll, ci, vp, vp], ci),
+        "sdfa_reconstruct_free_host": ([vp, vp, ci, vp], ci),
+        "sdfa_decode_reconstruct_free_dev": ([vp, vp, vp, ci, vp, vp], ci),
+        "sdfa_decode_reconstruct_free_host": ([vp, vp, vp, ci, vp], ci),
+        "sdfa_expand_free_dev": ([vp, vp, ci, vp, vp], ci),
         "sdfa_decode_dgrad_dev": ([vp, vp, vp, ci, vp, vp], ci),
         "sdfa_decode_compact_dev": ([vp, vp, vp, ci, vp, vp], ci),
         "sdfa_compact_layout": ([vp, vp, ci], ci),
@@ -64,10 +72,12 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ["sdfa_create", "sdfa_destroy", "sdfa_info", "sdfa_last_error", "sdfa_set_constraint_positions",
+EXPORTS = ["sdfa_create", "sdfa_create_with", "sdfa_set_option", "sdfa_destroy", "sdfa_info", "sdfa_last_error", "sdfa_set_constraint_positions",
            "sdfa_set_correspondences", "sdfa_reconstruct_dev", "sdfa_reconstruct_host", "sdfa_get_mesh_f64",
            "sdfa_get_mesh_from_dm_f64", "sdfa_set_pca", "sdfa_decode_reconstruct_dev",
-           "sdfa_decode_reconstruct_host", "sdfa_decode_dgrad_dev", "sdfa_decode_compact_dev", "sdfa_compact_layout",
+           "sdfa_decode_reconstruct_host", "sdfa_free_vertices", "sdfa_reconstruct_free_dev",
+           "sdfa_reconstruct_free_host", "sdfa_decode_reconstruct_free_dev", "sdfa_decode_reconstruct_free_host",
+           "sdfa_expand_free_dev", "sdfa_decode_dgrad_dev", "sdfa_decode_compact_dev", "sdfa_compact_layout",
            "sdfa_get_deform_grad_host", "sdfa_deform_grad_batch_dev", "sdfa_seek_dev",
            "sdfa_launch_count", "sdfa_set_timing", "sdfa_last_timing", "sdfa_debug_get"]
 

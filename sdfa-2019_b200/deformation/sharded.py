@@ -81,3 +81,118 @@ def gather_meshes(local, n_frames, dst=0, group=None):
         return _unpad(stacked, sizes)
     dist.gather(send, None, dst=dst, group=group)
     return None
+
+
+class GatherPipeline:
+    """Reconstruct this rank's frames chunk by chunk and gather every chunk while the next one is computed.
+
+    SURVEY 8(e): the collective runs on a side stream after the output kernel has written the contiguous send
+    buffer and overlaps with the next chunk's kernels.  Only the FREE rows travel (``free_only`` results,
+    [frames, n_free, 3]: 15 KB instead of 60 KB per FLAME frame -- the constrained rows are constants every rank
+    already holds); ``expand=True`` rebuilds the reference layout [frames, n_verts, 3] on the receiving side with
+    ``Reconstructor.expand_free``.
+
+    ``rec`` needs ``decode_and_get_mesh(xs, xr, out=, free_only=True)`` / ``get_mesh_batch(x, out=, free_only=True)``,
+    ``expand_free(rows, out=)``, ``n_free`` and ``n_verts`` -- a ``deformation.Reconstructor`` bound to this rank's GPU
+    (the CPU tests pass a stand-in and gloo).  Every rank must hold the same number of frames per call (the bench's
+    weak-scaling layout); ragged batches go through ``all_gather_meshes``.
+    """
+
+    def __init__(self, rec, chunk_frames=9472, group=None, mode="all", dst=0, expand=False):
+        import torch.distributed as dist
+        assert mode in ("all", "root")
+        self.rec, self.chunk, self.group, self.mode, self.dst, self.expand = rec, int(chunk_frames), group, mode, dst, expand
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._side = None
+        self._bufs = None
+
+    def _streams(self, device):
+        import torch
+        if device.type != "cuda":
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device)
+        return self._side
+
+    def _buffers(self, device):
+        import torch
+        if self._bufs is None or self._bufs[0].device != device:
+            rows = (self.chunk, self.rec.n_free, 3)
+            self._bufs = [torch.empty(rows, dtype=torch.float32, device=device) for _ in range(2)]          # send, double buffered
+            self._recv = [torch.empty((self.world,) + rows, dtype=torch.float32, device=device) for _ in range(2)]
+        return self._bufs, self._recv
+
+    def run(self, compute, inputs, out=None):
+        """``compute(*chunk_inputs, out=send_rows)`` fills ``send_rows`` [nf, n_free, 3] for a chunk of this rank's
+        frames.  Returns, on the receiving ranks, [world * n_local, n_free, 3] (rank-major: rank r's frames at
+        ``r * n_local``), or [world * n_local, n_verts, 3] with ``expand=True``; ``None`` on the other ranks in
+        ``mode="root"``."""
+        import torch
+        import torch.distributed as dist
+        n_local = inputs[0].shape[0]
+        device = inputs[0].device
+        rows_out = self.rec.n_verts if self.expand else self.rec.n_free
+        receiver = self.mode == "all" or self.rank == self.dst
+        if receiver and out is None:
+            out = torch.empty((self.world * n_local, rows_out, 3), dtype=torch.float32, device=device)
+        if self.world == 1:
+            for c0 in range(0, n_local, self.chunk):
+                nf = min(self.chunk, n_local - c0)
+                if self.expand:
+                    (send, _), _ = self._buffers(device), None
+                    compute(*[x[c0:c0 + nf] for x in inputs], out=send[:nf])
+                    self.rec.expand_free(send[:nf], out=out[c0:c0 + nf])
+                else:
+                    compute(*[x[c0:c0 + nf] for x in inputs], out=out[c0:c0 + nf])
+            return out
+        side = self._streams(device)
+        send, recv = self._buffers(device)
+        main = torch.cuda.current_stream(device) if side is not None else None
+        done = [None, None]                   # the side stream's event per buffer: its previous gather has been consumed
+        for i, c0 in enumerate(range(0, n_local, self.chunk)):
+            nf, b = min(self.chunk, n_local - c0), i & 1
+            if side is not None and done[b] is not None:
+                main.wait_event(done[b])      # the send buffer is free again
+            compute(*[x[c0:c0 + nf] for x in inputs], out=send[b][:nf])
+            ctx = torch.cuda.stream(side) if side is not None else _null()
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+            with ctx:
+                src = send[b][:nf]
+                # a ragged last chunk gets its own (side-stream) receive buffer so that the gather output stays contiguous
+                fresh = lambda: torch.empty((self.world, nf) + tuple(src.shape[1:]), dtype=src.dtype, device=device)  # noqa: E731
+                if self.mode == "all":
+                    got = recv[b] if nf == self.chunk else fresh()
+                    dist.all_gather_into_tensor(got.view((self.world * nf,) + tuple(src.shape[1:])), src, group=self.group)
+                else:
+                    if self.rank == self.dst:
+                        got = recv[b] if nf == self.chunk else fresh()
+                        parts = [got[r] for r in range(self.world)]
+                        dist.gather(src, parts, dst=self.dst, group=self.group)
+                    else:
+                        dist.gather(src, None, dst=self.dst, group=self.group)
+                        got = None
+                if got is not None:
+                    for r in range(self.world):
+                        tgt = out[r * n_local + c0: r * n_local + c0 + nf]
+                        if self.expand:
+                            self.rec.expand_free(got[r], out=tgt, **({"stream": side.cuda_stream} if side is not None else {}))
+                        else:
+                            tgt.copy_(got[r])
+                if side is not None:
+                    done[b] = torch.cuda.Event()
+                    done[b].record(side)
+        if side is not None:
+            main.wait_stream(side)
+        return out if receiver else None
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

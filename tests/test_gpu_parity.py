@@ -333,7 +333,7 @@ def test_config3_batch_sizes_give_identical_frames(rec, flame):
         assert torch.equal(out[:64], ref) and torch.equal(out[n - 64:], ref), n
 
 
-def test_chunk_pipeline_is_bit_identical(rec, flame, monkeypatch):
+def test_chunk_pipeline_is_bit_identical(rec, flame):
     """Large batches run chunk by chunk with the output kernel of a chunk on a second stream (api.cpp
     reconstruct_chunks): forced to 256-frame chunks, both entry points return exactly what the single pass returns,
     ragged last chunk included, and back-to-back calls do not race on the two scratch buffers."""
@@ -344,9 +344,9 @@ def test_chunk_pipeline_is_bit_identical(rec, flame, monkeypatch):
     cs, ms, cr, mr = W.random_pca(len(F), seed=1)
     rec.set_pca(cs, ms, cr, mr)
     xs, xr = (torch.from_numpy(a).cuda() for a in W.random_coeffs(n, seed=8))
-    monkeypatch.setenv("SDFA_PIPE_CHUNK", "0")
+    rec.set_option("pipe_chunk", 0)
     ref_a, ref_b = rec.get_mesh_batch(dg), rec.decode_and_get_mesh(xs, xr)
-    monkeypatch.setenv("SDFA_PIPE_CHUNK", "256")
+    rec.set_option("pipe_chunk", 256)
     for _ in range(3):
         out_a, out_b = rec.get_mesh_batch(dg), rec.decode_and_get_mesh(xs, xr)
         assert torch.equal(out_a, ref_a) and torch.equal(out_b, ref_b)
@@ -355,6 +355,7 @@ def test_chunk_pipeline_is_bit_identical(rec, flame, monkeypatch):
         out_c = rec.decode_and_get_mesh(xs, xr, stream=side.cuda_stream)
     side.synchronize()
     assert torch.equal(out_c, ref_b)
+    rec.set_option("pipe_chunk", -1)                  # back to the automatic chunk size (the handle is shared)
 
 
 def test_config4_network_to_mesh_on_device(rec, chk, flame):
