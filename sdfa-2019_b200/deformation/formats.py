@@ -125,3 +125,110 @@ def load_pca(dgrad_root):
     d = os.path.join(dgrad_root, "pca")
     return tuple(np.load(os.path.join(d, n + ".npy")).astype(np.float32)
                  for n in ("scale_compT", "scale_means", "rotat_compT", "rotat_means"))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A trained model's PCA bases straight from its checkpoint (second half).
+# The reference registers them as buffers of the two PcaInversion modules (output_module.py:103-113), so they travel
+# inside every ``.ckpt`` under ``state`` (saber/trainer/manager/checkpoints.py:14-25, :52-57); old checkpoints carry
+# other key names, which api.py:170-197 renames before ``load_state_dict``.
+
+# api.py:173-188, the pairs that can touch the PCA buffers' keys (the others rename encoder layers)
+_CKPT_LEGACY_KEYS = (("anime_decoder.proj_scale", "_model._output_module._scale_pca"),
+                     ("anime_decoder.proj_rotat", "_model._output_module._rotat_pca"))
+_PCA_KEYS = {"compT_scale": "_model._output_module._scale_pca.compT", "means_scale": "_model._output_module._scale_pca.means",
+             "compT_rotat": "_model._output_module._rotat_pca.compT", "means_rotat": "_model._output_module._rotat_pca.means"}
+
+
+def load_hparams(path):
+    """``hparams.json`` as written by ConfigDict.dump (saber/utils/config_dict.py:221-243): plain JSON, every level
+    carrying an ``__entirety__`` flag.  ``path`` may be the file or the log directory holding it (experiment.py:32)."""
+    import json
+    if os.path.isdir(path):
+        path = os.path.join(path, "hparams.json")
+    with open(path) as fp:
+        return json.load(fp)
+
+
+def pca_dims_from_hparams(hparams):
+    """(output_dim_scale, output_dim_rotat, k_scale, k_rotat) the model was built with
+    (config/model/dgrad.py:75-92: the last fc of layers_scale / layers_rotat gives K, output_dim_* the rows)."""
+    out = hparams["model"]["output"]
+    return (int(out["output_dim_scale"]), int(out["output_dim_rotat"]),
+            int(out["layers_scale"][-1][2]), int(out["layers_rotat"][-1][2]))
+
+
+def load_pca_from_checkpoint(ckpt_path, hparams=None):
+    """-> (compT_scale [6*n_tris, Ks], means_scale, compT_rotat [3*n_tris, Kr], means_rotat) float32, ready for
+    ``set_pca``, from a reference checkpoint (``torch.load`` -> ``["state"]``; a bare state dict is accepted too).
+    Legacy key names are renamed like api.py:170-197 does.  With ``hparams`` (dict, file or log dir) the shapes are
+    checked against the model description the checkpoint was trained with."""
+    import torch
+    ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    state = ckpt["state"] if isinstance(ckpt, dict) and "state" in ckpt else ckpt
+    renamed = {}
+    for k, v in state.items():
+        for old, new in _CKPT_LEGACY_KEYS:
+            k = k.replace(old, new)
+        renamed[k] = v
+    missing = [k for k in _PCA_KEYS.values() if k not in renamed]
+    if missing:
+        raise KeyError(f"{ckpt_path}: no PCA buffers in the checkpoint (missing {missing[0]}); "
+                       "was the model trained with using_pca=True?")
+    got = {n: renamed[k].detach().to(torch.float32).cpu().numpy() for n, k in _PCA_KEYS.items()}
+    cs, ms, cr, mr = got["compT_scale"], got["means_scale"].reshape(-1), got["compT_rotat"], got["means_rotat"].reshape(-1)
+    if cs.ndim != 2 or cr.ndim != 2 or len(ms) != cs.shape[0] or len(mr) != cr.shape[0] or cs.shape[0] != 2 * cr.shape[0]:
+        raise ValueError(f"{ckpt_path}: inconsistent PCA buffer shapes {cs.shape} {ms.shape} {cr.shape} {mr.shape}")
+    if hparams is not None:
+        hp = hparams if isinstance(hparams, dict) else load_hparams(hparams)
+        want = pca_dims_from_hparams(hp)
+        have = (cs.shape[0], cr.shape[0], cs.shape[1], cr.shape[1])
+        if want != have:
+            raise ValueError(f"{ckpt_path}: PCA buffers {have} do not match hparams {want}")
+    return (np.ascontiguousarray(cs), np.ascontiguousarray(ms), np.ascontiguousarray(cr), np.ascontiguousarray(mr))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Foreign-topology inputs of ``set_template_mesh`` (viewer/frame.py:48-96; evaluate.sh --mesh_constraints / --mesh_tricorres)
+
+def read_constraints(path):
+    """frame.py:55-58: whitespace-separated vertex indices over any number of lines."""
+    with open(path) as fp:
+        return np.asarray([int(x) for x in " ".join(l.strip() for l in fp.readlines()).split()], dtype=np.uint32)
+
+
+def read_tricorres(path, n_faces):
+    """frame.py:59-90: first line = number of records, then ``src_tri,dst_tri,<anything>`` per line; the source triangles
+    of a target triangle keep file order.  -> dict(corr_count [n_faces], corr_faces [sum(max(count,1))]) exactly as the
+    reference builds them (a target triangle without sources gets count 0 and one placeholder entry 0)."""
+    by_dst = {}
+    with open(path) as fp:
+        count = 0
+        for i, line in enumerate(fp):
+            if i == 0:
+                count = int(line.strip())
+                continue
+            if count == 0:
+                break
+            src, dst, _ = line.strip().split(",")
+            by_dst.setdefault(int(dst), []).append(int(src))
+            count -= 1
+    corr_count, corr_faces = [], []
+    for i in range(n_faces):
+        srcs = by_dst.get(i)
+        if not srcs:
+            corr_count.append(0)
+            corr_faces.append(0)
+        else:
+            corr_count.append(len(srcs))
+            corr_faces += srcs
+    return dict(corr_count=np.asarray(corr_count, dtype=np.uint32), corr_faces=np.asarray(corr_faces, dtype=np.uint32))
+
+
+def load_template(template_path, constraints_path=None, corres_path=None):
+    """The inputs ``set_template_mesh`` (frame.py:48-96) hands to ``deformation.set_target``:
+    -> (verts [n,3] f32, faces [m,3] u32, c_indices or None, corres dict or None)."""
+    verts, faces = read_mesh(template_path, dtype=np.float32)
+    c = read_constraints(constraints_path) if constraints_path is not None else None
+    corres = read_tricorres(corres_path, len(faces)) if corres_path is not None else None
+    return verts, faces, c, corres
