@@ -234,6 +234,280 @@ def parity_check(out_rows, sample_ids, xs, xr, ref, tol, free_ids=None):
     return float(err.max()), err
 
 
+def _dist_setup():
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return torch, dist, world, rank, local, dev, barrier, max_over_ranks
+
+
+def run_config4(args):
+    """configs[3]: audio -> mel (+ deltas) -> random-init temporal-attention network -> PCA coefficients -> K1..K5, the
+    utterances sharded over the ranks; the network (plain PyTorch, not the product) is timed separately from the
+    dgrad -> mesh path.  One step = every utterance of this rank once."""
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "config 4: the reference network needs saber/librosa "
+                              "(absent here); the reference arm exists for the headline config only"}))
+        return
+    torch, dist, world, rank, local, dev, barrier, max_over_ranks = _dist_setup()
+    import deformation as D
+    from deformation import frontend as FE, sharded, workloads as W
+    V, F, nfv, nft = W.load_flame()
+    pca = W.random_pca(len(F), seed=1, zero_tris=nft)
+    rec = D.Reconstructor(V, F, cnsts=nfv, device=local)
+    rec.set_pca(*pca)
+    tol = 1e-6 * W.bbox_diag(V)
+    lo, hi = sharded.shard_range(args.utterances, rank, world)
+    n_utt, frames_per_utt = hi - lo, FRAMES_PER_SENTENCE
+    n = n_utt * frames_per_utt
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    feats_mod, net = FE.MelFeatures().to(dev), FE.build_network(seed=0, device=dev, coeff_gain=8.0)
+    audio = FE.band_limited_noise(n_utt, seconds=4.0, seed=100 + rank, device=dev)     # [n_utt, 32000], resident in HBM
+    speaker = (torch.arange(n_utt, device=dev) + lo) % net.num_speakers
+    xs = torch.empty((n, 85), dtype=torch.float32, device=dev)
+    xr = torch.empty((n, 180), dtype=torch.float32, device=dev)
+    out = torch.empty((n, N_VERTS, 3), dtype=torch.float32, device=dev)
+    UB = 8                                                      # utterances per network batch (1920 windows, 0.75 GB of features)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(n_batches=None):
+        t_feat = t_net = 0.0
+        marks = []
+        with torch.no_grad():
+            for bi, u0 in enumerate(range(0, n_utt, UB)):
+                if n_batches is not None and bi >= n_batches:
+                    break
+                u1 = min(n_utt, u0 + UB)
+                e0, e1, e2 = ev(), ev(), ev()
+                e0.record()
+                f = feats_mod(audio[u0:u1], frames_per_utt)                           # [u, 240, 64, 128, 3]
+                e1.record()
+                spk = speaker[u0:u1].repeat_interleave(frames_per_utt)
+                cs_, cr_ = net(f.reshape(-1, 64, 128, 3), spk)
+                xs[u0 * frames_per_utt: u1 * frames_per_utt] = cs_
+                xr[u0 * frames_per_utt: u1 * frames_per_utt] = cr_
+                e2.record()
+                marks.append((e0, e1, e2))
+            m0, m1 = ev(), ev()
+            m0.record()
+            if n_batches is None:
+                rec.decode_and_get_mesh(xs, xr, out=out)
+            else:
+                k = min(n, n_batches * UB * frames_per_utt)
+                rec.decode_and_get_mesh(xs[:k], xr[:k], out=out[:k])
+            m1.record()
+        torch.cuda.synchronize()
+        for e0, e1, e2 in marks:
+            t_feat += e0.elapsed_time(e1)
+            t_net += e1.elapsed_time(e2)
+        return t_feat, t_net, m0.elapsed_time(m1)
+
+    for _ in range(max(1, args.warmup)):
+        step(n_batches=2)                                       # warm-up: cuDNN plans, allocator, the path's workspaces
+    barrier()
+    steps = max(1, min(args.steps, 3))
+    launches0 = D.lib.sdfa_launch_count()
+    tf = tn = tm = 0.0
+    with ClockSampler(local) as clocks:
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(steps):
+            f_, n_, m_ = step()
+            tf, tn, tm = tf + f_ / steps, tn + n_ / steps, tm + m_ / steps
+        b.record()
+        barrier()
+    ms_step = max_over_ranks(a.elapsed_time(b) / steps)
+    tf, tn, tm = max_over_ranks(tf), max_over_ranks(tn), max_over_ranks(tm)
+    launches = (D.lib.sdfa_launch_count() - launches0) // steps
+    ids = np.unique(np.linspace(0, n - 1, 12).astype(np.int64))
+    sel = torch.from_numpy(ids).to(dev)
+    got, cxs, cxr = out[sel].cpu().numpy(), xs[sel].cpu().numpy(), xr[sel].cpu().numpy()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ref = CpuReference(V, F, nfv, pca, os.cpu_count() or 1)
+    worst, _ = parity_check(got, np.arange(len(ids)), cxs, cxr, ref, tol)
+    total = args.utterances * frames_per_utt
+    print(json.dumps({
+        "metric": "audio->mesh frames/s (config 4, FLAME 5023v)", "value": total / (ms_step * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 (network: TF32 matmuls allowed)", "data": "synthetic",
+        "config": {"workload": f"configs[3]: {args.utterances} utterances x 4 s band-limited noise at 8 kHz -> 240 windows "
+                               "[64,128,3] (mel + delta + delta-delta) each -> random-init network of config/model/dgrad.py "
+                               "-> coefficients [85]+[180] -> decode + reconstruction, FLAME default mask",
+                   "utterances_per_gpu": n_utt, "frames_per_gpu": n, "parallelism": f"utterances sharded x{world}",
+                   "network_batch_windows": UB * frames_per_utt},
+        "stage_ms_per_step": {"features_ms": tf, "network_ms": tn, "dgrad_to_mesh_ms": tm},
+        "dgrad_to_mesh": {"value": n * world / (tm * 1e-3), "unit": "frames/s",
+                          "what": "decode_and_get_mesh on the network's coefficients, device resident, same step"},
+        "network": {"value": n * world / ((tf + tn) * 1e-3), "unit": "frames/s", "what": "features + network, plain PyTorch (not the product)"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "parity": {"max_abs_m": worst, "tol": tol, "frames": [int(i) for i in ids], "checker": ref.kind,
+                   "what": "sampled frames of the timed output vs fp32 F.linear decode + reference get_mesh on the network's own coefficients",
+                   "ok": bool(worst <= tol)},
+    }))
+    if dist is not None:
+        dist.destroy_process_group()
+    if worst > tol:
+        sys.exit(1)
+
+
+def run_config5(args):
+    """configs[4]: twice-subdivided FLAME (79 936 v / 159 616 tris, 20 653 unknowns, propagated mask), synthetic iid dgrad
+    resident in HBM in the reference layout, frames sharded over the ranks (large-factor solve: the SIMT sweeps)."""
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        W = load_workloads()
+        from oracle import ref_loader
+        V, F, c = W.flame_sub2()
+        nt = min(4, os.cpu_count() or 1)
+        rs = ref_loader.RefSolver(nt)
+        rs.set_target(V, F, cnsts=c)
+        dg = W.iid_dgrad(2 * nt, len(F), sigma=0.01, seed=5)
+        rs.get_mesh_batch(dg[:nt], V[c])
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            rs.get_mesh_batch(dg, V[c])
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        v = len(dg) / dt
+        print(json.dumps({"impl": "reference", "metric": "dgrad->mesh frames/s (subdivided FLAME 79936v)", "value": v,
+                          "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": "configs[4] (bounded sample)"},
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": nt, "kind": "reference",
+                                           "sample": f"{len(dg)} frames per step on {nt} host threads, one reference solver each"},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+    torch, dist, world, rank, local, dev, barrier, max_over_ranks = _dist_setup()
+    import deformation as D
+    from deformation import sharded, workloads as W
+    V, F, c = W.flame_sub2()
+    rec = D.Reconstructor(V, F, cnsts=c, device=local)
+    tol = 1e-6 * W.bbox_diag(V)
+    lo, hi = sharded.shard_range(args.frames, rank, world)
+    n = hi - lo
+    width = len(F) * 9
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    dgrad = torch.empty((n, width), dtype=torch.float32, device=dev)         # 5.75 MB per frame: 57 GB for 10 000 frames
+    for a in range(0, n, 256):
+        dgrad[a:a + 256].normal_(0.0, 0.01, generator=g)
+    out = torch.empty((n, len(V), 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    steps = max(1, args.steps)
+    for _ in range(max(1, args.warmup)):
+        rec.get_mesh_batch(dgrad, out=out)
+    barrier()
+    launches0 = D.lib.sdfa_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with ClockSampler(local) as clocks:
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            rec.get_mesh_batch(dgrad, out=out)
+            b.record()
+        barrier()
+    ms_step = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / steps)
+    launches = (D.lib.sdfa_launch_count() - launches0) // steps
+    rec.set_timing(True)
+    stage = {"assembly_ms": 0.0, "solve_ms": 0.0, "output_ms": 0.0}
+    for i in range(3):
+        rec.get_mesh_batch(dgrad, out=out)
+        if i:
+            t = rec.last_timing()
+            for k in stage:
+                stage[k] += t[k] / 2
+    rec.set_timing(False)
+    stage = {k: max_over_ranks(v) for k, v in stage.items()}
+    ids = np.unique(np.array([0, 1, n // 2, n - 1]))
+    sel = torch.from_numpy(ids).to(dev)
+    got, dg_s = out[sel].cpu().numpy(), dgrad[sel].cpu().numpy()
+    # end to end through the host-buffer call on a bounded slice (pinned host dgrad in, host vertices out)
+    ne = min(n, 512)
+    dg_h = dgrad[:ne].cpu().pin_memory().numpy()
+    out_h = torch.empty((ne, len(V), 3), dtype=torch.float32).pin_memory().numpy()
+    rec.get_mesh_batch(dg_h, out=out_h)
+    barrier()
+    t0 = time.perf_counter()
+    rec.get_mesh_batch(dg_h, out=out_h)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    from oracle import ref_loader
+    from oracle.dgrad_oracle import TriangleDeformationOracle
+    chk = ref_loader.RefSolver(1) if ref_loader.ref_available() else TriangleDeformationOracle()
+    chk.set_target(V, F, cnsts=c)
+    worst = 0.0
+    for i in range(len(ids)):
+        want = chk.get_mesh(dg_s[i].astype(np.float64), vert_cnsts=V[c])
+        worst = max(worst, float(np.abs(got[i] - want).max()))
+    peaks, peak_src = measured_peaks()
+    n_active = rec.n_active
+    bytes_path = 36 * n_active + 12 * len(V)                                  # 2 457 408 B/frame, SURVEY 8(d)
+    bytes_solve = 2 * 12 * rec.n_free
+    total = args.frames
+    dom = max(stage, key=lambda k: stage[k])
+    kb = {"assembly_ms": ("k_assemble_gather (K2)", 36 * n_active + 12 * rec.n_free), "solve_ms": ("k_solve (K3, SIMT sweeps)", bytes_solve),
+          "output_ms": ("k_output (K5)", 12 * rec.n_free + 12 * len(V))}
+    path_gbs = bytes_path * total / (ms_step * 1e-3) / 1e9
+    ach = kb[dom][1] * n / (stage[dom] * 1e-3) / 1e9
+    result = {
+        "metric": "dgrad->mesh frames/s (subdivided FLAME 79936v)", "value": total / (ms_step * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[4]: FLAME subdivided twice ({len(V)} v / {len(F)} tris, {rec.n_free} unknowns, "
+                               f"{n_active} active triangles, nnz(L) {rec.nnz_l}), {args.frames} frames iid sigma 0.01 dgrad resident "
+                               "in HBM (device RNG), reference layout", "frames_per_gpu": n,
+                   "parallelism": f"frames sharded x{world}", "l2": "flushed between timed iterations; input 5.7 MB per frame"},
+        "e2e": {"value": ne * world / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(ne * width * 4),
+                "d2h_bytes_per_step": int(ne * len(V) * 12), "ms_per_step": e2e_ms,
+                "api": f"get_mesh_batch(numpy) -> sdfa_reconstruct_host on a bounded slice of {ne} frames per GPU, pinned buffers"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "parity": {"max_abs_m": worst, "tol": tol, "frames": [int(i) for i in ids],
+                   "checker": "reference" if ref_loader.ref_available() else "port", "ok": bool(worst <= tol)},
+        "roofline": {"kernel": kb[dom][0], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_frame": kb[dom][1], "peak_source": peak_src},
+        "roofline_path": {"what": f"whole call, {bytes_path} algorithmic B/frame (SURVEY 8d)", "achieved": path_gbs,
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": path_gbs / peaks["hbm_gbs"]},
+        "kernel_ms_per_step": stage, "frames_per_solve_tile": int(rec.debug("stats")[14]),
+    }
+    print(json.dumps(result))
+    if dist is not None:
+        dist.destroy_process_group()
+    if worst > tol:
+        sys.exit(1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,7 +519,16 @@ def main():
                          "= 11.98 per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather leg at N > 1")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json configs[] entry (1-based): 2 = the headline workload (default), 4 = audio -> mel -> "
+                         "network -> mesh end to end, 5 = subdivided FLAME (large-factor solve)")
+    ap.add_argument("--utterances", type=int, default=1000, help="config 4: 4 s utterances in total, sharded over the ranks")
+    ap.add_argument("--frames", type=int, default=10000, help="config 5: frames in total, sharded over the ranks")
     args = ap.parse_args()
+    if args.config == 4:
+        return run_config4(args)
+    if args.config == 5:
+        return run_config5(args)
     if args.impl == "reference":
         return run_reference(args)
 

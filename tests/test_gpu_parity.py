@@ -359,26 +359,29 @@ def test_chunk_pipeline_is_bit_identical(rec, flame):
 
 
 def test_config4_network_to_mesh_on_device(rec, chk, flame):
-    """Config 4 in miniature: audio features -> random-init temporal network (plain torch, stands in for
-    speech_anime's model, config/model/dgrad.py:60-86) -> PCA coefficients -> K1..K5, everything staying on the
-    device; checked against fp32 F.linear decode + the reference solver on the same coefficients."""
+    """Config 4 in miniature: synthetic audio -> mel + deltas -> the reference's network architecture, random init
+    (deformation/frontend.py restates speech_anime/config/model/dgrad.py:56-100 in plain torch) -> PCA coefficients ->
+    K1..K5, everything staying on the device; checked against fp32 F.linear decode + the reference solver on the
+    network's own coefficients."""
     import torch
+    from deformation import frontend as FE
     V, F, nfv, tol = flame["V"], flame["F"], flame["nfv"], flame["tol"]
     cs, ms, cr, mr = W.random_pca(len(F), seed=1)
     rec.set_pca(cs, ms, cr, mr)
-    torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Conv1d(128 * 3, 256, 5, padding=2), torch.nn.ReLU(),
-                              torch.nn.Conv1d(256, 85 + 180, 5, padding=2)).cuda()
-    feats = torch.randn(2, 128 * 3, 240, device="cuda")        # 2 utterances x 240 frames of mel + deltas
+    dev = torch.device("cuda", 0)
+    audio = FE.band_limited_noise(2, seconds=2.0, seed=4, device=dev)
     with torch.no_grad():
-        y = net(feats).permute(0, 2, 1).reshape(-1, 85 + 180)  # [480, 265]
-    xs, xr = y[:, :85].contiguous(), y[:, 85:].contiguous()
-    out = rec.decode_and_get_mesh(xs, xr)
-    assert out.is_cuda and out.shape == (480, 5023, 3)
+        feats = FE.MelFeatures().to(dev)(audio, 120)                 # [2, 120, 64, 128, 3]
+        net = FE.build_network(seed=0, device=dev, coeff_gain=8.0)
+        spk = torch.tensor([1, 6], device=dev).repeat_interleave(120)
+        xs, xr = net(feats.reshape(-1, 64, 128, 3), spk)
+    assert xs.shape == (240, 85) and xr.shape == (240, 180) and float(xs.std()) > 0.05
+    out = rec.decode_and_get_mesh(xs.contiguous(), xr.contiguous())
+    assert out.is_cuda and out.shape == (240, 5023, 3)
     lin_s = torch.nn.functional.linear(xs.cpu(), torch.from_numpy(cs), torch.from_numpy(ms))
     lin_r = torch.nn.functional.linear(xr.cpu(), torch.from_numpy(cr), torch.from_numpy(mr))
-    dg = torch.cat((lin_s.view(480, -1, 6), lin_r.view(480, -1, 3)), dim=-1).view(480, -1).numpy()
-    for i in (0, 239, 240, 479):
+    dg = torch.cat((lin_s.view(240, -1, 6), lin_r.view(240, -1, 3)), dim=-1).view(240, -1).numpy()
+    for i in (0, 119, 120, 239):
         ref = chk.get_mesh(dg[i].astype(np.float64), vert_cnsts=V[nfv])
         assert np.abs(out[i].cpu().numpy() - ref).max() <= tol, i
 
