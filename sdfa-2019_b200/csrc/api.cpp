@@ -266,7 +266,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
 
 // "key=value;key=value" -> map; unknown keys are an error so that a typo does not silently select the default
 static int parse_options(const char *options, std::map<std::string, std::string> &kv) {
-    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf"};
+    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf", "asm_gather"};
     const std::string text = options ? options : "";
     size_t at = 0;
     while (at < text.size()) {
@@ -363,6 +363,10 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
     {
         const std::string pc = setting("pipe_chunk", "SDFA_PIPE_CHUNK");
         h->pipe_chunk = pc.empty() ? -1 : std::atoi(pc.c_str());
+    }
+    {
+        const std::string g = setting("asm_gather", "SDFA_ASM_GATHER");
+        h->dev.asm_gather_gen = g.empty() ? 2 : std::atoi(g.c_str());
     }
     h->dev.device = device;
     h->dev.n_verts = n_verts; h->dev.n_tris = n_tris; h->dev.n_cnsts = n_cnsts;

@@ -476,21 +476,146 @@ __global__ void __launch_bounds__(ASM_G_THREADS) k_assemble_gather(AsmParams P) 
     }
 }
 
+// Gather variant, second generation: the same walk, colours and packed two-frames-per-lane transform as k_assemble, fed
+// straight from a [frame][triangle][9] tensor.  An equation's input is one 36-byte record per frame; what is copied is the
+// 16-byte aligned 48-byte span around it (rows are 16-byte aligned: frame_stride % 4 == 0, checked by the launcher).  A
+// warp keeps the spans of its NEXT TWO equations in flight as 16-byte cp.async copies (six per lane and equation, no
+// registers held; chunk q = lane + 32 k of the [frame][3 chunks] image, so consecutive lanes copy consecutive chunks of a
+// span) into a private two-stage ring, and frees a stage as soon as its lane has pulled its two frames' spans into
+// registers with six LDS.128 (conflict free: 3 l + c is distinct mod 8 over a quarter warp).  The lane's two frames are
+// l and l + 32 -- position 2l / 2l + 1 of an accumulator line -- and the write-out undoes that pairing.
+// One CTA per SM: accumulator 86 KB + rings 96 KB, i.e. 96 KB of loads in flight per SM (three stages when the row blocks are small enough).
+constexpr int AG_REC = 12 * COMPACT_TILE;            // floats per image: [frame][12]
+constexpr int AG_COPIES = AG_REC / 4 / 32;           // 16-byte copies per lane and equation
+
+template <int SHIFT>
+__device__ __forceinline__ void ag_select(const float4 (&a)[3], const float4 (&b)[3], float2 (&d)[9]) {
+    const float wa[12] = {a[0].x, a[0].y, a[0].z, a[0].w, a[1].x, a[1].y, a[1].z, a[1].w, a[2].x, a[2].y, a[2].z, a[2].w};
+    const float wb[12] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w, b[2].x, b[2].y, b[2].z, b[2].w};
+#pragma unroll
+    for (int j = 0; j < 9; ++j) d[j] = make_float2(wa[SHIFT + j], wb[SHIFT + j]);
+}
+
+template <int AG_STAGES>
+__global__ void __launch_bounds__(ASM_THREADS, 1) k_assemble_gather2(AsmParams P) {
+    extern __shared__ __align__(16) float acc[];                     // [row][3][64], frame pairing (l, l + 32)
+    constexpr int CT = COMPACT_TILE;
+    const int4 blk = P.blocks[blockIdx.x];
+    const int n_rows = blk.w - blk.z;
+    const int frame0 = blockIdx.y * CT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int acc_floats = (P.max_rows * 3 * CT + 3) & ~3;
+    float *ring = acc + acc_floats + warp * (AG_STAGES * AG_REC);
+    int4 *walk_sh = reinterpret_cast<int4 *>(acc + acc_floats + ASM_WARPS * (AG_STAGES * AG_REC));
+    for (int i = threadIdx.x; i < n_rows * 3 * CT; i += ASM_THREADS) acc[i] = 0.f;
+    for (int i = lane; i < AG_STAGES * AG_REC; i += 32) ring[i] = 0.f;         // frames past the batch read zeros
+    {
+        const int w0 = P.warp_ptr[blockIdx.x * ASM_WARPS], w1 = P.warp_ptr[blockIdx.x * ASM_WARPS + ASM_WARPS];
+        for (int i = threadIdx.x; i < w1 - w0; i += ASM_THREADS) walk_sh[i] = P.walk[w0 + i];
+    }
+    const int4 *walk = walk_sh + (P.warp_ptr[blockIdx.x * ASM_WARPS + warp] - P.warp_ptr[blockIdx.x * ASM_WARPS]);
+    // chunk q = lane + 32 k of an image is chunk q % 3 of frame q / 3: its offset inside the tile's rows, once per lane
+    int off[AG_COPIES];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int k = 0; k < AG_COPIES; ++k) {
+        const int q = lane + 32 * k, f = q / 3;
+        off[k] = (int)(f * P.frame_stride) + 4 * (q - 3 * f);
+        if (frame0 + f < P.n_frames) valid |= 1u << k;
+    }
+    const float *tile_rows = P.dgrad + (long long)frame0 * P.frame_stride;
+    const uint32_t ring_u32 = smem_u32(ring) + 16u * lane;
+    __syncthreads();                                                 // accumulator and rings zeroed, walks in shared memory
+    const int4 *wi = walk;                                           // issue pointer: AG_STAGES entries ahead of the transform
+    auto issue = [&](int stage) {
+        const int4 ent = *wi;
+        if (ent.x != ASM_SCHED_END) ++wi;
+        if (ent.x >= 0 && ent.y >= 0) {
+            const float *src = tile_rows + ((long long)ent.y * 9 & ~3LL);
+            const uint32_t dst = ring_u32 + 4u * AG_REC * (uint32_t)stage;
+#pragma unroll
+            for (int k = 0; k < AG_COPIES; ++k)
+                if (valid >> k & 1u)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * k), "l"(src + off[k]) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < AG_STAGES; ++i) issue(i);
+    for (int n = 0, stage = 0;; ++n, stage = stage + 1 == AG_STAGES ? 0 : stage + 1) {
+        const int4 ent = *walk++;
+        asm volatile("cp.async.wait_group %0;" ::"n"(AG_STAGES - 1) : "memory");   // this lane's copies of entry n have landed ...
+        __syncwarp();                                                // ... and so have the other lanes'
+        const bool rec = ent.x >= 0 && ent.y >= 0;
+        float4 wa[3], wb[3];
+        if (rec) {
+            const float4 *st = reinterpret_cast<const float4 *>(ring + stage * AG_REC);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { wa[c] = st[3 * lane + c]; wb[c] = st[3 * (lane + 32) + c]; }
+        }
+        __syncwarp();                                                // the stage is free: refill it with entry n + AG_STAGES
+        issue(stage);
+        if (ent.x == ASM_SCHED_END) break;
+        if (ent.x == ASM_SCHED_BARRIER) { __syncthreads(); continue; }
+        float2 d[9];
+        if (rec) {
+            switch ((ent.y * 9) & 3) {
+                case 0: ag_select<0>(wa, wb, d); break;
+                case 1: ag_select<1>(wa, wb, d); break;
+                case 2: ag_select<2>(wa, wb, d); break;
+                default: ag_select<3>(wa, wb, d); break;
+            }
+        }
+        const float4 m0 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2), m1 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2 + 1);
+        eq_apply2(acc, lane, P.mode, ent.y, d, m0, m1);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // write-out: position 2l of a line is frame l, 2l + 1 is frame l + 32
+    const int fa = frame0 + lane, fb = fa + 32;
+    float *dst_a = P.rhs + (long long)(fa / P.L.FL) * P.L.tile_stride + fa % P.L.FL;
+    float *dst_b = P.rhs + (long long)(fb / P.L.FL) * P.L.tile_stride + fb % P.L.FL;
+    const float2 *acc2 = reinterpret_cast<const float2 *>(acc) + lane;
+    for (int line = warp; line < n_rows * 3; line += ASM_WARPS) {
+        const int r = line / 3, c = line - 3 * r;
+        const float2 v = acc2[line * (CT / 2)];
+        const long long o = (long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride;
+        dst_a[o] = fa < P.n_frames ? v.x : 0.f;
+        dst_b[o] = fb < P.n_frames ? v.y : 0.f;
+    }
+}
+
+size_t assemble_gather2_smem(const DevicePlan &d, int stages) {
+    return (size_t)((d.asm_max_rows * 3 * COMPACT_TILE + 3) & ~3) * sizeof(float) + (size_t)ASM_WARPS * stages * AG_REC * sizeof(float) +
+           (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4);
+}
+
 cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long frame_stride, bool staged,
                             int n_frames, int mode, float *rhs, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     AsmParams P{d.asm_blocks, d.asm_walk, d.asm_warp_ptr, d.asm_eq_meta, d.asm_row_perm, d.asm_eq_src_local, d.asm_row_ptr, d.asm_inc,
                 d.asm_max_eq, dgrad, frame_stride, d.compact_s_rows, rhs, n_frames, mode, d.asm_max_rows, d.asm_max_walk, d.layout};
-    const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
-    const size_t smem = staged ? (size_t)d.asm_max_rows * 3 * COMPACT_TILE * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4)
-                               : (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * ASM_GPAD + d.asm_max_eq) * sizeof(float) +
-                                 (((size_t)d.asm_max_eq * 3 * sizeof(uint16_t) + 15) & ~(size_t)15);
-    cudaError_t e = staged ? cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)d.n_asm_blocks, (unsigned)((n_frames + COMPACT_TILE - 1) / COMPACT_TILE));
-    if (staged) k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
-    else {
+    if (staged) {
+        const size_t smem = (size_t)d.asm_max_rows * 3 * COMPACT_TILE * sizeof(float) + (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4);
+        cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
+    } else if (d.asm_gather_gen >= 2 && (long long)(COMPACT_TILE - 1) * frame_stride + 12 < 0x7fffffffLL && frame_stride % 4 == 0 &&
+               reinterpret_cast<uintptr_t>(dgrad) % 16 == 0) {   // 16-byte copies of aligned spans
+        // as many stages (equations in flight per warp) as fit beside the accumulator
+        const bool three = assemble_gather2_smem(d, 3) <= (size_t)227 * 1024;
+        const size_t smem = assemble_gather2_smem(d, three ? 3 : 2);
+        auto kern = three ? k_assemble_gather2<3> : k_assemble_gather2<2>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, ASM_THREADS, smem, stream>>>(P);
+    } else {
+        const size_t plane = (size_t)((3 * d.asm_max_eq + 3) & ~3);
+        const size_t smem = (6 * plane + 2 * (size_t)d.asm_max_eq * 9 + (size_t)d.asm_max_rows * 3 * ASM_GPAD + d.asm_max_eq) * sizeof(float) +
+                            (((size_t)d.asm_max_eq * 3 * sizeof(uint16_t) + 15) & ~(size_t)15);
+        cudaError_t e = cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         // whole 32-frame groups are covered so that the scratch's idle lanes of a partial group hold zeros
         grid.y = (unsigned)((n_frames + 31) / 32 * (32 / ASM_GF));
         k_assemble_gather<<<grid, ASM_G_THREADS, smem, stream>>>(P);
