@@ -190,6 +190,58 @@ class GatherPipeline:
         return out if receiver else None
 
 
+class PeerGather:
+    """The gather of the vertex buffers without a collective library on the data path: every rank's result buffer is
+    allocated as symmetric memory (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped into every peer
+    over NVLink), each chunk of free rows is reconstructed straight into this rank's block of its own buffer, and a side
+    stream pushes the finished chunk into the same block of every receiver's buffer with peer-to-peer copies (copy
+    engines: no SMs, no staging buffer, no unpack) while the next chunk is computed.  One device-side barrier per call.
+
+    ``mode="all"``: every rank ends up with [world * n_local, n_free, 3] (rank-major); ``mode="root"``: only ``dst``.
+    The returned tensor is the symmetric buffer itself: consume (or copy) it before the next ``run``.
+    Raises at construction if the box cannot map peer memory (then use ``GatherPipeline``: NCCL)."""
+
+    def __init__(self, rec, n_local, chunk_frames=9472, group=None, mode="all", dst=0):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        assert mode in ("all", "root")
+        self.rec, self.n_local, self.chunk, self.mode, self.dst = rec, int(n_local), int(chunk_frames), mode, dst
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        dev = torch.device("cuda", rec.device)
+        shape = (self.world * self.n_local, rec.n_free, 3)
+        self.buf = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.peers = [self.hdl.get_buffer(r, shape, torch.float32) for r in range(self.world)]
+        self.side = torch.cuda.Stream(dev)
+        self.bytes_pushed_per_run = 0
+
+    def run(self, compute, inputs):
+        import torch
+        n, lo = self.n_local, self.rank * self.n_local
+        assert inputs[0].shape[0] == n, "every rank holds n_local frames per call"
+        main = torch.cuda.current_stream(self.buf.device)
+        targets = [r for r in range(self.world) if r != self.rank and (self.mode == "all" or r == self.dst)]
+        self.hdl.barrier()                                 # every receiver is done with the previous result
+        pushed = 0
+        for c0 in range(0, n, self.chunk):
+            nf = min(self.chunk, n - c0)
+            mine = self.buf[lo + c0: lo + c0 + nf]
+            compute(*[x[c0:c0 + nf] for x in inputs], out=mine)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                for r in targets:
+                    self.peers[r][lo + c0: lo + c0 + nf].copy_(mine, non_blocking=True)
+                    pushed += mine.numel() * 4
+        main.wait_stream(self.side)
+        self.hdl.barrier()                                 # everybody's pushes have landed everywhere
+        self.bytes_pushed_per_run = pushed
+        return self.buf if (self.mode == "all" or self.rank == self.dst) else None
+
+
 class _null:
     def __enter__(self):
         return self

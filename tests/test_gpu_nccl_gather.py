@@ -42,6 +42,13 @@ def _worker(rank, world, port, n_local, chunk, q):
             got = pipe.run(lambda a, b, out: rec.decode_and_get_mesh(a, b, out=out, free_only=True), [xs_d, xr_d])
         torch.cuda.synchronize()
         res[(mode, expand)] = None if got is None else got.cpu().numpy()
+    # the same gather without NCCL on the data path: symmetric memory + peer-to-peer pushes (deformation/sharded.py: PeerGather)
+    for mode in ("all", "root"):
+        pg = sharded.PeerGather(rec, n_local, chunk_frames=chunk, mode=mode, dst=0)
+        for _ in range(2):
+            got = pg.run(lambda a, b, out: rec.decode_and_get_mesh(a, b, out=out, free_only=True), [xs_d, xr_d])
+        torch.cuda.synchronize()
+        res[("p2p", mode)] = None if got is None else got.cpu().numpy()
     # the plain collectives on device tensors as well (ragged shards: 7 frames over 2 ranks)
     a, b = sharded.shard_range(7, rank, world)
     local = rec.decode_and_get_mesh(torch.from_numpy(xs[a:b]).cuda(), torch.from_numpy(xr[a:b]).cuda())
@@ -84,9 +91,12 @@ def test_nccl_gather_of_free_rows_two_gpus(flame):
         assert np.array_equal(r[("all", False)], ref[:, ids])
         assert np.array_equal(r[("all", True)], ref)
         assert np.array_equal(r["ragged_all"], ref[:7])
+        assert np.array_equal(r[("p2p", "all")], ref[:, ids])         # peer-to-peer pushes into symmetric memory
+        assert (r[("p2p", "root")] is None) == (rank != 0)
         if rank == 0:
             assert np.array_equal(r[("root", True)], ref)
             assert np.array_equal(r["ragged_root"], ref[:7])
+            assert np.array_equal(r[("p2p", "root")], ref[:, ids])
         else:
             assert r[("root", True)] is None and r["ragged_root"] is None
     if ref_loader.ref_available():
