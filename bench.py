@@ -628,7 +628,11 @@ def main():
     free_n = free_h.numpy()
     e2e_free_ms = e2e(lambda: rec.decode_and_get_mesh(xs_n, xr_n, out=free_n, free_only=True))
     free_samples = free_n[sample_ids].copy()
-    del free_h, free_n
+    # what the host link gives for the same bytes with nothing else going on: plain pinned device->host copies of the
+    # free rows, all ranks at once (the e2e number cannot exceed it)
+    free_d = torch.empty((n, N_FREE, 3), dtype=torch.float32, device=dev)
+    d2h_ms = e2e(lambda: (free_h.copy_(free_d, non_blocking=True), torch.cuda.synchronize()))
+    del free_h, free_n, free_d
     full_h = torch.empty((n, N_VERTS, 3), dtype=torch.float32).pin_memory()
     full_n = full_h.numpy()
     e2e_full_ms = e2e(lambda: rec.decode_and_get_mesh(xs_n, xr_n, out=full_n))
@@ -778,7 +782,10 @@ def main():
                 "d2h_bytes_per_step": int(n * N_FREE * 12), "ms_per_step": e2e_free_ms,
                 "api": "deformation.Reconstructor.decode_and_get_mesh(numpy, free_only=True) -> "
                        "sdfa_decode_reconstruct_free_host: pinned host coefficients in, the 1261 free vertices of every frame "
-                       "out (the 3762 constrained rows are the caller's own vert_cnsts constants)"},
+                       "out (the 3762 constrained rows are the caller's own vert_cnsts constants)",
+                "host_link_ceiling": {"value": total / (d2h_ms * 1e-3), "unit": "frames/s", "ms_per_step": d2h_ms,
+                                      "aggregate_d2h_gbs": world * n * N_FREE * 12 / (d2h_ms * 1e-3) / 1e9,
+                                      "what": "plain pinned cudaMemcpy D2H of the same free-row bytes, all ranks at once, no kernels"}},
         "e2e_full_layout": {"value": total / (e2e_full_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_full_ms,
                             "d2h_bytes_per_step": int(n * N_VERTS * 12),
                             "api": "decode_and_get_mesh(numpy) -> sdfa_decode_reconstruct_host, pinned buffers, all 5023 rows"},

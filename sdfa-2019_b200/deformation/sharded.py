@@ -214,7 +214,7 @@ class PeerGather:
         self.buf = symm_mem.empty(shape, dtype=torch.float32, device=dev)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.peers = [self.hdl.get_buffer(r, shape, torch.float32) for r in range(self.world)]
-        self.side = torch.cuda.Stream(dev)
+        self.sides = [torch.cuda.Stream(dev) for _ in range(2)]      # two pushes in flight (two copy engines)
         self.bytes_pushed_per_run = 0
 
     def run(self, compute, inputs):
@@ -222,7 +222,9 @@ class PeerGather:
         n, lo = self.n_local, self.rank * self.n_local
         assert inputs[0].shape[0] == n, "every rank holds n_local frames per call"
         main = torch.cuda.current_stream(self.buf.device)
-        targets = [r for r in range(self.world) if r != self.rank and (self.mode == "all" or r == self.dst)]
+        # staggered order: in phase s every rank pushes to rank + s, so no receiver has two senders at once
+        targets = [(self.rank + s) % self.world for s in range(1, self.world)]
+        targets = [r for r in targets if self.mode == "all" or r == self.dst]
         self.hdl.barrier()                                 # every receiver is done with the previous result
         pushed = 0
         for c0 in range(0, n, self.chunk):
@@ -231,12 +233,14 @@ class PeerGather:
             compute(*[x[c0:c0 + nf] for x in inputs], out=mine)
             ev = torch.cuda.Event()
             ev.record(main)
-            self.side.wait_event(ev)
-            with torch.cuda.stream(self.side):
-                for r in targets:
+            for i, r in enumerate(targets):
+                side = self.sides[i % len(self.sides)]
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
                     self.peers[r][lo + c0: lo + c0 + nf].copy_(mine, non_blocking=True)
-                    pushed += mine.numel() * 4
-        main.wait_stream(self.side)
+                pushed += mine.numel() * 4
+        for side in self.sides:
+            main.wait_stream(side)
         self.hdl.barrier()                                 # everybody's pushes have landed everywhere
         self.bytes_pushed_per_run = pushed
         return self.buf if (self.mode == "all" or self.rank == self.dst) else None
