@@ -266,7 +266,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
 
 // "key=value;key=value" -> map; unknown keys are an error so that a typo does not silently select the default
 static int parse_options(const char *options, std::map<std::string, std::string> &kv) {
-    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf", "asm_gather"};
+    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf", "asm_gather", "decode"};
     const std::string text = options ? options : "";
     size_t at = 0;
     while (at < text.size()) {
@@ -367,6 +367,9 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
     {
         const std::string g = setting("asm_gather", "SDFA_ASM_GATHER");
         h->dev.asm_gather_gen = g.empty() ? 2 : std::atoi(g.c_str());
+        const std::string dk = setting("decode", "SDFA_DECODE");
+        if (!dk.empty() && dk != "f16" && dk != "tf32") { delete h; return fail(SDFA_ERR_ARG, "sdfa_create: decode must be f16 or tf32"); }
+        h->dev.decode_fp16 = dk != "tf32";
     }
     h->dev.device = device;
     h->dev.n_verts = n_verts; h->dev.n_tris = n_tris; h->dev.n_cnsts = n_cnsts;
@@ -474,6 +477,7 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
             if ((r = upload_eq_src(h))) return r;
             if (!p.use_tensor) CUDA_TRY(configure_solve(d));
             CUDA_TRY(configure_decode_tc(d));
+            CUDA_TRY(configure_decode_tc16(d));
             if (std::getenv("SDFA_SOLVE_PROFILE")) {
                 std::vector<long long> zero(std::max((size_t)h->dev.sm_count * 4 * 8, (3 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
                 if ((r = upload_mut(h, zero, &d.solve_prof))) return r;
@@ -814,6 +818,14 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     const int mt_r = tc_build_basis(compT_rotat, means_rotat, k_rotat, src_r, img_r);
     if (mt_s * tc_rows_per_tile() != d.compact_s_rows || mt_r * tc_rows_per_tile() != d.compact_stride - d.compact_s_rows)
         return fail(SDFA_ERR_STATE, "sdfa_set_pca: compact layout and decode tiles disagree");
+    // second-generation decode: scaled FP16 hi/lo images of the same rows (decode_tc16.cu), when the widths fit it
+    const bool use16 = d.decode_fp16 && tc16_fits(k_scale, k_rotat);
+    std::vector<uint16_t> img16_s, img16_r;
+    float inv_sw[2] = {1.f, 1.f};
+    if (use16) {
+        tc16_build_basis(compT_scale, means_scale, k_scale, src_s, img16_s, &inv_sw[0]);
+        tc16_build_basis(compT_rotat, means_rotat, k_rotat, src_r, img16_r, &inv_sw[1]);
+    }
     // replace the previous basis (every call used to leak ~60 MB): nothing may still be reading it
     if ((rc = wait_async(h))) return rc;
     for (auto &w : h->ws) if (w.stream) CUDA_TRY(cudaStreamSynchronize(w.stream));
@@ -821,6 +833,8 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
     for (void *p : h->pca_allocs) cudaFree(p);
     h->pca_allocs.clear();
     d.wfull_scale = d.mfull_scale = d.wfull_rotat = d.mfull_rotat = d.tc_w_scale = d.tc_w_rotat = nullptr;
+    d.tc16_w_scale = d.tc16_w_rotat = nullptr;
+    d.tc16_ready = false;
     auto put = [&](const float *src, size_t n, float **dst) -> int {
         void *p = nullptr;
         CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(float), 16)));
@@ -833,6 +847,17 @@ int sdfa_set_pca(sdfa_handle *h, const float *compT_scale, const float *means_sc
         (rc = put(compT_rotat, (size_t)nt * 3 * k_rotat, &d.wfull_rotat)) || (rc = put(means_rotat, (size_t)nt * 3, &d.mfull_rotat)) ||
         (rc = put(img_s.data(), img_s.size(), &d.tc_w_scale)) || (rc = put(img_r.data(), img_r.size(), &d.tc_w_rotat)))
         return rc;
+    if (use16) {
+        float *p16s = nullptr, *p16r = nullptr;       // uploaded as raw bytes (two halves per float)
+        if ((rc = put(reinterpret_cast<const float *>(img16_s.data()), img16_s.size() / 2, &p16s)) ||
+            (rc = put(reinterpret_cast<const float *>(img16_r.data()), img16_r.size() / 2, &p16r)))
+            return rc;
+        d.tc16_w_scale = reinterpret_cast<const uint16_t *>(p16s);
+        d.tc16_w_rotat = reinterpret_cast<const uint16_t *>(p16r);
+        d.tc16_inv_sw[0] = inv_sw[0];
+        d.tc16_inv_sw[1] = inv_sw[1];
+        d.tc16_ready = true;
+    }
     d.k_scale = k_scale; d.k_rotat = k_rotat;
     d.tc_mt_scale = mt_s; d.tc_mt_rotat = mt_r;
     d.n_pca_tris = nt;
@@ -846,11 +871,11 @@ static int decode_reconstruct_core(sdfa_handle *h, sdfa_handle::Workspace &w, co
     const long long stride = h->dev.compact_stride;
     const int chunk = pipe_chunk(h, n_frames), cap = chunk ? chunk : n_frames;
     if ((rc = grow(&w.dgrad_c, &w.dgrad_c_cap, ((size_t)cap + COMPACT_TILE - 1) / COMPACT_TILE * COMPACT_TILE * stride))) return rc;
-    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(cap, h->dev.k_scale)))) return rc;
-    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(cap, h->dev.k_rotat)))) return rc;
+    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, std::max(tc_ximg_floats(cap, h->dev.k_scale), tc16_ximg_floats(cap, h->dev.k_scale))))) return rc;
+    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, std::max(tc_ximg_floats(cap, h->dev.k_rotat), tc16_ximg_floats(cap, h->dev.k_rotat))))) return rc;
     auto decode = [&](int f0, int nf) -> int {
-        CUDA_TRY(launch_decode_tc(h->dev, cs_dev + (size_t)f0 * h->dev.k_scale, cr_dev + (size_t)f0 * h->dev.k_rotat, nf,
-                                  w.ximg_s, w.ximg_r, w.dgrad_c, s));
+        CUDA_TRY((h->dev.tc16_ready ? launch_decode_tc16 : launch_decode_tc)(
+            h->dev, cs_dev + (size_t)f0 * h->dev.k_scale, cr_dev + (size_t)f0 * h->dev.k_rotat, nf, w.ximg_s, w.ximg_r, w.dgrad_c, s));
         return SDFA_OK;
     };
     if (chunk)
@@ -942,9 +967,10 @@ int sdfa_decode_compact_dev(sdfa_handle *h, const float *coeff_scale_dev, const 
     cudaStream_t s = (cudaStream_t)stream;
     if ((rc = order_after_last(h, s))) return rc;
     sdfa_handle::Workspace &w = h->ws[0];
-    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, tc_ximg_floats(n_frames, h->dev.k_scale)))) return rc;
-    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, tc_ximg_floats(n_frames, h->dev.k_rotat)))) return rc;
-    CUDA_TRY(launch_decode_tc(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, w.ximg_s, w.ximg_r, dgrad_compact_dev, s));
+    if ((rc = grow(&w.ximg_s, &w.ximg_s_cap, std::max(tc_ximg_floats(n_frames, h->dev.k_scale), tc16_ximg_floats(n_frames, h->dev.k_scale))))) return rc;
+    if ((rc = grow(&w.ximg_r, &w.ximg_r_cap, std::max(tc_ximg_floats(n_frames, h->dev.k_rotat), tc16_ximg_floats(n_frames, h->dev.k_rotat))))) return rc;
+    CUDA_TRY((h->dev.tc16_ready ? launch_decode_tc16 : launch_decode_tc)(h->dev, coeff_scale_dev, coeff_rotat_dev, n_frames, w.ximg_s,
+                                                                         w.ximg_r, dgrad_compact_dev, s));
     return mark_async(h, s);
 }
 

@@ -77,6 +77,12 @@ struct DevicePlan {
     // tensor-core decode (decode_tc.cu): pre-split, pre-tiled basis images, bias and output offsets per row
     float *tc_w_scale = nullptr, *tc_w_rotat = nullptr;
     int tc_mt_scale = 0, tc_mt_rotat = 0;
+    // second generation (decode_tc16.cu): scaled FP16 hi/lo basis images and 1 / s_w per part; used when decode_fp16 and the
+    // basis widths fit its resident frames operands (tc16_fits), else the TF32 kernel
+    const uint16_t *tc16_w_scale = nullptr, *tc16_w_rotat = nullptr;
+    float tc16_inv_sw[2] = {1.f, 1.f};
+    bool decode_fp16 = true, tc16_ready = false;
+    int decode16_max_clusters = 0;
 };
 
 enum AssemblyMode { ASM_DGRAD = 0, ASM_MATRIX = 1 };
@@ -105,6 +111,14 @@ cudaError_t launch_seek(const float *seq, long long width, const int2 *pairs, co
 cudaError_t launch_decode_tc(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
                              float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);
 size_t tc_ximg_floats(int n_frames, int K);
+// decode_tc16.cu
+cudaError_t launch_decode_tc16(const DevicePlan &d, const float *coeff_scale, const float *coeff_rotat, int n_frames,
+                               float *ximg_scale, float *ximg_rotat, float *dgrad_out, cudaStream_t stream);
+size_t tc16_ximg_floats(int n_frames, int K);
+bool tc16_fits(int k_scale, int k_rotat);
+int tc16_build_basis(const float *W, const float *mean, int K, const std::vector<int32_t> &rows_src, std::vector<uint16_t> &img,
+                     float *inv_sw);
+cudaError_t configure_decode_tc16(DevicePlan &d);
 // Occupancy queries of the persistent kernels, stored in the plan (called by sdfa_create with the device current).
 cudaError_t configure_solve(DevicePlan &d);
 cudaError_t configure_decode_tc(DevicePlan &d);
