@@ -738,22 +738,33 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     tf32_tflops = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    a, b = a.half(), b.half()
+    for _ in range(3):
+        a @ b
+    e0.record()
+    for _ in range(10):
+        a @ b
+    e1.record()
+    torch.cuda.synchronize()
+    f16_tflops = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
     del a, b
+    decode_kernel = "k_decode_tc16" if rec.debug("decode_kind")[0] == 16 else "k_decode_tc"
+    tensor_peak = f16_tflops if decode_kernel == "k_decode_tc16" else tf32_tflops
 
     total = n * world
     dom = max(("solve_ms", "assembly_ms", "decode_ms", "output_ms"), key=lambda k: stage[k])
     solver_kernel = "k_solve_tc" if rec.debug("ts_stats")[0] else "k_solve"
     if dom == "decode_ms":
         rows_s, rows_r = -(-6 * rec.n_active // 256) * 256, -(-3 * rec.n_active // 256) * 256
-        issued = 3 * 2 * (rows_s * 96 + rows_r * 192)     # 3 TF32 products per K step, K and rows padded to tiles
+        issued = 3 * 2 * (rows_s * 96 + rows_r * 192)     # 3 split products per K step, K and rows padded to tiles
         ach = DECODE_FLOP * n / (stage[dom] * 1e-3) / 1e12
-        roof = {"kernel": "k_decode_tc (K1)", "bound": "tensor", "achieved": ach, "peak": tf32_tflops, "unit": "TFLOP/s",
-                "frac": ach / tf32_tflops, "traffic": ncu_traffic("k_decode_tc"),
+        roof = {"kernel": decode_kernel + " (K1)", "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": ach / tensor_peak, "traffic": ncu_traffic(decode_kernel),
                 "useful_flop_per_frame": DECODE_FLOP, "issued_flop_per_frame": issued,
-                "issued_frac": issued * n / (stage[dom] * 1e-3) / 1e12 / tf32_tflops,
-                "peak_source": "torch fp32 8192^3 matmul with allow_tf32, measured in this run",
+                "issued_frac": issued * n / (stage[dom] * 1e-3) / 1e12 / tensor_peak,
+                "peak_source": "torch 8192^3 matmul in the kernel's operand type (fp16, or fp32 with allow_tf32), measured in this run",
                 "note": "achieved = SURVEY 8(d) useful FLOP (active triangles, K = 85 / 180, one product); the kernel issues "
-                        "3xTF32 on padded tiles (issued_frac) and writes the 94 KB/frame compact dgrad"}
+                        "three split products on padded tiles (issued_frac) and writes the 94 KB/frame compact dgrad"}
     else:
         b_, kname = {"solve_ms": (BYTES_SOLVE, solver_kernel), "assembly_ms": (BYTES_ASSEMBLY, "k_assemble"),
                      "output_ms": (BYTES_OUTPUT, "k_output")}[dom]
@@ -765,13 +776,14 @@ def main():
     roof["traffic_source"] = traffic_src
     # every kernel of the path against its own algorithmic bytes (decode: useful FLOP against the TF32 peak as well)
     per_kernel = {}
-    for key, nm, by in (("decode_ms", "k_decode_tc", BYTES_DECODE_OUT), ("assembly_ms", "k_assemble", BYTES_ASSEMBLY),
+    for key, nm, by in (("decode_ms", decode_kernel, BYTES_DECODE_OUT), ("assembly_ms", "k_assemble", BYTES_ASSEMBLY),
                         ("solve_ms", solver_kernel, BYTES_SOLVE), ("output_ms", "k_output", BYTES_OUTPUT)):
         gbs = by * n / (stage[key] * 1e-3) / 1e9
         per_kernel[nm] = {"ms": stage[key], "algorithmic_bytes_per_frame": by, "achieved_gbs": gbs,
                           "frac_of_hbm": gbs / peaks["hbm_gbs"], "ncu_dram_bytes_per_launch": ncu_traffic(nm)}
-    per_kernel["k_decode_tc"]["useful_tflops"] = DECODE_FLOP * n / (stage["decode_ms"] * 1e-3) / 1e12
-    per_kernel["k_decode_tc"]["frac_of_tf32_peak"] = per_kernel["k_decode_tc"]["useful_tflops"] / tf32_tflops
+    per_kernel[decode_kernel]["useful_tflops"] = DECODE_FLOP * n / (stage["decode_ms"] * 1e-3) / 1e12
+    per_kernel[decode_kernel]["frac_of_tensor_peak"] = per_kernel[decode_kernel]["useful_tflops"] / tensor_peak
+    per_kernel[decode_kernel]["tensor_peak_tflops"] = tensor_peak
     path_gbs = BYTES_PATH * n / (ms_dgrad * 1e-3) / 1e9
     result = {
         "metric": METRIC, "value": total / (ms_step * 1e-3), "unit": "frames/s",
@@ -800,7 +812,7 @@ def main():
         "dgrad_resident": {"value": total / (ms_dgrad * 1e-3), "unit": "frames/s", "ms_per_step": ms_dgrad},
         "kernel_ms_per_step": stage,
         "roofline_kernels": per_kernel,
-        "tf32_matmul_tflops_measured": tf32_tflops,
+        "tf32_matmul_tflops_measured": tf32_tflops, "f16_matmul_tflops_measured": f16_tflops,
         "host_cpus_bound": len(cpus) if cpus else None,
     }
     if gather is not None:

@@ -1142,6 +1142,7 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
     if (w == "asm_eq_rows") return give(p.asmplan.eq_rows, dst, cap);
     if (w == "asm_colour_ptr") return give(p.asmplan.colour_ptr, dst, cap);
     if (w == "scratch_row") return give(p.scratch_row, dst, cap);
+    if (w == "decode_kind") { std::vector<int32_t> v = {h->dev.tc16_ready ? 16 : 32}; return give(v, dst, cap); }
     if (w == "compact_tile") { std::vector<int32_t> v = {COMPACT_TILE}; return give(v, dst, cap); }
     if (w == "ts_mma") return give(p.tplan.mma, dst, cap);
     if (w == "ts_epi") return give(p.tplan.epi, dst, cap);

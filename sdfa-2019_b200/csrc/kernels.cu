@@ -635,7 +635,10 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
 // The factor is never re-read from HBM per frame: every task entry fetched from the ring is applied to
 // 96 right-hand sides (32 frames x 3 coordinates) of the tile.
 constexpr int RING = 3;
-constexpr int NCW = 12;                         // consumer warps
+#ifndef SOLVE_NCW
+#define SOLVE_NCW 12
+#endif
+constexpr int NCW = SOLVE_NCW;                  // consumer warps
 constexpr int SOLVE_THREADS = 32 * (NCW + 2);
 
 struct SolveParams {

@@ -102,7 +102,7 @@ _DEBUG_DTYPES = {
     "active_eq": np.int32, "tri_u": np.float64, "prog": np.uint8, "stage_off": np.uint32, "io_desc": np.uint32, "io_phase": np.uint32, "eq_src": np.int32,
     "asm_eq_id": np.int32, "asm_eq_u": np.float32, "asm_row_perm": np.int32, "asm_eq_rows": np.int16,
     "asm_colour_ptr": np.int32, "solve_prof": np.int64, "asm_blocks": np.int32, "stats": np.int64,
-    "scratch_row": np.int32, "compact_tile": np.int32, "ts_mma": np.uint8, "ts_epi": np.uint8, "ts_matrix": np.uint8, "ts_chunk_off": np.uint32,
+    "scratch_row": np.int32, "compact_tile": np.int32, "decode_kind": np.int32, "ts_mma": np.uint8, "ts_epi": np.uint8, "ts_matrix": np.uint8, "ts_chunk_off": np.uint32,
     "ts_why_not": np.uint8, "ts_stats": np.int64,
 }
 

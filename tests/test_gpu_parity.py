@@ -183,24 +183,35 @@ def test_tensor_core_decode_matches_fp64(rec, flame):
 
 
 def test_tensor_core_decode_other_basis_sizes(flame):
-    """K1 with bases of other widths than the reference's 85 + 180: a scale basis wider than three K-blocks (its frames
-    operand is then streamed instead of resident in shared memory), a one-block rotation basis, and widths that
-    are exact multiples of the 32-float K-block (the means' column opens a new block).  Several frame tiles, so that
-    CTA pairs change tiles mid-walk."""
+    """K1 with bases of other widths than the reference's 85 + 180, on both generations of the kernel: the FP16-split
+    kernel (both frames operands resident: up to five 64-wide K-blocks over the two parts, partial last blocks, widths
+    that are exact multiples of a block so that the means' column opens a new one) and the TF32-split kernel it falls
+    back to for wider bases (forced with ``decode=tf32`` for the narrow ones: streamed scale operand, one-block bases).
+    Several frame tiles, so that CTA pairs change tiles mid-walk."""
     import torch
     V, F, nfv = flame["V"], flame["F"], flame["nfv"]
-    r = D.Reconstructor(V, F, cnsts=nfv, device=0)
-    for ks, kr in ((120, 20), (96, 31), (32, 64), (5, 200)):
-        cs, ms, cr, mr = W.random_pca(len(F), seed=3, k_scale=ks, k_rotat=kr)
-        r.set_pca(cs, ms, cr, mr)
-        n = 700
-        xs, xr = W.random_coeffs(n, seed=ks, k_scale=ks, k_rotat=kr)
-        got = r.decode_compact(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda()).cpu().numpy()
-        lay = r.compact_layout()
-        used = lay >= 0
-        dg64 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float64)[:, lay[used]]
-        assert np.abs(got[:, used] - dg64).max() <= 5e-7, (ks, kr)
-    r.close()
+    for opts, want_kind, sizes in (({}, 16, ((120, 20), (96, 31), (32, 64), (5, 200), (63, 127))),
+                                   ({}, 32, ((300, 40),)),                       # too wide for the resident operands
+                                   ({"decode": "tf32"}, 32, ((120, 20), (96, 31), (32, 64), (5, 200)))):
+        r = D.Reconstructor(V, F, cnsts=nfv, device=0, options=opts)
+        for ks, kr in sizes:
+            cs, ms, cr, mr = W.random_pca(len(F), seed=3, k_scale=ks, k_rotat=kr)
+            r.set_pca(cs, ms, cr, mr)
+            assert int(r.debug("decode_kind")[0]) == want_kind, (opts, ks, kr)
+            n = 700
+            xs, xr = W.random_coeffs(n, seed=ks, k_scale=ks, k_rotat=kr)
+            xs[3] *= 1e-4                                     # per-frame scaling: a frame of tiny and one of huge coefficients
+            xr[5] *= 300.0
+            got = r.decode_compact(torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda()).cpu().numpy()
+            lay = r.compact_layout()
+            used = lay >= 0
+            dg64 = pca_decode(xs, cs, ms, xr, cr, mr, dtype=np.float64)[:, lay[used]]
+            err = np.abs(got[:, used] - dg64)
+            big = np.zeros(n, dtype=bool)
+            big[5] = True
+            assert err[~big].max() <= 5e-7, (opts, ks, kr)
+            assert err[big].max() <= 5e-7 * 300, (opts, ks, kr)   # relative to that frame's magnitude
+        r.close()
 
 
 def test_decode_and_reconstruct_config2(rec, chk, flame):
