@@ -600,6 +600,11 @@ def main():
     del dgrad
     torch.cuda.empty_cache()
 
+    # ---- configs[1] literally: ONE 240-frame sentence per call (latency of the call, device resident, CUDA events)
+    one = FRAMES_PER_SENTENCE
+    out_one = torch.empty((one, N_VERTS, 3), dtype=torch.float32, device=dev)
+    ms_sentence = timed(lambda: rec.decode_and_get_mesh(xs_d[:one], xr_d[:one], out=out_one), max(args.steps, 20), args.warmup)
+
     # ---- per-kernel device time (library's own CUDA events on the launch stream), separate pass
     rec.set_timing(True)
     stage = {"decode_ms": 0.0, "assembly_ms": 0.0, "solve_ms": 0.0, "output_ms": 0.0}
@@ -810,6 +815,9 @@ def main():
         "roofline_path": {"what": "K2+K3+K5 with dgrad resident in HBM, 153 912 algorithmic B/frame (SURVEY 8d)",
                           "achieved": path_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": path_gbs / peaks["hbm_gbs"]},
         "dgrad_resident": {"value": total / (ms_dgrad * 1e-3), "unit": "frames/s", "ms_per_step": ms_dgrad},
+        "single_sentence": {"frames": one, "ms_per_call": ms_sentence, "value": one / (ms_sentence * 1e-3), "unit": "frames/s",
+                            "what": "configs[1] as one call: decode + reconstruction of one 240-frame sentence, device resident, "
+                                    "L2 flushed before every call"},
         "kernel_ms_per_step": stage,
         "roofline_kernels": per_kernel,
         "tf32_matmul_tflops_measured": tf32_tflops, "f16_matmul_tflops_measured": f16_tflops,

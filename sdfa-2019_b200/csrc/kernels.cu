@@ -1025,16 +1025,72 @@ __global__ void __launch_bounds__(OUT_THREADS) k_output(OutParams P) {
     }
 }
 
+// Second generation of the output kernel: no shared-memory staging and no block barrier.  A thread still owns one output
+// element of the chunk for FC consecutive frames; if the element is a free coordinate its FC solved values are ONE
+// contiguous run of the scratch line, so the thread pulls them with FC / 4 independent 16-byte loads issued up front (all
+// of a CTA's loads are in flight at once; the sectors a warp's first load touches are completed by its next ones out of L1),
+// adds the base, and every frame's store stays one full-warp instruction (constrained lanes select their constant).
+// Measured equal to the staged kernel (1.41 against 1.43 ms per 75 600 FLAME frames): the kernel is bound by the store
+// pattern itself -- tools/micro/outbw.cu writes the same 192-float x 32-frame pieces with no loads at all in 0.93 ms
+// (4.9 TB/s), while whole frames written front to back reach 6 - 7 TB/s.  A frame-major variant (a CTA owns four whole
+// frames, stages their free coordinates with one 16-byte load per scratch line) was tried and dropped: 2.3 - 3.0 ms, because
+// a CTA then uses 16 bytes of every 512-byte scratch line it touches.
+template <int FC>
+__global__ void __launch_bounds__(OUT_THREADS) k_output2(OutParams P) {
+    const int chunk = blockIdx.x, frame0 = blockIdx.y * FC;
+    const int nvalid = min(FC, P.n_frames - frame0);
+    const int e = threadIdx.x;
+    const long long row = (long long)P.n_verts * 3;
+    if ((long long)chunk * OUT_THREADS + e >= row) return;
+    const int line = P.line_of[chunk * OUT_THREADS + e];
+    float c = P.cval[chunk * OUT_THREADS + e];
+    float4 v[FC / 4];
+    float lo = 0.f;
+    if (line >= 0) {
+        const int l = P.line_ptr[chunk] + line;
+        const float4 *src = reinterpret_cast<const float4 *>(P.scratch + (long long)(frame0 / P.FR) * P.tile_stride + frame0 % P.FR +
+                                                             P.line_off[l]);
+#pragma unroll
+        for (int i = 0; i < FC / 4; ++i) v[i] = __ldcs(src + i);
+        c = P.line_hi[l];
+        lo = P.line_lo[l];
+    } else {
+#pragma unroll
+        for (int i = 0; i < FC / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float *dst = P.out + (long long)frame0 * row + (long long)chunk * OUT_THREADS + e;
+    // c + (lo + x): for a constrained element lo = x = 0 and c is its constant, so the arithmetic is the same instruction
+    // stream for every lane and the value of a free element is hi + (lo + x) as before
+#pragma unroll
+    for (int i = 0; i < FC / 4; ++i) {
+        const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = 4 * i + j;
+            if (f < nvalid) __stcs(dst + (long long)f * row, line >= 0 ? c + (lo + x[j]) : c);
+        }
+    }
+}
+
 cudaError_t launch_output(const DevicePlan &d, const DevicePlan::OutTables &t, const float *scratch, int n_frames, float *out,
                           cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
     const int FR = d.layout.FL, FC = std::min(FR, 32);
     OutParams P{scratch, t.line_of, t.cval, t.line_ptr, t.line_off, t.line_hi, t.line_lo,
                 out, n_frames, t.n_rows, FR, FC, d.layout.tile_stride};
+    dim3 grid((unsigned)((t.n_rows + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));
+    if (d.out_gen >= 2 && FR % FC == 0 && FC % 4 == 0) {
+        switch (FC) {
+            case 32: k_output2<32><<<grid, OUT_THREADS, 0, stream>>>(P); break;
+            case 16: k_output2<16><<<grid, OUT_THREADS, 0, stream>>>(P); break;
+            default: k_output2<8><<<grid, OUT_THREADS, 0, stream>>>(P); break;
+        }
+        g_launches++;
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)std::max(t.max_lines, 1) * (FC + 1) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_output, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((t.n_rows + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));
     k_output<<<grid, OUT_THREADS, smem, stream>>>(P);
     g_launches++;
     return cudaGetLastError();
