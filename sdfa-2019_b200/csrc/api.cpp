@@ -266,7 +266,7 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
 
 // "key=value;key=value" -> map; unknown keys are an error so that a typo does not silently select the default
 static int parse_options(const char *options, std::map<std::string, std::string> &kv) {
-    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf", "asm_gather", "decode", "output"};
+    static const char *known[] = {"solver", "pipe_chunk", "frames_per_tile", "asm_rows", "ts_leaf", "asm_gather", "decode", "output", "output_frames"};
     const std::string text = options ? options : "";
     size_t at = 0;
     while (at < text.size()) {
@@ -369,6 +369,12 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
         h->dev.asm_gather_gen = g.empty() ? 2 : std::atoi(g.c_str());
         const std::string og = setting("output", "SDFA_OUTPUT");
         h->dev.out_gen = og.empty() ? 2 : std::atoi(og.c_str());
+        const std::string of = setting("output_frames", "SDFA_OUTPUT_FRAMES");
+        if (!of.empty()) {
+            const int fc = std::atoi(of.c_str());
+            if (fc != 8 && fc != 16 && fc != 32) { delete h; return fail(SDFA_ERR_ARG, "sdfa_create: output_frames must be 8, 16 or 32"); }
+            h->dev.out_fc = fc;
+        }
         const std::string dk = setting("decode", "SDFA_DECODE");
         if (!dk.empty() && dk != "f16" && dk != "tf32") { delete h; return fail(SDFA_ERR_ARG, "sdfa_create: decode must be f16 or tf32"); }
         h->dev.decode_fp16 = dk != "tf32";

@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(OUT_THREADS) k_output2(OutParams P) {
 cudaError_t launch_output(const DevicePlan &d, const DevicePlan::OutTables &t, const float *scratch, int n_frames, float *out,
                           cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    const int FR = d.layout.FL, FC = std::min(FR, 32);
+    const int FR = d.layout.FL, FC = std::min(FR, d.out_gen >= 2 ? d.out_fc : 32);
     OutParams P{scratch, t.line_of, t.cval, t.line_ptr, t.line_off, t.line_hi, t.line_lo,
                 out, n_frames, t.n_rows, FR, FC, d.layout.tile_stride};
     dim3 grid((unsigned)((t.n_rows + OUT_VC - 1) / OUT_VC), (unsigned)((n_frames + FC - 1) / FC));

@@ -13,6 +13,15 @@ __global__ void __launch_bounds__(192) k(float *out, long long R, int n_frames, 
         if (g >= 0 && g < R) __stcs(out + base + g, 1.f);
     }
 }
+// CTA = (W floats of every row, FG frames): thread = element(s), one 128-byte store per warp, frame and 32 elements
+__global__ void k_piece(float *out, long long R, int n_frames, int W, int FG) {
+    const int frame0 = blockIdx.y * FG;
+    for (int e = threadIdx.x; e < W; e += blockDim.x) {
+        const long long g = (long long)blockIdx.x * W + e;
+        if (g >= R) break;
+        for (int f = 0; f < FG && frame0 + f < n_frames; ++f) __stcs(out + (long long)(frame0 + f) * R + g, 1.f);
+    }
+}
 // CTA = FB whole frames: one contiguous block of FB * R floats, written front to back
 __global__ void __launch_bounds__(1024) k_rows(float *out, long long R, int n_frames, int FB) {
     const long long base = (long long)blockIdx.x * FB * R, total = (long long)min(FB, n_frames - blockIdx.x * FB) * R;
@@ -28,6 +37,14 @@ int main() {
             float best = 1e9;
             for (int i = 0; i < 4; ++i) { cudaEventRecord(a); k<<<grid, 192>>>(out, R, n, mode); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); best = std::min(best, ms); }
             printf("R = %lld floats, %s windows: %.3f ms  %.0f GB/s  %s\n", R, mode ? "line-aligned (shifted)" : "fixed", best, (double)n * R * 4 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        }
+    for (int W : {192, 384, 768, 1536, 3072, 15069})
+        for (int FG : {8, 32}) {
+            const int threads = W >= 768 ? 768 : W;
+            dim3 grid((unsigned)((15069 + W - 1) / W), (unsigned)((n + FG - 1) / FG));
+            float best = 1e9;
+            for (int i = 0; i < 4; ++i) { cudaEventRecord(a); k_piece<<<grid, threads>>>(out, 15069, n, W, FG); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); best = std::min(best, ms); }
+            printf("pieces of %d floats x %d frames, %d threads: %.3f ms  %.0f GB/s  %s\n", W, FG, threads, best, (double)n * 15069 * 4 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
         }
     for (int FB : {1, 4, 8, 16})
         for (int threads : {256, 1024}) {
