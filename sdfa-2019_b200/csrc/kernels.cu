@@ -542,8 +542,16 @@ __global__ void __launch_bounds__(ASM_THREADS, 1) k_assemble_gather2(AsmParams P
     };
 #pragma unroll
     for (int i = 0; i < AG_STAGES; ++i) issue(i);
+    // the equation record (U0, U1, corner rows) of the NEXT entry is fetched one iteration ahead, under this entry's transform
+    auto meta = [&](const int4 e, float4 &a, float4 &b) {
+        if (e.x >= 0) { a = __ldg(P.eq_meta + (size_t)(blk.x + e.x) * 2); b = __ldg(P.eq_meta + (size_t)(blk.x + e.x) * 2 + 1); }
+    };
+    float4 m0n = make_float4(0.f, 0.f, 0.f, 0.f), m1n = m0n;
+    meta(*walk, m0n, m1n);
     for (int n = 0, stage = 0;; ++n, stage = stage + 1 == AG_STAGES ? 0 : stage + 1) {
         const int4 ent = *walk++;
+        const float4 m0 = m0n, m1 = m1n;
+        if (ent.x != ASM_SCHED_END) meta(*walk, m0n, m1n);
         asm volatile("cp.async.wait_group %0;" ::"n"(AG_STAGES - 1) : "memory");   // this lane's copies of entry n have landed ...
         __syncwarp();                                                // ... and so have the other lanes'
         const bool rec = ent.x >= 0 && ent.y >= 0;
@@ -566,7 +574,6 @@ __global__ void __launch_bounds__(ASM_THREADS, 1) k_assemble_gather2(AsmParams P
                 default: ag_select<3>(wa, wb, d); break;
             }
         }
-        const float4 m0 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2), m1 = __ldg(P.eq_meta + (size_t)(blk.x + ent.x) * 2 + 1);
         eq_apply2(acc, lane, P.mode, ent.y, d, m0, m1);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
