@@ -214,7 +214,9 @@ class PeerGather:
         self.buf = symm_mem.empty(shape, dtype=torch.float32, device=dev)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.peers = [self.hdl.get_buffer(r, shape, torch.float32) for r in range(self.world)]
-        self.sides = [torch.cuda.Stream(dev) for _ in range(min(4, max(1, self.world - 1)))]   # pushes in flight at once (copy engines)
+        # two pushes in flight (measured at eight GPUs: two streams 13.6 ms per step, four 24.3 ms -- more concurrent pushes
+        # put several senders on one receiver's link again)
+        self.sides = [torch.cuda.Stream(dev) for _ in range(2)]
         self.bytes_pushed_per_run = 0
 
     def run(self, compute, inputs):
