@@ -40,7 +40,11 @@ constexpr int H_WH_BYTES = H_W_BYTES / H_CLUSTER;           // 16 KB: this CTA's
 constexpr int H_X_BYTES = H_BN * H_BK * 2;                  // 16 KB: hi (or lo) image of the CTA's frames, one K-block
 constexpr int H_SUBS = 4;                                   // ring sub-slots
 constexpr int H_XS_KB = 5;                                  // resident K-blocks of the frames operands (both parts), hi | lo each
-constexpr int H_EPI_WARPS = 8;
+#ifndef H_EPI_WARPS_N
+#define H_EPI_WARPS_N 8
+#endif
+constexpr int H_EPI_WARPS = H_EPI_WARPS_N;       // 4 lane quarters x (H_EPI_WARPS / 4) column parts
+constexpr int H_COLS_PER_WARP = H_BM / (H_EPI_WARPS / 4);
 constexpr int H_THREADS = 32 * (2 + H_EPI_WARPS);
 constexpr int H_TMEM_COLS = 512;
 constexpr size_t H_SMEM = (size_t)H_SUBS * H_WH_BYTES + (size_t)H_XS_KB * 2 * H_X_BYTES + 256 + 1024;
@@ -306,7 +310,7 @@ __global__ void __cluster_dims__(H_CLUSTER, 1, 1) __launch_bounds__(H_THREADS, 1
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> scale -> global
         const int lane_grp = warp & 3;
-        const int col_half = (warp - 2) >> 2;
+        const int col_part = (warp - 2) >> 2;                       // which H_COLS_PER_WARP of the 256 columns (basis rows) it drains
         const uint32_t tempty0 = mapa(bar_tempty, 0);
         uint32_t tc = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++tc) {
@@ -317,12 +321,12 @@ __global__ void __cluster_dims__(H_CLUSTER, 1, 1) __launch_bounds__(H_THREADS, 1
             const bool live = frame0 < P.n_frames;
             const float inv = __ldg(P.inv[ti.part] + frame0 + lane);
             float *out_tile = P.out + ((size_t)(frame0 / COMPACT_TILE) * P.out_stride + P.part_off[ti.part] + (size_t)m * H_BM +
-                                       col_half * (H_BM / 2)) * COMPACT_TILE + frame0 % COMPACT_TILE + lane;
+                                       col_part * H_COLS_PER_WARP) * COMPACT_TILE + frame0 % COMPACT_TILE + lane;
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * H_BM + col_half * (H_BM / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + acc * H_BM + col_part * H_COLS_PER_WARP;
 #pragma unroll 1
-            for (int chunk = 0; chunk < H_BM / 64; ++chunk) {
+            for (int chunk = 0; chunk < H_COLS_PER_WARP / 32; ++chunk) {
                 uint32_t v[32];
                 tmem_ld32(taddr + chunk * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
