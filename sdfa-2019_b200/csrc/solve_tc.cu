@@ -28,7 +28,7 @@ namespace {
 constexpr int TS_RING = 3;                     // matrix ring stages (32 KB each)
 constexpr int TS_ROWRING = 2;                  // scratch-row ring stages (<= 64 rows x 128 columns each)
 constexpr int TS_ROWSTAGE_BYTES = TS_MAX_NODE * TS_COLS * 4;
-constexpr int TS_EPI_WARPS = 8;                // two warps per tensor-memory lane quarter, each takes every other 8-column chunk
+constexpr int TS_EPI_WARPS = 8;                // two warps per tensor-memory lane quarter: the first four 8-column chunks of an op, and the rest
 constexpr int TS_THREADS = 32 * (4 + TS_EPI_WARPS);   // streamer, issuer, row loader, row storer, epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,6 +82,59 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v) {
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+// k (1 .. 4, warp uniform) consecutive 8-column chunks in as few tensor-memory instructions as possible: an epilogue op is
+// a chain of tensor-memory round trips, and four x8 accesses cost about four times one x32 access
+__device__ __forceinline__ void tmem_ld_chunks(uint32_t taddr, int k, uint32_t (&v)[32]) {
+    switch (k) {
+        case 4: tmem_ld32(taddr, v); break;
+        case 3: tmem_ld16(taddr, v); tmem_ld8(taddr + 16, v + 16); break;
+        case 2: tmem_ld16(taddr, v); break;
+        case 1: tmem_ld8(taddr, v); break;
+        default: break;
+    }
+}
+__device__ __forceinline__ void tmem_st_chunks(uint32_t taddr, int k, const uint32_t (&v)[32]) {
+    switch (k) {
+        case 4: tmem_st32(taddr, v); break;
+        case 3: tmem_st16(taddr, v); tmem_st8(taddr + 16, v + 16); break;
+        case 2: tmem_st16(taddr, v); break;
+        case 1: tmem_st8(taddr, v); break;
+        default: break;
+    }
 }
 
 struct TsParams {
@@ -257,10 +310,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     } else {
         // ------------------------------------------------------------------ epilogue: thread = column
         const int lane_grp = warp & 3;                               // tensor-memory lanes 32*lane_grp.. belong to this warp
-        const int half = (warp - 4) >> 2;                            // this warp takes chunks half, half + 2, ...
+        const int half = (warp - 4) >> 2;                            // this warp takes the chunks NC * half .. NC * half + NC - 1
         const int col = lane_grp * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         constexpr int NC = TS_MAX_CHUNKS8 / 2;
+        static_assert(NC == 4, "a warp's share of an op is at most four chunks = one x32 tensor-memory access");
+        const int c0 = half * NC;
         uint32_t tcount = 0, lit = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t par = tcount & 1u;
@@ -271,8 +326,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                 const EpiOp op = nxt;
                 nxt = epi_sm[e + 1 < P.n_epi ? e + 1 : e];
                 if (prof) P.prof[6 * e] = clock64();
-                const int nch = op.n_chunks, nv = op.n_valid;
-                float g[NC][8];                                      // chunk 2 * c + half
+                const int nv = op.n_valid;
+                const int k = min(NC, max(0, (int)op.n_chunks - c0));   // this warp's chunks of the op (warp uniform)
+                float g[NC * 8];                                     // chunk c0 + c, row i of it at g[8 c + i]
                 const bool ring_op = (op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL)) != 0;
                 const uint32_t rs = lit % TS_ROWRING;
                 float *stage_col = rowring + (size_t)rs * (TS_ROWSTAGE_BYTES / 4) + col;
@@ -282,21 +338,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                 }
                 if (op.flags & EPI_ADD_GLOBAL) {                     // the rows are staged in the row ring
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = (2 * c + half) * 8 + i;
-                            g[c][i] = r < nv ? stage_col[r * TS_COLS] : 0.f;
-                        }
+                    for (int j = 0; j < NC * 8; ++j) {
+                        const int r = c0 * 8 + j;
+                        g[j] = r < nv ? stage_col[r * TS_COLS] : 0.f;
+                    }
                     if (!(op.flags & EPI_STORE_GLOBAL)) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(bar_rempty + rs));
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) g[c][i] = 0.f;
+                    for (int j = 0; j < NC * 8; ++j) g[j] = 0.f;
                 }
                 if (prof) P.prof[6 * e + 1] = clock64();
                 if (op.wait_mma >= 0) {
@@ -305,32 +357,26 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                 }
                 if (prof) P.prof[6 * e + 2] = clock64();
                 if (op.flags & EPI_FROM_TMEM) {
-                    uint32_t v[NC][8];
-#pragma unroll
-                    for (int c = 0; c < NC; ++c)
-                        if (2 * c + half < nch) tmem_ld8(tlane + op.src_col + 8 * (2 * c + half), v[c]);
+                    uint32_t v[NC * 8];
+                    tmem_ld_chunks(tlane + op.src_col + 8 * c0, k, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (2 * c + half < nch) g[c][i] = ((2 * c + half) * 8 + i < nv) ? g[c][i] + __uint_as_float(v[c][i]) : 0.f;
+                    for (int j = 0; j < NC * 8; ++j)
+                        if (j < 8 * k) g[j] = (c0 * 8 + j < nv) ? g[j] + __uint_as_float(v[j]) : 0.f;
                     if (op.flags & EPI_ZERO_SRC) {
-                        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                        uint32_t z[NC * 8];
 #pragma unroll
-                        for (int c = 0; c < NC; ++c)
-                            if (2 * c + half < nch) tmem_st8(tlane + op.src_col + 8 * (2 * c + half), z);
+                        for (int j = 0; j < NC * 8; ++j) z[j] = 0u;
+                        tmem_st_chunks(tlane + op.src_col + 8 * c0, k, z);
                     }
                 }
                 if (prof) P.prof[6 * e + 3] = clock64();
                 if (op.flags & EPI_STORE_GLOBAL) {                   // into the op's ring stage; the storer bulk-stores it
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = (2 * c + half) * 8 + i;
-                            if (r < nv) stage_col[r * TS_COLS] = g[c][i];
-                        }
+                    for (int j = 0; j < NC * 8; ++j) {
+                        const int r = c0 * 8 + j;
+                        if (r < nv) stage_col[r * TS_COLS] = g[j];
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(bar_sdone + rs));
@@ -338,19 +384,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                 if (prof) P.prof[6 * e + 4] = clock64();
                 if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT)) {
                     const bool split = (op.flags & EPI_ST_SPLIT) != 0;
+                    uint32_t hi[NC * 8], lo[NC * 8];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
-                        if (2 * c + half < nch) {
-                            uint32_t hi[8], lo[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const uint32_t u = __float_as_uint(g[c][i]);
-                                hi[i] = split ? (u & 0xFFFFE000u) : u;
-                                lo[i] = __float_as_uint(g[c][i] - __uint_as_float(hi[i])) & 0xFFFFE000u;
-                            }
-                            tmem_st8(tlane + op.hi_col + 8 * (2 * c + half), hi);
-                            if (split) tmem_st8(tlane + op.lo_col + 8 * (2 * c + half), lo);
-                        }
+                    for (int j = 0; j < NC * 8; ++j) {
+                        const uint32_t u = __float_as_uint(g[j]);
+                        hi[j] = split ? (u & 0xFFFFE000u) : u;
+                        lo[j] = __float_as_uint(g[j] - __uint_as_float(hi[j])) & 0xFFFFE000u;
+                    }
+                    tmem_st_chunks(tlane + op.hi_col + 8 * c0, k, hi);
+                    if (split) tmem_st_chunks(tlane + op.lo_col + 8 * c0, k, lo);
                 }
                 if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT | EPI_ZERO_SRC)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 if (op.signal_epi >= 0) {
