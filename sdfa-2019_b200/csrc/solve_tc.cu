@@ -25,8 +25,14 @@ namespace sdfa {
 
 namespace {
 
-constexpr int TS_RING = 3;                     // matrix ring stages (32 KB each)
-constexpr int TS_ROWRING = 2;                  // scratch-row ring stages (<= 64 rows x 128 columns each)
+#ifndef TS_RING_N
+#define TS_RING_N 3
+#endif
+#ifndef TS_ROWRING_N
+#define TS_ROWRING_N 2
+#endif
+constexpr int TS_RING = TS_RING_N;             // matrix ring stages (32 KB each)
+constexpr int TS_ROWRING = TS_ROWRING_N;       // scratch-row ring stages (<= 64 rows x 128 columns each)
 constexpr int TS_ROWSTAGE_BYTES = TS_MAX_NODE * TS_COLS * 4;
 constexpr int TS_EPI_WARPS = 8;                // two warps per tensor-memory lane quarter: the first four 8-column chunks of an op, and the rest
 constexpr int TS_THREADS = 32 * (4 + TS_EPI_WARPS);   // streamer, issuer, row loader, row storer, epilogue warps
