@@ -195,7 +195,8 @@ class PeerGather:
     allocated as symmetric memory (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped into every peer
     over NVLink), each chunk of free rows is reconstructed straight into this rank's block of its own buffer, and a side
     stream pushes the finished chunk into the same block of every receiver's buffer with peer-to-peer copies (copy
-    engines: no SMs, no staging buffer, no unpack) while the next chunk is computed.  One device-side barrier per call.
+    engines: no SMs, no staging buffer, no unpack) while the next chunk is computed.  A device-side barrier at either end
+    of a call.
 
     ``mode="all"``: every rank ends up with [world * n_local, n_free, 3] (rank-major); ``mode="root"``: only ``dst``.
     The returned tensor is the symmetric buffer itself: consume (or copy) it before the next ``run``.
