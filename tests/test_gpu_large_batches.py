@@ -321,3 +321,42 @@ def test_config5_vs_compiled_reference():
         assert np.abs(got - ref).max() <= tol, (i, float(np.abs(got - ref).max()))
         assert np.array_equal(got[c], V[c])
     r.close()
+
+
+def test_kernel_generations_agree(flame):
+    """Every build-in alternative of a kernel (options of sdfa_create_with) against the defaults on one batch: the output
+    kernels must agree bit for bit whatever their generation and frames per CTA (they move the same values), the two
+    assembly generations and the two decode generations within the arithmetic's tolerance, and all of them with the
+    compiled reference on sampled frames."""
+    import torch
+    V, F, nfv, nft, tol = flame["V"], flame["F"], flame["nfv"], flame["nft"], flame["tol"]
+    pca = W.random_pca(len(F), seed=1, zero_tris=nft)
+    n = 1500                                                   # 23.4 tiles of 64 frames: partial tiles everywhere
+    xs, xr = W.random_coeffs(n, seed=21)
+    xs_d, xr_d = torch.from_numpy(xs).cuda(), torch.from_numpy(xr).cuda()
+
+    def run(options):
+        r = D.Reconstructor(V, F, cnsts=nfv, device=0, options=options)
+        r.set_pca(*pca)
+        dec = r.decode_and_get_mesh(xs_d, xr_d).cpu().numpy()
+        free = r.decode_and_get_mesh(xs_d, xr_d, free_only=True).cpu().numpy()
+        dg = r.decode_dgrad(xs_d, xr_d)
+        rec = r.get_mesh_batch(dg).cpu().numpy()
+        ids = r.free_vertices
+        r.close()
+        assert np.array_equal(dec[:, ids], free)
+        return dec, rec
+
+    base_dec, base_rec = run({})
+    for opts in ({"output": 1}, {"output": 2, "output_frames": 32}, {"output": 2, "output_frames": 16}):
+        dec, rec = run(opts)
+        assert np.array_equal(dec, base_dec) and np.array_equal(rec, base_rec), opts
+    dec, rec = run({"asm_gather": 1})
+    assert np.array_equal(dec, base_dec) and np.abs(rec - base_rec).max() <= 1e-7
+    dec, rec = run({"decode": "tf32"})
+    assert np.array_equal(rec, base_rec) and np.abs(dec - base_dec).max() <= 1e-7
+    chk = _checker(V, F, nfv)
+    dgh = pca_decode(xs, *pca[:2], xr, *pca[2:], dtype=np.float32)
+    for i in (0, 63, 64, n - 1):
+        want = chk.get_mesh(dgh[i].astype(np.float64), vert_cnsts=V[nfv])
+        assert np.abs(base_dec[i] - want).max() <= tol and np.abs(base_rec[i] - want).max() <= tol
