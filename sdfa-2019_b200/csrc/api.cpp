@@ -458,6 +458,7 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
                 d.ts_n_chunks = (int)tp.chunk_off.size() - 1;
                 d.ts_n_mma_events = tp.n_mma_events;
                 d.ts_n_epi_events = tp.n_epi_events;
+                d.ts_n_ring_ops = tp.n_ring_ops;
                 d.layout.FL = TS_COLS;
                 d.layout.tile_stride = 3LL * p.n_free * TS_COLS;
                 d.layout.row_stride = TS_COLS;
@@ -487,7 +488,7 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
             CUDA_TRY(configure_decode_tc(d));
             CUDA_TRY(configure_decode_tc16(d));
             if (std::getenv("SDFA_SOLVE_PROFILE")) {
-                std::vector<long long> zero(std::max((size_t)h->dev.sm_count * 4 * 8, (3 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
+                std::vector<long long> zero(std::max((size_t)h->dev.sm_count * 4 * 8, (5 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
                 if ((r = upload_mut(h, zero, &d.solve_prof))) return r;
             }
             return SDFA_OK;
@@ -1161,7 +1162,8 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
         std::vector<long long> v = {p.use_tensor ? 1 : 0, p.tplan.valid ? 1 : 0, (long long)p.tplan.mma.size(), (long long)p.tplan.epi.size(),
                                     (long long)p.tplan.chunk_off.size() - 1, (long long)p.tplan.matrix.size(), p.tplan.n_mma_events,
                                     p.tplan.n_epi_events, p.tplan.n_nodes, p.tplan.n_leaves, p.tplan.nk_products, p.tplan.tmem_fwd,
-                                    p.tplan.tmem_bwd, (long long)solve_tc_smem_bytes((int)p.tplan.mma.size(), (int)p.tplan.epi.size())};
+                                    p.tplan.tmem_bwd, (long long)solve_tc_smem_bytes((int)p.tplan.mma.size(), (int)p.tplan.epi.size()),
+                                    p.tplan.n_streams, p.tplan.n_ring_ops};
         return give(v, dst, cap);
     }
     if (w == "asm_blocks") {
@@ -1170,7 +1172,7 @@ long long sdfa_debug_get(const sdfa_handle *h, const char *what, void *dst, long
         return give(b, dst, cap);
     }
     if (w == "solve_prof") {
-        std::vector<long long> v(std::max((size_t)h->dev.sm_count * 4 * 8, (3 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
+        std::vector<long long> v(std::max((size_t)h->dev.sm_count * 4 * 8, (5 * p.tplan.mma.size() + 6 * p.tplan.epi.size())), 0);
         if (h->dev.solve_prof) cudaMemcpy(v.data(), h->dev.solve_prof, v.size() * 8, cudaMemcpyDeviceToHost);
         return give(v, dst, cap);
     }

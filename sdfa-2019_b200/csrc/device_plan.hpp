@@ -55,7 +55,7 @@ struct DevicePlan {
     const EpiOp    *ts_epi = nullptr;
     const uint8_t  *ts_matrix = nullptr;
     const uint32_t *ts_chunk_off = nullptr;
-    int ts_n_mma = 0, ts_n_epi = 0, ts_n_chunks = 0, ts_n_mma_events = 0, ts_n_epi_events = 0;
+    int ts_n_mma = 0, ts_n_epi = 0, ts_n_chunks = 0, ts_n_mma_events = 0, ts_n_epi_events = 0, ts_n_ring_ops = 0;
     // ---- output (K5)
     // per 64-vertex chunk tables of the output kernel (rebuilt by upload_base when the base / constraints change):
     // out_full writes every vertex [n_verts,3] (the reference layout), out_free only the free vertices [n_free,3] in

@@ -12,13 +12,15 @@
 // A_hi B_hi + A_lo B_hi + A_hi B_lo into the fp32 accumulator.
 //
 // One persistent CTA per SM loops over 128-column tiles of scratch[tile][row][128]; warp roles:
-//   warp 0   streamer  : matrix chunks -> ring (mbarrier full / empty)
-//   warp 1   issuer    : one thread walks the MmaOp stream
-//   warp 2   row loader: the scratch rows the EpiOp stream will add, TMA bulk copies into a second ring, ops ahead
-//   warp 3   row storer: bulk-stores the rows an op has written into its ring stage, then frees the stage
-//   warps 4-11 epilogue: thread = column = tensor-memory lane (two warps per lane quarter split an op's chunks),
-//                        walks the EpiOp stream
-// The two streams synchronise through single-use-per-tile mbarrier events chosen by the planner.
+//   warp 16   streamer  : matrix chunks -> ring (mbarrier full / empty)
+//   warp 17   issuer    : one thread walks the MmaOp stream
+//   warp 18   row loader: the scratch rows the EpiOp streams will add, TMA bulk copies into a second ring, ops ahead
+//   warps 0-7 EPI stream 0, warps 8-15 EPI stream 1: thread = column = tensor-memory lane (two warps per lane
+//             quarter split an op's chunks); each walks its own ops of the EpiOp list.  Rows leave as plain
+//             coalesced stores (one 128-byte line per warp and row).
+// The three instruction streams synchronise through single-use-per-tile mbarrier events chosen by the planner; a
+// named barrier over the EPI warps closes a tile.  Per-op latencies (a tensor-memory round trip, the hand-off to the
+// other stream) bound a tile, not bandwidth: two EPI streams let the round trips of independent tree nodes overlap.
 #include "device_plan.hpp"
 
 namespace sdfa {
@@ -28,14 +30,20 @@ namespace {
 #ifndef TS_RING_N
 #define TS_RING_N 3
 #endif
+#ifndef TS_STAGED_STORES
+#define TS_STAGED_STORES 1       // 1: rows leave through the op's row-ring stage and a bulk store (storer warp); 0: plain stores
+#endif
 #ifndef TS_ROWRING_N
-#define TS_ROWRING_N 2
+#define TS_ROWRING_N 3
 #endif
 constexpr int TS_RING = TS_RING_N;             // matrix ring stages (32 KB each)
 constexpr int TS_ROWRING = TS_ROWRING_N;       // scratch-row ring stages (<= 64 rows x 128 columns each)
 constexpr int TS_ROWSTAGE_BYTES = TS_MAX_NODE * TS_COLS * 4;
-constexpr int TS_EPI_WARPS = 8;                // two warps per tensor-memory lane quarter: the first four 8-column chunks of an op, and the rest
-constexpr int TS_THREADS = 32 * (4 + TS_EPI_WARPS);   // streamer, issuer, row loader, row storer, epilogue warps
+constexpr int TS_EPI_WARPS = 8;                // per EPI stream; two warps per tensor-memory lane quarter: the first four 8-column chunks of an op, and the rest
+constexpr int TS_EPI_STREAMS = 2;
+constexpr int TS_EPI_ALL = TS_EPI_STREAMS * TS_EPI_WARPS;           // warps 0 .. 15: the EPI streams (a warp's tensor-memory lane quarter is warp % 4)
+constexpr int TS_W_STREAMER = TS_EPI_ALL, TS_W_ISSUER = TS_EPI_ALL + 1, TS_W_LOADER = TS_EPI_ALL + 2, TS_W_STORER = TS_EPI_ALL + 3;
+constexpr int TS_THREADS = 32 * (TS_EPI_ALL + 3 + TS_STAGED_STORES);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -133,6 +141,10 @@ __device__ __forceinline__ void tmem_ld_chunks(uint32_t taddr, int k, uint32_t (
         default: break;
     }
 }
+__device__ __forceinline__ void tmem_zero_chunks(uint32_t taddr, int k) {
+    for (int c = 0; c < k; ++c)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + 8 * c), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void tmem_st_chunks(uint32_t taddr, int k, const uint32_t (&v)[32]) {
     switch (k) {
         case 4: tmem_st32(taddr, v); break;
@@ -143,21 +155,27 @@ __device__ __forceinline__ void tmem_st_chunks(uint32_t taddr, int k, const uint
     }
 }
 
+// a profiling stamp, or (regular build) a point the compiler does not move memory operations across: keeps an op's
+// phases -- and the registers they need -- apart
+#define TS_STAMP(i) do { if (prof) P.prof[i] = clock64(); else asm volatile("" ::: "memory"); } while (0)
+
 struct TsParams {
     const MmaOp *mma;
     const EpiOp *epi;
     const uint8_t *matrix;
     const uint32_t *chunk_off;
-    int n_mma, n_epi, n_chunks, n_mma_events, n_epi_events;
+    int n_mma, n_epi, n_chunks, n_mma_events, n_epi_events, n_ring_ops;
     float *scratch;            // [n_tiles][n_rows][128]
     int n_rows, n_tiles;
-    long long *prof;           // optional timeline of CTA 0's second tile: 3 clocks per EPI op, then 3 per MMA op
+    long long *prof;           // optional timeline of CTA 0's second tile: 6 clocks per EPI op, then 5 per MMA op
 };
 
 // instruction descriptor: D fp32, A / B tf32, both K-major, M = 128; N is filled in per op
 constexpr uint32_t TS_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
 constexpr int TS_MAX_CHUNKS8 = TS_MAX_NODE / 8;
+constexpr int TS_N_BARS = 2 * TS_RING + 3 * TS_ROWRING + 1 + 2 * TS_MAX_EVENTS;
 
+template <bool PROF>
 __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B images: 1024-byte aligned
@@ -180,16 +198,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
         for (int s = 0; s < TS_RING; ++s) { mbar_init(smem_u32(bar_full + s), 1); mbar_init(smem_u32(bar_empty + s), 1); }
         for (int s = 0; s < TS_ROWRING; ++s) {
             mbar_init(smem_u32(bar_rfull + s), 1);
-            mbar_init(smem_u32(bar_rempty + s), TS_EPI_WARPS);   // the epilogue warps, or the storer on their behalf
+            mbar_init(smem_u32(bar_rempty + s), TS_EPI_WARPS);   // the warps of the stream whose op owns the stage, or the storer on their behalf
             mbar_init(smem_u32(bar_sdone + s), TS_EPI_WARPS);
         }
-        mbar_init(smem_u32(bar_fwd), 1);
+        mbar_init(smem_u32(bar_fwd), TS_STAGED_STORES ? 1 : TS_EPI_WARPS);   // whoever stores the forward sweep's rows
         for (int e = 0; e < P.n_mma_events; ++e) mbar_init(smem_u32(bar_mma + e), 1);     // tcgen05.commit
-        for (int e = 0; e < P.n_epi_events; ++e) mbar_init(smem_u32(bar_epi + e), TS_EPI_WARPS);     // one arrive per epilogue warp
+        for (int e = 0; e < P.n_epi_events; ++e) mbar_init(smem_u32(bar_epi + e), TS_EPI_WARPS);     // one arrive per warp of the op's stream
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == TS_W_ISSUER) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TS_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -200,7 +218,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
 
-    if (warp == 0) {
+    if (warp == TS_W_STREAMER) {
         // ------------------------------------------------------------------ streamer
         if (leader) {
             uint32_t it = 0;
@@ -213,30 +231,30 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     tma_bulk_g2s(smem_u32(ring + s * TS_STAGE_BYTES), P.matrix + off, bytes, smem_u32(bar_full + s));
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == TS_W_ISSUER) {
         // ------------------------------------------------------------------ MMA issuer
         if (leader) {
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t par = tcount & 1u;
                 uint32_t stage = 0, slot = 0;
-                const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1;
+                const bool prof = PROF && blockIdx.x == 0 && tcount == 1;
                 MmaOp nxt = mma_sm[0];
                 for (int m = 0; m < P.n_mma; ++m) {
                     const MmaOp op = nxt;
                     nxt = mma_sm[m + 1 < P.n_mma ? m + 1 : m];
-                    if (prof) P.prof[6 * P.n_epi + 3 * m] = clock64();
-                    if (op.wait_epi >= 0) {
-                        mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
-                        tc_fence_after();
-                    }
+                    if (prof) P.prof[6 * P.n_epi + 5 * m] = clock64();
+                    if (op.wait_epi >= 0) mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
+                    if (op.wait_epi2 >= 0) mbar_wait(smem_u32(bar_epi + op.wait_epi2), par);
+                    if (op.wait_epi >= 0 || op.wait_epi2 >= 0) tc_fence_after();
+                    if (prof) P.prof[6 * P.n_epi + 5 * m + 1] = clock64();
                     if (op.flags & MMA_CHUNK_FIRST) {
                         slot = it % TS_RING;
                         mbar_wait(smem_u32(bar_full + slot), (it / TS_RING) & 1u);
                         tc_fence_after();
                         stage = smem_u32(ring + slot * TS_STAGE_BYTES);
                     }
-                    if (prof) P.prof[6 * P.n_epi + 3 * m + 1] = clock64();
+                    if (prof) P.prof[6 * P.n_epi + 5 * m + 2] = clock64();
                     const uint32_t idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
                     const uint32_t d = tmem_base + op.d_col;
                     uint32_t a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
@@ -255,15 +273,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                         const uint32_t step = (j & 3u) == 3u ? kb_step : 2u;
                         b_hi += step; b_lo += step;
                     }
+                    if (prof) P.prof[6 * P.n_epi + 5 * m + 3] = clock64();
                     if (op.flags & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
                     if (op.commit_mma >= 0) tc_commit(smem_u32(bar_mma + op.commit_mma));
-                    if (prof) P.prof[6 * P.n_epi + 3 * m + 2] = clock64();
+                    if (prof) P.prof[6 * P.n_epi + 5 * m + 4] = clock64();
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == TS_W_LOADER) {
         // ------------------------------------------------------------------ row loader
-        // every op that adds or stores scratch rows owns the next stage of the row ring
+        // every op that adds or stores scratch rows owns the next stage of the row ring (in list order, whichever stream runs it)
         if (leader) {
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                     const EpiOp op = epi_sm[e];
                     if (!(op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL))) continue;
                     // rows stored earlier in this tile (the forward sweep's u) are only read by the backward sweep:
-                    // wait until the storer has seen those bulk stores complete
+                    // wait until those stores are complete
                     if (op.flags & EPI_AFTER_STORES) mbar_wait(smem_u32(bar_fwd), tcount & 1u);
                     const uint32_t s = it % TS_ROWRING, ph = (it / TS_ROWRING) & 1u;
                     mbar_wait(smem_u32(bar_rempty + s), ph ^ 1u);
@@ -286,18 +305,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                 }
             }
         }
-    } else if (warp == 3) {
+#if TS_STAGED_STORES
+    } else if (warp == TS_W_STORER) {
         // ------------------------------------------------------------------ row storer
         if (leader) {
-            uint32_t it = 0, tcount = 0, sdone_par = 0;              // bit s: parity of stage s's next "written" phase
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
+            uint32_t it = 0, sdone_par = 0;                          // bit s: parity of stage s's next "written" phase
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                 float *sc = P.scratch + (size_t)tile * P.n_rows * TS_COLS;
                 for (int e = 0; e < P.n_epi; ++e) {
                     const EpiOp op = epi_sm[e];
                     if (!(op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL))) continue;
                     const uint32_t s = it % TS_ROWRING;
                     ++it;
-                    if (!(op.flags & EPI_STORE_GLOBAL)) continue;   // the epilogue frees such stages itself
+                    if (!(op.flags & EPI_STORE_GLOBAL)) continue;   // the op's stream frees such stages itself
                     mbar_wait(smem_u32(bar_sdone + s), (sdone_par >> s) & 1u);   // all warps have written their columns (and fenced)
                     sdone_par ^= 1u << s;
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -313,106 +333,130 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
+#endif
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = column
+        // ------------------------------------------------------------------ EPI streams: thread = column
+        const int my_stream = warp / TS_EPI_WARPS;
+        const int sw = warp % TS_EPI_WARPS;                    // warp inside the stream
         const int lane_grp = warp & 3;                               // tensor-memory lanes 32*lane_grp.. belong to this warp
-        const int half = (warp - 4) >> 2;                            // this warp takes the chunks NC * half .. NC * half + NC - 1
+        const int half = sw >> 2;                                    // this warp takes the chunks NC * half .. NC * half + NC - 1
         const int col = lane_grp * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         constexpr int NC = TS_MAX_CHUNKS8 / 2;
         static_assert(NC == 4, "a warp's share of an op is at most four chunks = one x32 tensor-memory access");
         const int c0 = half * NC;
-        uint32_t tcount = 0, lit = 0;
+        uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t par = tcount & 1u;
-            const bool prof = P.prof != nullptr && blockIdx.x == 0 && tcount == 1 && threadIdx.x == 128;
-            EpiOp nxt = epi_sm[0];
+            const bool prof = PROF && blockIdx.x == 0 && tcount == 1 && sw == 0 && lane == 0;
+            const uint32_t ring_base = tcount * (uint32_t)P.n_ring_ops;
 #pragma unroll 1
             for (int e = 0; e < P.n_epi; ++e) {
-                const EpiOp op = nxt;
-                nxt = epi_sm[e + 1 < P.n_epi ? e + 1 : e];
-                if (prof) P.prof[6 * e] = clock64();
-                const int nv = op.n_valid;
+                if (epi_sm[e].stream != my_stream) continue;
+                const EpiOp op = epi_sm[e];
+                TS_STAMP(6 * e);
+                const int nv = op.n_valid - c0 * 8;                  // valid rows among this warp's NC * 8
                 const int k = min(NC, max(0, (int)op.n_chunks - c0));   // this warp's chunks of the op (warp uniform)
-                float g[NC * 8];                                     // chunk c0 + c, row i of it at g[8 c + i]
+                uint32_t g[NC * 8];                                  // chunk c0 + c, row i of it at g[8 c + i] (float bits)
                 const bool ring_op = (op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL)) != 0;
-                const uint32_t rs = lit % TS_ROWRING;
-                float *stage_col = rowring + (size_t)rs * (TS_ROWSTAGE_BYTES / 4) + col;
-                if (ring_op) {
-                    mbar_wait(smem_u32(bar_rfull + rs), (lit / TS_ROWRING) & 1u);
-                    ++lit;
-                }
-                if (op.flags & EPI_ADD_GLOBAL) {                     // the rows are staged in the row ring
+                const uint32_t rit = ring_base + op.ring_seq, rs = rit % TS_ROWRING;
+                float *stage_col = rowring + (size_t)rs * (TS_ROWSTAGE_BYTES / 4) + c0 * 8 * TS_COLS + col;
+                if (ring_op) mbar_wait(smem_u32(bar_rfull + rs), (rit / TS_ROWRING) & 1u);   // long done, normally: the loader runs ops ahead
+                const bool rows_first = (op.flags & (EPI_ADD_GLOBAL | EPI_FROM_TMEM)) == EPI_ADD_GLOBAL;
+                if (rows_first) {                                    // a leaf's rows: into registers before any event wait
 #pragma unroll
-                    for (int j = 0; j < NC * 8; ++j) {
-                        const int r = c0 * 8 + j;
-                        g[j] = r < nv ? stage_col[r * TS_COLS] : 0.f;
-                    }
-                    if (!(op.flags & EPI_STORE_GLOBAL)) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(bar_rempty + rs));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NC * 8; ++j) g[j] = 0.f;
+                    for (int j = 0; j < NC * 8; ++j) g[j] = j < nv ? __float_as_uint(stage_col[j * TS_COLS]) : 0u;
                 }
-                if (prof) P.prof[6 * e + 1] = clock64();
-                if (op.wait_mma >= 0) {
-                    mbar_wait(smem_u32(bar_mma + op.wait_mma), par);
-                    tc_fence_after();
-                }
-                if (prof) P.prof[6 * e + 2] = clock64();
+                TS_STAMP(6 * e + 1);
+                if (op.wait_epi >= 0) mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
+                if (op.wait_mma >= 0) mbar_wait(smem_u32(bar_mma + op.wait_mma), par);
+                if (op.wait_epi >= 0 || op.wait_mma >= 0) tc_fence_after();
+                TS_STAMP(6 * e + 2);
                 if (op.flags & EPI_FROM_TMEM) {
-                    uint32_t v[NC * 8];
-                    tmem_ld_chunks(tlane + op.src_col + 8 * c0, k, v);
+                    tmem_ld_chunks(tlane + op.src_col + 8 * c0, k, g);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (op.signal_read >= 0) {                       // the source columns may be overwritten from here on
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(bar_epi + op.signal_read));
+                    }
+#pragma unroll
+                    for (int j = 0; j < NC * 8; ++j) g[j] = j < nv ? g[j] : 0u;   // padding rows / chunks this op does not have
+                    if (op.flags & EPI_ZERO_SRC) tmem_zero_chunks(tlane + op.src_col + 8 * c0, k);
+                } else if (!rows_first) {
+#pragma unroll
+                    for (int j = 0; j < NC * 8; ++j) g[j] = 0u;
+                }
+                TS_STAMP(6 * e + 3);
+                if ((op.flags & EPI_ADD_GLOBAL) && !rows_first) {    // the rows are staged in the row ring
 #pragma unroll
                     for (int j = 0; j < NC * 8; ++j)
-                        if (j < 8 * k) g[j] = (c0 * 8 + j < nv) ? g[j] + __uint_as_float(v[j]) : 0.f;
-                    if (op.flags & EPI_ZERO_SRC) {
-                        uint32_t z[NC * 8];
-#pragma unroll
-                        for (int j = 0; j < NC * 8; ++j) z[j] = 0u;
-                        tmem_st_chunks(tlane + op.src_col + 8 * c0, k, z);
-                    }
+                        if (j < nv) g[j] = __float_as_uint(__uint_as_float(g[j]) + stage_col[j * TS_COLS]);
                 }
-                if (prof) P.prof[6 * e + 3] = clock64();
-                if (op.flags & EPI_STORE_GLOBAL) {                   // into the op's ring stage; the storer bulk-stores it
+#if TS_STAGED_STORES
+                if (op.flags & EPI_STORE_GLOBAL) {                   // into the op's ring stage; the storer bulk-stores it and frees the stage
 #pragma unroll
-                    for (int j = 0; j < NC * 8; ++j) {
-                        const int r = c0 * 8 + j;
-                        if (r < nv) stage_col[r * TS_COLS] = g[j];
-                    }
+                    for (int j = 0; j < NC * 8; ++j)
+                        if (j < nv) stage_col[j * TS_COLS] = __uint_as_float(g[j]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(bar_sdone + rs));
+                } else if (ring_op) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(bar_rempty + rs));
                 }
-                if (prof) P.prof[6 * e + 4] = clock64();
-                if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT)) {
-                    const bool split = (op.flags & EPI_ST_SPLIT) != 0;
-                    uint32_t hi[NC * 8], lo[NC * 8];
+#else
+                if (ring_op) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(bar_rempty + rs));
+                }
+                if (op.flags & EPI_STORE_GLOBAL) {                   // one 128-byte line per warp and row
+                    float *dst = P.scratch + ((size_t)tile * P.n_rows + op.row_out + c0 * 8) * TS_COLS + col;
 #pragma unroll
-                    for (int j = 0; j < NC * 8; ++j) {
-                        const uint32_t u = __float_as_uint(g[j]);
-                        hi[j] = split ? (u & 0xFFFFE000u) : u;
-                        lo[j] = __float_as_uint(g[j] - __uint_as_float(hi[j])) & 0xFFFFE000u;
+                    for (int j = 0; j < NC * 8; ++j)
+                        if (j < nv) dst[j * TS_COLS] = __uint_as_float(g[j]);
+                    if (op.flags & EPI_LAST_FWD_STORE) {
+                        // the forward sweep's rows (all stored by this stream's threads) will be bulk-loaded again by the
+                        // row loader: make them visible to the async proxy, then tell it
+                        __threadfence();
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(bar_fwd));
                     }
-                    tmem_st_chunks(tlane + op.hi_col + 8 * c0, k, hi);
-                    if (split) tmem_st_chunks(tlane + op.lo_col + 8 * c0, k, lo);
                 }
+#endif
+                TS_STAMP(6 * e + 4);
+                if (op.flags & EPI_ST_SPLIT) {                       // lo halves leave 16 columns at a time (registers), hi in place
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t hi = g[16 * h + j] & 0xFFFFE000u;
+                            lo[j] = __float_as_uint(__uint_as_float(g[16 * h + j]) - __uint_as_float(hi)) & 0xFFFFE000u;
+                            g[16 * h + j] = hi;
+                        }
+                        const int kh = k - 2 * h;                    // chunks of this half
+                        if (kh >= 2) tmem_st16(tlane + op.lo_col + 8 * c0 + 16 * h, lo);
+                        else if (kh == 1) tmem_st8(tlane + op.lo_col + 8 * c0 + 16 * h, lo);
+                    }
+                }
+                if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT)) tmem_st_chunks(tlane + op.hi_col + 8 * c0, k, g);
                 if (op.flags & (EPI_ST_RAW | EPI_ST_SPLIT | EPI_ZERO_SRC)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 if (op.signal_epi >= 0) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(bar_epi + op.signal_epi));
                 }
-                if (prof) P.prof[6 * e + 5] = clock64();
+                TS_STAMP(6 * e + 5);
             }
+            // tile boundary: both streams are done with tensor memory (one of them has waited for the last MMA)
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TS_EPI_ALL) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == TS_W_ISSUER) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS) : "memory");
     }
@@ -421,8 +465,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
 }  // namespace
 
 size_t solve_tc_smem_bytes(int n_mma, int n_epi) {
-    return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)TS_ROWRING * TS_ROWSTAGE_BYTES +
-           (size_t)(2 * TS_RING + 3 * TS_ROWRING + 1 + 2 * TS_MAX_EVENTS) * 8 + 16 +
+    return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)TS_ROWRING * TS_ROWSTAGE_BYTES + (size_t)TS_N_BARS * 8 + 16 +
            (size_t)n_mma * sizeof(MmaOp) + (size_t)n_epi * sizeof(EpiOp);
 }
 
@@ -430,15 +473,17 @@ cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, c
     if (n_frames <= 0) return cudaSuccess;
     const size_t smem = solve_tc_smem_bytes(d.ts_n_mma, d.ts_n_epi);
     {   // per function and device, not per handle: set on every launch (another handle may need a different size)
-        cudaError_t e = cudaFuncSetAttribute(k_solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_solve_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_solve_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int n_tiles = 3 * ((n_frames + TS_COLS - 1) / TS_COLS);
     TsParams P{d.ts_mma, d.ts_epi, d.ts_matrix, d.ts_chunk_off, d.ts_n_mma, d.ts_n_epi, d.ts_n_chunks,
-               d.ts_n_mma_events, d.ts_n_epi_events, scratch, d.n_free, n_tiles, d.solve_prof};
+               d.ts_n_mma_events, d.ts_n_epi_events, d.ts_n_ring_ops, scratch, d.n_free, n_tiles, d.solve_prof};
     int grid = d.sm_count;
     if (grid > n_tiles) grid = n_tiles;
-    k_solve_tc<<<grid, TS_THREADS, smem, stream>>>(P);
+    if (d.solve_prof) k_solve_tc<true><<<grid, TS_THREADS, smem, stream>>>(P);     // per-op clocks of one tile (SDFA_SOLVE_PROFILE=1)
+    else k_solve_tc<false><<<grid, TS_THREADS, smem, stream>>>(P);
     count_launch();
     return cudaGetLastError();
 }

@@ -7,6 +7,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -56,7 +57,10 @@ struct Builder {
     int used_slots = 0, used_ring = 0;    // pipelining depth the tensor-memory budget allowed (emit)
     std::string err;
 
-    Builder(HostPlan &hp, int lm) : p(hp), t(hp.tplan), n(hp.n_free), leaf_max(lm) {}
+    Builder(HostPlan &hp, int lm) : p(hp), t(hp.tplan), n(hp.n_free), leaf_max(lm) {
+        if (const char *e = std::getenv("SDFA_TS_STREAMS")) n_streams = std::atoi(e) == 1 ? 1 : 2;
+        if (const char *e = std::getenv("SDFA_TS_EARLY")) early_signals = std::atoi(e) != 0;
+    }
 
     const float *pos(int f) const { return &p.verts[(size_t)p.free_to_vi[f] * 3]; }
 
@@ -245,28 +249,89 @@ struct Builder {
     }
 
     // ---------------------------------------------------------------- program emission
-    std::vector<int> epi_wait_op, mma_wait_op;              // op index in the other stream, -1 none
-    std::vector<char> epi_signals, mma_commits;
-    int last_epi_write[TS_TMEM_COLS], last_epi_read[TS_TMEM_COLS], last_mma_write[TS_TMEM_COLS], last_mma_read[TS_TMEM_COLS];
+    // Streams: 0 / 1 = the EPI streams, 2 = the MMA stream.  EPI ops share one index space (t.epi), MMA ops
+    // theirs (t.mma).  Per tensor-memory column the last op of every stream that wrote / read it; an op waits
+    // for the latest conflicting op of each OTHER stream (read after write, write after read / write).
+    static constexpr int SM = 2;
+    int n_streams = 2;
+    std::vector<int> epi_wait_mma_op, epi_wait_epi_op;      // per EPI op: op index to wait for in the MMA / other EPI stream, -1 none
+    std::vector<std::array<int, 2>> mma_wait_epi_op;        // per MMA op: op index per EPI stream
+    std::vector<char> epi_signals, epi_signals_read, mma_commits;   // per op: someone waits for its end / for its source read
+    std::vector<char> epi_wait_epi_early;                   // per EPI op: the EPI wait is for the other op's read event
+    std::vector<std::array<char, 2>> mma_wait_early;        // per MMA op and EPI stream: likewise
+    int covered_read[3][2];                                 // [s][q]: latest op of EPI stream q whose source read stream s is known to be after
+    bool early_signals = true;
+    int last_write[3][TS_TMEM_COLS], last_read[3][TS_TMEM_COLS];
+    // every stream runs in order, so having waited for op k of a stream implies all its earlier ops; and a wait
+    // is transitive: the op waited for had itself waited (covered[][] at that point) -- skip what is implied
+    int covered[3][3];                                      // covered[s][o]: latest op of stream o that stream s is known to be after
+    std::vector<std::array<int, 3>> epi_cov, mma_cov;       // snapshot of the op's stream's covered[] row when the op ends
     uint32_t chunk_fill = 0;
-    int epi_waited_mma = -1, mma_waited_epi = -1;           // latest op of the other stream each stream has already waited for
 
     struct Range { int c0, c1; };
 
-    void add_epi(EpiOp op, std::vector<Range> reads, std::vector<Range> writes) {
-        int need = -1;
-        const int e = (int)t.epi.size();
-        for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) need = std::max(need, last_mma_write[c]);
-        for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) need = std::max(need, std::max(last_mma_write[c], last_mma_read[c]));
-        for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) last_epi_read[c] = e;
-        for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) last_epi_write[c] = e;
-        // both streams run in order, so an event implies every earlier one of its stream: skip redundant waits
-        if (need <= epi_waited_mma) need = -1;
-        else epi_waited_mma = need;
-        if (need >= 0) mma_commits[need] = 1;
-        epi_wait_op.push_back(need);
+    void absorb(int s, int o, int k) {                      // stream s now waits for op k of stream o
+        covered[s][o] = std::max(covered[s][o], k);
+        const std::array<int, 3> &snap = o == SM ? mma_cov[k] : epi_cov[k];
+        for (int q = 0; q < 3; ++q) if (q != s) covered[s][q] = std::max(covered[s][q], snap[q]);
+    }
+
+    // wait of stream s for op `need` of EPI stream q; `read_only`: only that op's tensor-memory READ conflicts.
+    // Returns -1 when implied by earlier waits, else `need`, with early = the read event suffices.
+    int epi_need(int s, int q, int need_w, int need_r, bool &early) {
+        early = false;
+        if (!early_signals) { need_w = std::max(need_w, need_r); need_r = -1; }
+        if (need_w >= need_r) {
+            if (need_w <= covered[s][q]) return -1;
+            absorb(s, q, need_w);
+            covered_read[s][q] = std::max(covered_read[s][q], need_w);
+            return need_w;
+        }
+        if (need_r <= covered[s][q] || need_r <= covered_read[s][q]) return -1;
+        covered_read[s][q] = need_r;
+        if (need_r > 0) {                                   // everything before it in its stream is complete
+            // ops of stream q before need_r: the latest one
+            int prev = -1;
+            for (int e = need_r - 1; e >= 0; --e) if (t.epi[e].stream == q) { prev = e; break; }
+            if (prev > covered[s][q]) absorb(s, q, prev);
+        }
+        // the op itself has started: what it waited for is implied
+        for (int r = 0; r < 3; ++r) if (r != s && r != q) covered[s][r] = std::max(covered[s][r], epi_cov[need_r][r]);
+        early = true;
+        return need_r;
+    }
+
+    void add_epi(EpiOp op, int s, std::vector<Range> reads, std::vector<Range> writes) {
+        if (n_streams < 2) s = 0;
+        const int e = (int)t.epi.size(), o = 1 - s;
+        int need_m = -1, need_ew = -1, need_er = -1;
+        for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) {
+            need_m = std::max(need_m, last_write[SM][c]);
+            need_ew = std::max(need_ew, last_write[o][c]);
+        }
+        for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) {
+            need_m = std::max(need_m, std::max(last_write[SM][c], last_read[SM][c]));
+            need_ew = std::max(need_ew, last_write[o][c]);
+            need_er = std::max(need_er, last_read[o][c]);
+        }
+        for (auto r : reads) for (int c = r.c0; c < r.c1; ++c) last_read[s][c] = e;
+        for (auto r : writes) for (int c = r.c0; c < r.c1; ++c) last_write[s][c] = e;
+        if (need_m <= covered[s][SM]) need_m = -1;
+        else absorb(s, SM, need_m);
+        bool early = false;
+        const int need_e = epi_need(s, o, need_ew, need_er, early);
+        if (need_m >= 0) mma_commits[need_m] = 1;
+        if (need_e >= 0) (early ? epi_signals_read : epi_signals)[need_e] = 1;
+        epi_wait_mma_op.push_back(need_m);
+        epi_wait_epi_op.push_back(need_e);
+        epi_wait_epi_early.push_back(early);
         epi_signals.push_back(0);
-        op.wait_mma = op.signal_epi = -1;
+        epi_signals_read.push_back(0);
+        covered[s][s] = e;
+        epi_cov.push_back({covered[s][0], covered[s][1], covered[s][2]});
+        op.wait_mma = op.signal_epi = op.wait_epi = op.signal_read = -1;
+        op.stream = (uint16_t)s;
+        op.ring_seq = (op.flags & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL)) ? (uint16_t)t.n_ring_ops++ : (uint16_t)0;
         t.epi.push_back(op);
     }
 
@@ -274,16 +339,27 @@ struct Builder {
     void add_mma(MmaOp op, const std::function<double(int, int)> &bt) {
         const int m = (int)t.mma.size();
         const int K = op.k8 * 8, N = op.n;
-        int need = -1;
-        for (int c = 0; c < K; ++c) need = std::max(need, std::max(last_epi_write[op.a_hi_col + c], last_epi_write[op.a_lo_col + c]));
-        for (int c = 0; c < N; ++c) need = std::max(need, std::max(last_epi_write[op.d_col + c], last_epi_read[op.d_col + c]));
-        for (int c = 0; c < K; ++c) last_mma_read[op.a_hi_col + c] = last_mma_read[op.a_lo_col + c] = m;
-        for (int c = 0; c < N; ++c) last_mma_write[op.d_col + c] = m;
-        if (need <= mma_waited_epi) need = -1;
-        else mma_waited_epi = need;
-        if (need >= 0) epi_signals[need] = 1;
-        mma_wait_op.push_back(need);
+        std::array<int, 2> need = {-1, -1};
+        std::array<char, 2> early = {0, 0};
+        for (int q = 0; q < 2; ++q) {
+            int need_w = -1, need_r = -1;
+            for (int c = 0; c < K; ++c) need_w = std::max(need_w, std::max(last_write[q][op.a_hi_col + c], last_write[q][op.a_lo_col + c]));
+            for (int c = 0; c < N; ++c) {
+                need_w = std::max(need_w, last_write[q][op.d_col + c]);
+                need_r = std::max(need_r, last_read[q][op.d_col + c]);
+            }
+            bool ea = false;
+            need[q] = epi_need(SM, q, need_w, need_r, ea);
+            early[q] = ea;
+        }
+        for (int c = 0; c < K; ++c) last_read[SM][op.a_hi_col + c] = last_read[SM][op.a_lo_col + c] = m;
+        for (int c = 0; c < N; ++c) last_write[SM][op.d_col + c] = m;
+        for (int q = 0; q < 2; ++q) if (need[q] >= 0) (early[q] ? epi_signals_read : epi_signals)[need[q]] = 1;
+        mma_wait_early.push_back(early);
+        mma_wait_epi_op.push_back(need);
         mma_commits.push_back(0);
+        covered[SM][SM] = m;
+        mma_cov.push_back({covered[SM][0], covered[SM][1], covered[SM][2]});
         // tile images: K-blocks of 32, each an [N x 32] K-major SWIZZLE_128B image; hi then lo
         const int kb = (K + 31) / 32;
         const uint32_t half = (uint32_t)kb * N * 128, bytes = 2 * half;
@@ -309,16 +385,19 @@ struct Builder {
                 hi[at] = h;
                 lo[at] = l;
             }
-        op.wait_epi = op.commit_mma = -1;
+        op.wait_epi = op.wait_epi2 = op.commit_mma = -1;
         t.mma.push_back(op);
         t.nk_products += (long long)N * K;
     }
 
     bool emit(const std::vector<int> &post) {
-        std::fill(last_epi_write, last_epi_write + TS_TMEM_COLS, -1);
-        std::fill(last_epi_read, last_epi_read + TS_TMEM_COLS, -1);
-        std::fill(last_mma_write, last_mma_write + TS_TMEM_COLS, -1);
-        std::fill(last_mma_read, last_mma_read + TS_TMEM_COLS, -1);
+        for (int q = 0; q < 3; ++q) {
+            std::fill(last_write[q], last_write[q] + TS_TMEM_COLS, -1);
+            std::fill(last_read[q], last_read[q] + TS_TMEM_COLS, -1);
+            for (int r = 0; r < 3; ++r) covered[q][r] = -1;
+            covered_read[q][0] = covered_read[q][1] = -1;
+        }
+        t.n_streams = n_streams;
         std::vector<int> steps;
         int kmax = 0, nmax = 0, acc_cols = 0, xs_cols = 0;
         for (int v : post) {
@@ -356,7 +435,7 @@ struct Builder {
             op.flags = EPI_ST_RAW;
             op.n_chunks = (uint16_t)(std::min(TS_MAX_NODE, acc_cols - c0) / 8);
             op.hi_col = (uint16_t)c0;
-            add_epi(op, {}, {{c0, c0 + op.n_chunks * 8}});
+            add_epi(op, 0, {}, {{c0, c0 + op.n_chunks * 8}});
         }
         auto emit_prep = [&](int i) {
             const TNode &nd = nodes[steps[i]];
@@ -378,7 +457,7 @@ struct Builder {
             }
             std::vector<Range> wr = {{slot_hi(sl), slot_hi(sl) + k8}, {slot_lo(sl), slot_lo(sl) + k8}};
             if (!nd.children.empty()) wr.push_back({nd.acc_off, nd.acc_off + k8});
-            add_epi(op, rd, wr);
+            add_epi(op, 0, rd, wr);                           // the forward sweep's loads: EPI stream 0
         };
         const int ns = (int)steps.size();
         if (ns == 0) { err = "empty system"; return false; }
@@ -416,7 +495,7 @@ struct Builder {
             op.src_col = (uint16_t)du;
             op.row_out = (uint32_t)nd.row0;
             if (i == ns - 1) op.flags |= EPI_LAST_FWD_STORE;
-            add_epi(op, {{du, du + k8}}, {});
+            add_epi(op, 1, {{du, du + k8}}, {});              // ... and its stores: EPI stream 1
         }
         // ---- backward sweep (reverse post-order: every node after its ancestors)
         int ri = 0;
@@ -445,10 +524,12 @@ struct Builder {
             op.n_valid = (uint16_t)k;
             op.row_in = op.row_out = (uint32_t)nd.row0;
             std::vector<Range> rd, wr;
+            int stream = 0;
             if (!first) {
                 op.flags |= EPI_FROM_TMEM;
                 op.src_col = (uint16_t)dx;
                 rd.push_back({dx, dx + k8});
+                stream = ri & 1;                                  // alternate with the result ring
                 ++ri;
             }
             if (!nd.children.empty()) {
@@ -458,31 +539,41 @@ struct Builder {
                 wr.push_back({nd.xs_off, nd.xs_off + k8});
                 wr.push_back({xs_cols + nd.xs_off, xs_cols + nd.xs_off + k8});
             }
-            add_epi(op, rd, wr);
+            add_epi(op, stream, rd, wr);
         }
         if (!t.mma.empty()) t.mma.back().flags |= MMA_CHUNK_LAST;
         t.chunk_off.push_back((uint32_t)t.matrix.size());
-        // the tile boundary is a full synchronisation: the last EPI op must wait for the last MMA op
+        // the tile boundary is a full synchronisation: the last EPI op waits for the last MMA op, and the kernel
+        // puts a barrier over all EPI warps behind the tile's ops (the MMA stream's first op of the next tile
+        // waits for an EPI op of that tile)
         if (!t.mma.empty()) {
             const int last = (int)t.mma.size() - 1;
-            if (epi_wait_op.back() < last) {
+            if (epi_wait_mma_op.back() < last) {
                 // only possible if the final node had no couplings; wait for everything anyway
-                epi_wait_op.back() = last;
+                epi_wait_mma_op.back() = last;
                 mma_commits[last] = 1;
             }
         }
         // ---- events
         std::vector<int> mma_evt(t.mma.size(), -1), epi_evt(t.epi.size(), -1);
         for (size_t m = 0; m < t.mma.size(); ++m) if (mma_commits[m]) mma_evt[m] = t.n_mma_events++;
-        for (size_t e = 0; e < t.epi.size(); ++e) if (epi_signals[e]) epi_evt[e] = t.n_epi_events++;
+        std::vector<int> epi_evt_read(t.epi.size(), -1);
+        for (size_t e = 0; e < t.epi.size(); ++e) {
+            if (epi_signals_read[e]) epi_evt_read[e] = t.n_epi_events++;
+            if (epi_signals[e]) epi_evt[e] = t.n_epi_events++;
+        }
         if (t.n_mma_events > TS_MAX_EVENTS || t.n_epi_events > TS_MAX_EVENTS) { err = "too many synchronisation events"; return false; }
         for (size_t m = 0; m < t.mma.size(); ++m) {
             t.mma[m].commit_mma = (int16_t)mma_evt[m];
-            t.mma[m].wait_epi = (int16_t)(mma_wait_op[m] >= 0 ? epi_evt[mma_wait_op[m]] : -1);
+            const std::array<int, 2> &w = mma_wait_epi_op[m];
+            t.mma[m].wait_epi = (int16_t)(w[0] >= 0 ? (mma_wait_early[m][0] ? epi_evt_read : epi_evt)[w[0]] : -1);
+            t.mma[m].wait_epi2 = (int16_t)(w[1] >= 0 ? (mma_wait_early[m][1] ? epi_evt_read : epi_evt)[w[1]] : -1);
         }
         for (size_t e = 0; e < t.epi.size(); ++e) {
             t.epi[e].signal_epi = (int16_t)epi_evt[e];
-            t.epi[e].wait_mma = (int16_t)(epi_wait_op[e] >= 0 ? mma_evt[epi_wait_op[e]] : -1);
+            t.epi[e].signal_read = (int16_t)epi_evt_read[e];
+            t.epi[e].wait_mma = (int16_t)(epi_wait_mma_op[e] >= 0 ? mma_evt[epi_wait_mma_op[e]] : -1);
+            t.epi[e].wait_epi = (int16_t)(epi_wait_epi_op[e] >= 0 ? (epi_wait_epi_early[e] ? epi_evt_read : epi_evt)[epi_wait_epi_op[e]] : -1);
         }
         return true;
     }

@@ -17,11 +17,14 @@
 // fixed matrices Bt streamed from L2 as pre-split TF32 hi/lo tile images (3xTF32: A_hi B_hi + A_lo B_hi +
 // A_hi B_lo, fp32 accumulation).
 //
-// The plan is two instruction streams per 128-column tile plus the matrix byte stream:
-//   MMA stream (one issuing thread)      : MmaOp  -- a product group on tensor-memory column ranges
-//   EPI stream (4 warps, thread = column): EpiOp  -- global rows <-> tensor memory, TF32 hi/lo splitting
-// synchronised by single-use-per-tile mbarrier events (an op names at most one event to wait for and at
-// most one to signal; the planner derives them from the column hazards).
+// The plan is three instruction streams per 128-column tile plus the matrix byte stream:
+//   MMA stream (one issuing thread)               : MmaOp  -- a product group on tensor-memory column ranges
+//   two EPI streams (8 warps each, thread = column): EpiOp  -- global rows <-> tensor memory, TF32 hi/lo splitting
+// synchronised by single-use-per-tile mbarrier events (an op names at most one event per other stream to wait
+// for and at most one to signal; the planner derives them from the column hazards).  The forward sweep's loads
+// (rhs rows -> operand slots) run on EPI stream 0 and its stores (u rows) on stream 1; the backward sweep's
+// x ops alternate between the streams with the result ring, so that the tensor-memory round trips of
+// independent tree nodes overlap.  (One EPI stream -- SDFA_TS_STREAMS=1 -- is the round-1 arrangement.)
 #pragma once
 #include <cstdint>
 #include <string>
@@ -53,7 +56,11 @@ struct EpiOp {                // 32 bytes
     uint16_t n_valid;         // rows that exist (the rest of the chunks is zero padding)
     uint16_t src_col, hi_col, lo_col, flags;
     uint32_t row_in, row_out; // scratch rows (tensor order)
-    uint32_t reserved[2];
+    uint16_t stream;          // EPI stream (0 / 1) that executes the op
+    int16_t  wait_epi;        // event of the OTHER EPI stream to wait for (-1: none)
+    uint16_t ring_seq;        // ops that add or store rows: position among them in the tile (row-ring stage = running count % stages)
+    int16_t  signal_read;     // EPI event to signal as soon as the op has READ its tensor-memory source (-1: none): the
+                              // columns may be overwritten while the op still stores rows / writes its own results
 };
 
 enum MmaFlags : uint16_t {
@@ -70,7 +77,9 @@ struct MmaOp {                // 32 bytes
     uint16_t k8;              // K / 8
     uint16_t flags;
     uint32_t b_hi_off, b_lo_off;   // byte offsets of the hi / lo tile images inside the ring stage (1024-aligned)
-    uint32_t reserved[2];
+    int16_t  wait_epi2;       // a second EPI event (of the other EPI stream) to wait for (-1: none)
+    uint16_t pad;
+    uint32_t reserved;
 };
 
 struct TensorPlan {
@@ -83,6 +92,8 @@ struct TensorPlan {
     std::vector<uint8_t> matrix;          // chunk payloads back to back (each 1024-aligned)
     std::vector<uint32_t> chunk_off;      // n_chunks + 1
     int n_mma_events = 0, n_epi_events = 0;
+    int n_streams = 1;                    // EPI streams the ops are dealt to
+    int n_ring_ops = 0;                   // ops per tile that add or store scratch rows (each owns a row-ring stage)
     int n_nodes = 0, n_leaves = 0;
     long long nk_products = 0;            // sum of N*K over all product groups (x3 MMAs each)
     int tmem_fwd = 0, tmem_bwd = 0;       // columns used by the two sweeps

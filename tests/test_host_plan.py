@@ -193,8 +193,13 @@ def test_emulated_config5_picks_smaller_tiles():
 
 def test_tensor_plan_budget(flame_rec_tensor):
     st = flame_rec_tensor.debug("ts_stats")
-    used, valid, n_mma, n_epi, n_chunks, nbytes, ev_m, ev_e, n_nodes, n_leaves, nk, t_f, t_b, smem = [int(x) for x in st]
-    assert used == 1 and valid == 1
+    used, valid, n_mma, n_epi, n_chunks, nbytes, ev_m, ev_e, n_nodes, n_leaves, nk, t_f, t_b, smem, n_streams, n_ring = [int(x) for x in st]
+    assert used == 1 and valid == 1 and n_streams == 2
+    epi = flame_rec_tensor.debug("ts_epi").view(T.EPI_DT)
+    assert n_ring == int(((epi["flags"] & (T.EPI_ADD_GLOBAL | T.EPI_STORE_GLOBAL)) > 0).sum())
+    # the forward sweep's stores all run on one stream (its threads fence them for the backward sweep's bulk loads)
+    fwd_store = ((epi["flags"] & 7) == 5)
+    assert len(set(epi["stream"][fwd_store])) == 1 and (epi["stream"] <= 1).all()
     assert t_f <= 512 and t_b <= 512 and ev_m <= 256 and ev_e <= 256 and smem <= 227 * 1024
     assert nk <= 300_000                      # N*K summed over the products of one 128-column tile
     rows = flame_rec_tensor.debug("scratch_row")

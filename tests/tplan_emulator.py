@@ -1,6 +1,6 @@
 """TEST-ONLY numpy interpreter of the tensor-core solve plan (csrc/tplan.cpp -> kernel K3T, csrc/solve_tc.cu).
 
-Runs the MMA and EPI instruction streams fetched through ``sdfa_debug_get`` the way the kernel does: two
+Runs the MMA stream and the two EPI instruction streams fetched through ``sdfa_debug_get`` the way the kernel does:
 sequential streams that only synchronise through the plan's events, interleaved by a seeded random scheduler,
 MMAs completing asynchronously and in order, tensor memory and the matrix ring poisoned with NaN, and the
 arithmetic restated as 3xTF32 (operands truncated to TF32, fp32 accumulation).  A missing event shows up as
@@ -11,16 +11,16 @@ import numpy as np
 
 f32 = np.float32
 EPI_FROM_TMEM, EPI_ADD_GLOBAL, EPI_STORE_GLOBAL, EPI_ST_RAW, EPI_ST_SPLIT = 1, 2, 4, 8, 16
-EPI_ZERO_SRC = 128
+EPI_LAST_FWD_STORE, EPI_AFTER_STORES, EPI_ZERO_SRC = 32, 64, 128
 MMA_ACCUMULATE, MMA_CHUNK_FIRST, MMA_CHUNK_LAST = 1, 2, 4
 TS_COLS, STAGE_BYTES, TMEM_COLS = 128, 32768, 512
 
 EPI_DT = np.dtype([("wait_mma", "<i2"), ("signal_epi", "<i2"), ("n_chunks", "<u2"), ("n_valid", "<u2"),
                    ("src_col", "<u2"), ("hi_col", "<u2"), ("lo_col", "<u2"), ("flags", "<u2"),
-                   ("row_in", "<u4"), ("row_out", "<u4"), ("r0", "<u4"), ("r1", "<u4")])
+                   ("row_in", "<u4"), ("row_out", "<u4"), ("stream", "<u2"), ("wait_epi", "<i2"), ("ring_seq", "<u2"), ("signal_read", "<i2")])
 MMA_DT = np.dtype([("wait_epi", "<i2"), ("commit_mma", "<i2"), ("d_col", "<u2"), ("a_hi_col", "<u2"),
                    ("a_lo_col", "<u2"), ("n", "<u2"), ("k8", "<u2"), ("flags", "<u2"),
-                   ("b_hi_off", "<u4"), ("b_lo_off", "<u4"), ("r0", "<u4"), ("r1", "<u4")])
+                   ("b_hi_off", "<u4"), ("b_lo_off", "<u4"), ("wait_epi2", "<i2"), ("pad", "<u2"), ("r1", "<u4")])
 
 
 def tf32(x):
@@ -54,7 +54,13 @@ def solve_tile(pl, scratch, seed=0, columns=TS_COLS):
     n_mma_evt, n_epi_evt = int(pl["stats"][6]), int(pl["stats"][7])
     mma_evt, epi_evt = np.zeros(n_mma_evt, bool), np.zeros(n_epi_evt, bool)
     pending = []                          # issued, not yet executed MMA work: ("mma", closure) / ("commit", evt)
-    pm = pe = 0
+    pm = 0
+    streams = [np.flatnonzero(epi["stream"] == q) for q in (0, 1)]   # op indices of each EPI stream, in order
+    pe = [0, 0]
+    held = [None, None]                   # an EPI stream between the two halves of an op: its register values
+    assert len(streams[0]) + len(streams[1]) == len(epi)
+    ring = epi["ring_seq"][(epi["flags"] & (EPI_ADD_GLOBAL | EPI_STORE_GLOBAL)) > 0]
+    assert np.array_equal(ring, np.arange(len(ring))), "ops that use the row ring are numbered in list order"
     chunk = -1
     stage = None
 
@@ -85,7 +91,8 @@ def solve_tile(pl, scratch, seed=0, columns=TS_COLS):
                 tmem[:, d:d + n] = prod
         pending.append(("mma", go))
 
-    def epi_step(op):
+    def epi_read(op):
+        """First half of an EPI op: rows + tensor-memory source -> registers (after it the op signals `signal_read`)."""
         nch, nv, fl = int(op["n_chunks"]), int(op["n_valid"]), int(op["flags"])
         v = np.zeros((columns, 8 * nch), dtype=f32)
         if fl & EPI_ADD_GLOBAL:
@@ -95,8 +102,14 @@ def solve_tile(pl, scratch, seed=0, columns=TS_COLS):
             assert not np.isnan(t[:, :nv]).any(), "EPI reads tensor memory that was never written"
             v[:, :nv] = v[:, :nv] + t[:, :nv]
             if fl & EPI_ZERO_SRC:
+                assert op["signal_read"] < 0
                 tmem[:, int(op["src_col"]):int(op["src_col"]) + 8 * nch] = 0
         v[:, nv:] = 0
+        return v
+
+    def epi_write(op, v):
+        """Second half: registers -> scratch rows / tensor memory (after it the op signals `signal_epi`)."""
+        nch, nv, fl = int(op["n_chunks"]), int(op["n_valid"]), int(op["flags"])
         if fl & EPI_STORE_GLOBAL:
             scratch[int(op["row_out"]):int(op["row_out"]) + nv] = v[:, :nv].T
         if fl & EPI_ST_RAW:
@@ -106,18 +119,40 @@ def solve_tile(pl, scratch, seed=0, columns=TS_COLS):
             tmem[:, int(op["hi_col"]):int(op["hi_col"]) + 8 * nch] = hi
             tmem[:, int(op["lo_col"]):int(op["lo_col"]) + 8 * nch] = tf32(v - hi)
 
+    # the row loader fetches the rows of the EPI_ADD_GLOBAL ops in list order and holds the first backward op's rows
+    # (EPI_AFTER_STORES) back until the forward sweep's last store has been fenced (bar_fwd in the kernel)
+    after = np.flatnonzero((epi["flags"] & EPI_AFTER_STORES) > 0)
+    first_bwd_seq = int(epi["ring_seq"][after[0]]) if len(after) else 1 << 30
+    fwd_done = [False]
+
+    def epi_blocked(q):
+        if pe[q] >= len(streams[q]):
+            return True
+        if held[q] is not None:
+            return False
+        op = epi[streams[q][pe[q]]]
+        if (op["flags"] & EPI_ADD_GLOBAL) and int(op["ring_seq"]) >= first_bwd_seq and not fwd_done[0]:
+            return True
+        return (op["wait_mma"] >= 0 and not mma_evt[op["wait_mma"]]) or (op["wait_epi"] >= 0 and not epi_evt[op["wait_epi"]])
+
+    def mma_blocked():
+        if pm >= len(mma):
+            return True
+        op = mma[pm]
+        return any(w >= 0 and not epi_evt[w] for w in (op["wait_epi"], op["wait_epi2"]))
+
     steps = 0
-    while pe < len(epi) or pm < len(mma) or pending:
+    while pe[0] < len(streams[0]) or pe[1] < len(streams[1]) or pm < len(mma) or pending:
         steps += 1
-        assert steps < 200000, "deadlock"
-        choice = rng.integers(0, 3)
+        assert steps < 400000, "deadlock"
+        choice = rng.integers(0, 4)
         if choice == 0 and pending:
             run_pending(int(rng.integers(1, 4)))
         elif choice == 1 and pm < len(mma):
             op = mma[pm]
-            if op["wait_epi"] >= 0 and not epi_evt[op["wait_epi"]]:
-                if not pending and (pe >= len(epi) or (epi[pe]["wait_mma"] >= 0 and not mma_evt[epi[pe]["wait_mma"]])):
-                    raise AssertionError(f"deadlock: mma op {pm} and epi op {pe} wait for each other")
+            if mma_blocked():
+                if not pending and epi_blocked(0) and epi_blocked(1):
+                    raise AssertionError(f"deadlock: mma op {pm}, epi ops {pe} wait for each other")
                 continue
             if op["flags"] & MMA_CHUNK_FIRST:
                 chunk += 1
@@ -129,15 +164,26 @@ def solve_tile(pl, scratch, seed=0, columns=TS_COLS):
             if op["commit_mma"] >= 0:
                 pending.append(("commit", int(op["commit_mma"])))
             pm += 1
-        elif choice == 2 and pe < len(epi):
-            op = epi[pe]
-            if op["wait_mma"] >= 0 and not mma_evt[op["wait_mma"]]:
+        elif choice >= 2:
+            q = int(choice - 2)
+            if pe[q] >= len(streams[q]):
+                continue
+            if epi_blocked(q):
                 run_pending(1)
                 continue
-            epi_step(op)
+            op = epi[streams[q][pe[q]]]
+            if held[q] is None:
+                held[q] = epi_read(op)
+                if op["signal_read"] >= 0:
+                    epi_evt[op["signal_read"]] = True
+                continue
+            epi_write(op, held[q])
+            held[q] = None
+            if op["flags"] & EPI_LAST_FWD_STORE:
+                fwd_done[0] = True
             if op["signal_epi"] >= 0:
                 epi_evt[op["signal_epi"]] = True
-            pe += 1
+            pe[q] += 1
     assert chunk + 2 == len(chunk_off)
     return scratch
 
