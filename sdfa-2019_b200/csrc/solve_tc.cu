@@ -159,6 +159,18 @@ __device__ __forceinline__ void tmem_st_chunks(uint32_t taddr, int k, const uint
 // phases -- and the registers they need -- apart
 #define TS_STAMP(i) do { if (prof) P.prof[i] = clock64(); else asm volatile("" ::: "memory"); } while (0)
 
+// An MmaOp as the issuing thread wants it: resolved shared-memory barrier addresses, absolute tensor-memory addresses,
+// descriptor words relative to the ring stage -- built once per CTA (thread = op) so that the per-op path of the one
+// thread every product of the tile goes through is a few loads and adds
+struct MmaIssue {              // 48 bytes
+    uint32_t wait0, wait1;     // barrier addresses (0: none)
+    uint32_t commit;           // barrier address (0: none)
+    uint32_t flags_k8;         // MmaFlags | k8 << 8
+    uint32_t idesc, d, a_hi, a_lo;
+    uint32_t b_hi_rel, b_lo_rel;   // (byte offset in the stage) >> 4
+    uint32_t kb_step, pad;
+};
+
 struct TsParams {
     const MmaOp *mma;
     const EpiOp *epi;
@@ -186,12 +198,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     uint64_t *bar_sdone = bar_rempty + TS_ROWRING;
     uint64_t *bar_fwd = bar_sdone + TS_ROWRING, *bar_mma = bar_fwd + 1, *bar_epi = bar_mma + TS_MAX_EVENTS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_epi + TS_MAX_EVENTS);
-    MmaOp *mma_sm = reinterpret_cast<MmaOp *>(tmem_slot + 4);
+    MmaIssue *mma_sm = reinterpret_cast<MmaIssue *>(tmem_slot + 4);
     EpiOp *epi_sm = reinterpret_cast<EpiOp *>(mma_sm + P.n_mma);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < P.n_mma * 8; i += TS_THREADS)
-        reinterpret_cast<uint32_t *>(mma_sm)[i] = reinterpret_cast<const uint32_t *>(P.mma)[i];
     for (int i = threadIdx.x; i < P.n_epi * 8; i += TS_THREADS)
         reinterpret_cast<uint32_t *>(epi_sm)[i] = reinterpret_cast<const uint32_t *>(P.epi)[i];
     if (threadIdx.x == 0) {
@@ -215,6 +225,25 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    for (int i = threadIdx.x; i < P.n_mma; i += TS_THREADS) {
+        const MmaOp op = P.mma[i];
+        MmaIssue q;
+        q.wait0 = op.wait_epi >= 0 ? smem_u32(bar_epi + op.wait_epi) : 0u;
+        q.wait1 = op.wait_epi2 >= 0 ? smem_u32(bar_epi + op.wait_epi2) : 0u;
+        if (q.wait0 == 0u) { q.wait0 = q.wait1; q.wait1 = 0u; }
+        q.commit = op.commit_mma >= 0 ? smem_u32(bar_mma + op.commit_mma) : 0u;
+        q.flags_k8 = (uint32_t)op.flags | ((uint32_t)op.k8 << 8);
+        q.idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
+        q.d = tmem_base + op.d_col;
+        q.a_hi = tmem_base + op.a_hi_col;
+        q.a_lo = tmem_base + op.a_lo_col;
+        q.b_hi_rel = op.b_hi_off >> 4;
+        q.b_lo_rel = op.b_lo_off >> 4;
+        q.kb_step = (uint32_t)op.n * 8u - 6u;                         // (n * 128 - 96) >> 4: on to the next 32-wide K block image
+        q.pad = 0u;
+        mma_sm[i] = q;
+    }
+    __syncthreads();
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
 
@@ -237,45 +266,45 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t par = tcount & 1u;
-                uint32_t stage = 0, slot = 0;
+                uint32_t stage16 = 0, slot = 0;                      // ring stage address >> 4
                 const bool prof = PROF && blockIdx.x == 0 && tcount == 1;
-                MmaOp nxt = mma_sm[0];
+                MmaIssue nxt = mma_sm[0];
                 for (int m = 0; m < P.n_mma; ++m) {
-                    const MmaOp op = nxt;
+                    const MmaIssue op = nxt;
                     nxt = mma_sm[m + 1 < P.n_mma ? m + 1 : m];
                     if (prof) P.prof[6 * P.n_epi + 5 * m] = clock64();
-                    if (op.wait_epi >= 0) mbar_wait(smem_u32(bar_epi + op.wait_epi), par);
-                    if (op.wait_epi2 >= 0) mbar_wait(smem_u32(bar_epi + op.wait_epi2), par);
-                    if (op.wait_epi >= 0 || op.wait_epi2 >= 0) tc_fence_after();
+                    if (op.wait0) {
+                        mbar_wait(op.wait0, par);
+                        if (op.wait1) mbar_wait(op.wait1, par);
+                        tc_fence_after();
+                    }
                     if (prof) P.prof[6 * P.n_epi + 5 * m + 1] = clock64();
-                    if (op.flags & MMA_CHUNK_FIRST) {
+                    if (op.flags_k8 & MMA_CHUNK_FIRST) {
                         slot = it % TS_RING;
                         mbar_wait(smem_u32(bar_full + slot), (it / TS_RING) & 1u);
                         tc_fence_after();
-                        stage = smem_u32(ring + slot * TS_STAGE_BYTES);
+                        stage16 = smem_u32(ring + slot * TS_STAGE_BYTES) >> 4;
                     }
                     if (prof) P.prof[6 * P.n_epi + 5 * m + 2] = clock64();
-                    const uint32_t idesc = TS_IDESC | ((uint32_t)(op.n >> 3) << 17);
-                    const uint32_t d = tmem_base + op.d_col;
-                    uint32_t a_hi = tmem_base + op.a_hi_col, a_lo = tmem_base + op.a_lo_col;
                     // descriptor low words (address >> 4): +2 per K = 8 step inside a 32-wide K block, then on to the next block image
                     constexpr uint64_t DESC_HI = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
-                    uint32_t b_hi = (((stage + op.b_hi_off) >> 4) & 0x3FFFu) | (1u << 16);
-                    uint32_t b_lo = (((stage + op.b_lo_off) >> 4) & 0x3FFFu) | (1u << 16);
-                    const uint32_t kb_step = (uint32_t)op.n * 8u - 6u;               // (n * 128 - 96) >> 4
-                    uint32_t acc = (op.flags & MMA_ACCUMULATE) ? 1u : 0u;
-                    for (uint32_t j = 0; j < op.k8; ++j) {
-                        umma_tf32_ts(d, a_hi, DESC_HI | b_hi, idesc, acc);
-                        umma_tf32_ts(d, a_lo, DESC_HI | b_hi, idesc, 1u);
-                        umma_tf32_ts(d, a_hi, DESC_HI | b_lo, idesc, 1u);
+                    uint32_t a_hi = op.a_hi, a_lo = op.a_lo;
+                    uint32_t b_hi = ((stage16 + op.b_hi_rel) & 0x3FFFu) | (1u << 16);
+                    uint32_t b_lo = ((stage16 + op.b_lo_rel) & 0x3FFFu) | (1u << 16);
+                    uint32_t acc = op.flags_k8 & MMA_ACCUMULATE;
+                    const uint32_t k8 = op.flags_k8 >> 8;
+                    for (uint32_t j = 0; j < k8; ++j) {
+                        umma_tf32_ts(op.d, a_hi, DESC_HI | b_hi, op.idesc, acc);
+                        umma_tf32_ts(op.d, a_lo, DESC_HI | b_hi, op.idesc, 1u);
+                        umma_tf32_ts(op.d, a_hi, DESC_HI | b_lo, op.idesc, 1u);
                         acc = 1u;
                         a_hi += 8; a_lo += 8;
-                        const uint32_t step = (j & 3u) == 3u ? kb_step : 2u;
+                        const uint32_t step = (j & 3u) == 3u ? op.kb_step : 2u;
                         b_hi += step; b_lo += step;
                     }
                     if (prof) P.prof[6 * P.n_epi + 5 * m + 3] = clock64();
-                    if (op.flags & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
-                    if (op.commit_mma >= 0) tc_commit(smem_u32(bar_mma + op.commit_mma));
+                    if (op.flags_k8 & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
+                    if (op.commit) tc_commit(op.commit);
                     if (prof) P.prof[6 * P.n_epi + 5 * m + 4] = clock64();
                 }
             }
@@ -466,7 +495,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
 
 size_t solve_tc_smem_bytes(int n_mma, int n_epi) {
     return 1024 + (size_t)TS_RING * TS_STAGE_BYTES + (size_t)TS_ROWRING * TS_ROWSTAGE_BYTES + (size_t)TS_N_BARS * 8 + 16 +
-           (size_t)n_mma * sizeof(MmaOp) + (size_t)n_epi * sizeof(EpiOp);
+           (size_t)n_mma * sizeof(MmaIssue) + (size_t)n_epi * sizeof(EpiOp);
 }
 
 cudaError_t launch_solve_tc(const DevicePlan &d, float *scratch, int n_frames, cudaStream_t stream) {
