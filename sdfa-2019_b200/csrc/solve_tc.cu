@@ -157,7 +157,10 @@ __device__ __forceinline__ void tmem_st_chunks(uint32_t taddr, int k, const uint
 
 // a profiling stamp, or (regular build) a point the compiler does not move memory operations across: keeps an op's
 // phases -- and the registers they need -- apart
-#define TS_STAMP(i) do { if (prof) P.prof[i] = clock64(); else asm volatile("" ::: "memory"); } while (0)
+#ifndef TS_PROF_LIGHT
+#define TS_PROF_LIGHT 0           // 1: the profiling build only stamps the start of every MMA op (least perturbation)
+#endif
+#define TS_STAMP(i) do { if (prof && !TS_PROF_LIGHT) P.prof[i] = clock64(); else asm volatile("" ::: "memory"); } while (0)
 
 // An MmaOp as the issuing thread wants it: resolved shared-memory barrier addresses, absolute tensor-memory addresses,
 // descriptor words relative to the ring stage -- built once per CTA (thread = op) so that the per-op path of the one
@@ -278,14 +281,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                         if (op.wait1) mbar_wait(op.wait1, par);
                         tc_fence_after();
                     }
-                    if (prof) P.prof[6 * P.n_epi + 5 * m + 1] = clock64();
+                    if (prof && !TS_PROF_LIGHT) P.prof[6 * P.n_epi + 5 * m + 1] = clock64();
                     if (op.flags_k8 & MMA_CHUNK_FIRST) {
                         slot = it % TS_RING;
                         mbar_wait(smem_u32(bar_full + slot), (it / TS_RING) & 1u);
                         tc_fence_after();
                         stage16 = smem_u32(ring + slot * TS_STAGE_BYTES) >> 4;
                     }
-                    if (prof) P.prof[6 * P.n_epi + 5 * m + 2] = clock64();
+                    if (prof && !TS_PROF_LIGHT) P.prof[6 * P.n_epi + 5 * m + 2] = clock64();
                     // descriptor low words (address >> 4): +2 per K = 8 step inside a 32-wide K block, then on to the next block image
                     constexpr uint64_t DESC_HI = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
                     uint32_t a_hi = op.a_hi, a_lo = op.a_lo;
@@ -302,10 +305,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_solve_tc(TsParams P) {
                         const uint32_t step = (j & 3u) == 3u ? op.kb_step : 2u;
                         b_hi += step; b_lo += step;
                     }
-                    if (prof) P.prof[6 * P.n_epi + 5 * m + 3] = clock64();
+                    if (prof && !TS_PROF_LIGHT) P.prof[6 * P.n_epi + 5 * m + 3] = clock64();
                     if (op.flags_k8 & MMA_CHUNK_LAST) { tc_commit(smem_u32(bar_empty + slot)); ++it; }
                     if (op.commit) tc_commit(op.commit);
-                    if (prof) P.prof[6 * P.n_epi + 5 * m + 4] = clock64();
+                    if (prof && !TS_PROF_LIGHT) P.prof[6 * P.n_epi + 5 * m + 4] = clock64();
                 }
             }
         }
