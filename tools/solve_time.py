@@ -1,4 +1,4 @@
-"""Solve-kernel time of a get_mesh_batch call (library's own CUDA events), for A/B runs: SDFA_LIB / SDFA_TS_* in the environment."""
+"""Per-kernel times (solve, output, gather assembly) of a get_mesh_batch call (library's own CUDA events), for A/B runs: SDFA_LIB / SDFA_TS_* in the environment."""
 import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "sdfa-2019_b200")]
@@ -14,12 +14,13 @@ for _ in range(3):
     rec.get_mesh_batch(dg, out=out)
 torch.cuda.synchronize()
 rec.set_timing(True)
-t = []
+t, to, ta = [], [], []
 for _ in range(8):
     rec.get_mesh_batch(dg, out=out)
-    t.append(rec.last_timing()["solve_ms"])
+    lt = rec.last_timing()
+    t.append(lt["solve_ms"]); to.append(lt["output_ms"]); ta.append(lt["assembly_ms"])
 ref = D.Reconstructor(V, F, cnsts=nfv, device=0, solver="simt")
 rec.set_timing(False)
 a = rec.get_mesh_batch(dg[:4096]); b = ref.get_mesh_batch(dg[:4096])
-print(f"solve_ms min {min(t):.4f} median {sorted(t)[len(t)//2]:.4f}  |tensor-simt| {float((a-b).abs().max()):.3e}  "
+print(f"solve_ms min {min(t):.4f} median {sorted(t)[len(t)//2]:.4f}  output_ms min {min(to):.4f}  assembly(gather)_ms min {min(ta):.4f}  |tensor-simt| {float((a-b).abs().max()):.3e}  "
       f"env {dict((k, v) for k, v in os.environ.items() if k.startswith('SDFA_'))}")
