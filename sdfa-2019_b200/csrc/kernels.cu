@@ -7,6 +7,8 @@
 // Numerics: everything is float32 and works on the DISPLACEMENT from the identity deformation:
 //   x = x_base + M^-1 A^T (T^T - I),  x_base = M^-1 A^T (stack(I) - A_r C) computed in fp64 on the host,
 // which keeps the result within 1e-6 x bbox of the reference's fp64 path.
+#include <cuda.h>
+
 #include "device_plan.hpp"
 #include "plan.hpp"
 
@@ -592,6 +594,128 @@ __global__ void __launch_bounds__(ASM_THREADS, 1) k_assemble_gather2(AsmParams P
     }
 }
 
+// Gather variant, third generation: k_assemble_gather2 with the copies handed to the TMA engine.  The dgrad tensor is a 2-D
+// tensor map [frame][floats of a row]; an equation's 64 spans (one per frame of the tile, 48 bytes each, 359 KB apart) are
+// ONE cp.async.bulk.tensor box {12 floats, 64 frames} issued by one lane into the warp's ring stage, completion on a
+// per-stage mbarrier (frames past the batch are zero-filled by the engine).  The stage image, the conflict-free LDS.128
+// pull and everything behind it are the second generation's.
+__device__ __forceinline__ void ag_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <int AG_STAGES>
+__global__ void __launch_bounds__(ASM_THREADS, 1) k_assemble_gather3(AsmParams P, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float acc[];                    // [row][3][64], frame pairing (l, l + 32)
+    constexpr int CT = COMPACT_TILE;
+    const int4 blk = P.blocks[blockIdx.x];
+    const int n_rows = blk.w - blk.z;
+    const int frame0 = blockIdx.y * CT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int acc_floats = (P.max_rows * 3 * CT + 31) & ~31;
+    // ring stages are TMA destinations: 128-byte aligned whatever the dynamic shared memory's own base is
+    float *ring0 = acc + acc_floats + ((128u - (smem_u32(acc + acc_floats) & 127u)) & 127u) / 4u;
+    float *ring = ring0 + warp * (AG_STAGES * AG_REC);
+    int4 *walk_sh = reinterpret_cast<int4 *>(ring0 + ASM_WARPS * (AG_STAGES * AG_REC));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(walk_sh + P.max_walk * ASM_WARPS) + warp * AG_STAGES;
+    for (int i = threadIdx.x; i < n_rows * 3 * CT; i += ASM_THREADS) acc[i] = 0.f;
+    {
+        const int w0 = P.warp_ptr[blockIdx.x * ASM_WARPS], w1 = P.warp_ptr[blockIdx.x * ASM_WARPS + ASM_WARPS];
+        for (int i = threadIdx.x; i < w1 - w0; i += ASM_THREADS) walk_sh[i] = P.walk[w0 + i];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < AG_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    const int4 *walk = walk_sh + (P.warp_ptr[blockIdx.x * ASM_WARPS + warp] - P.warp_ptr[blockIdx.x * ASM_WARPS]);
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    __syncthreads();                                                 // accumulator zeroed, walks in shared memory, barriers live
+    const int4 *wi = walk;                                           // issue pointer: AG_STAGES entries ahead of the transform
+    auto issue = [&](int stage) {
+        const int4 ent = *wi;
+        if (ent.x != ASM_SCHED_END) ++wi;
+        if (ent.x >= 0 && ent.y >= 0 && lane == 0) {
+            const uint32_t bar = bars_u32 + 8u * (uint32_t)stage, dst = ring_u32 + 4u * AG_REC * (uint32_t)stage;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * AG_REC) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(&tmap), "r"((ent.y * 9) & ~3), "r"(frame0), "r"(bar) : "memory");
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < AG_STAGES; ++i) issue(i);
+    auto meta = [&](const int4 e, float4 &a, float4 &b) {
+        if (e.x >= 0) { a = __ldg(P.eq_meta + (size_t)(blk.x + e.x) * 2); b = __ldg(P.eq_meta + (size_t)(blk.x + e.x) * 2 + 1); }
+    };
+    float4 m0n = make_float4(0.f, 0.f, 0.f, 0.f), m1n = m0n;
+    meta(*walk, m0n, m1n);
+    uint32_t phase = 0;                                              // bit s: parity of stage s's next completion
+    for (int n = 0, stage = 0;; ++n, stage = stage + 1 == AG_STAGES ? 0 : stage + 1) {
+        const int4 ent = *walk++;
+        const float4 m0 = m0n, m1 = m1n;
+        if (ent.x != ASM_SCHED_END) meta(*walk, m0n, m1n);
+        const bool rec = ent.x >= 0 && ent.y >= 0;
+        float4 wa[3], wb[3];
+        if (rec) {
+            ag_mbar_wait(bars_u32 + 8u * (uint32_t)stage, (phase >> stage) & 1u);   // the box of entry n has landed
+            phase ^= 1u << stage;
+            const float4 *st = reinterpret_cast<const float4 *>(ring + stage * AG_REC);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { wa[c] = st[3 * lane + c]; wb[c] = st[3 * (lane + 32) + c]; }
+        }
+        __syncwarp();                                                // the stage is free: refill it with entry n + AG_STAGES
+        issue(stage);
+        if (ent.x == ASM_SCHED_END) break;
+        if (ent.x == ASM_SCHED_BARRIER) { __syncthreads(); continue; }
+        float2 d[9];
+        if (rec) {
+            switch ((ent.y * 9) & 3) {
+                case 0: ag_select<0>(wa, wb, d); break;
+                case 1: ag_select<1>(wa, wb, d); break;
+                case 2: ag_select<2>(wa, wb, d); break;
+                default: ag_select<3>(wa, wb, d); break;
+            }
+        }
+        eq_apply2(acc, lane, P.mode, ent.y, d, m0, m1);
+    }
+    __syncthreads();
+    // write-out: position 2l of a line is frame l, 2l + 1 is frame l + 32
+    const int fa = frame0 + lane, fb = fa + 32;
+    float *dst_a = P.rhs + (long long)(fa / P.L.FL) * P.L.tile_stride + fa % P.L.FL;
+    float *dst_b = P.rhs + (long long)(fb / P.L.FL) * P.L.tile_stride + fb % P.L.FL;
+    const float2 *acc2 = reinterpret_cast<const float2 *>(acc) + lane;
+    for (int line = warp; line < n_rows * 3; line += ASM_WARPS) {
+        const int r = line / 3, c = line - 3 * r;
+        const float2 v = acc2[line * (CT / 2)];
+        const long long o = (long long)P.row_perm[blk.z + r] * P.L.row_stride + c * P.L.c_stride;
+        dst_a[o] = fa < P.n_frames ? v.x : 0.f;
+        dst_b[o] = fb < P.n_frames ? v.y : 0.f;
+    }
+}
+
+size_t assemble_gather3_smem(const DevicePlan &d, int stages) {
+    return (size_t)((d.asm_max_rows * 3 * COMPACT_TILE + 31) & ~31) * sizeof(float) + (size_t)ASM_WARPS * stages * AG_REC * sizeof(float) +
+           (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4) + (size_t)ASM_WARPS * stages * 8 + 128;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
 size_t assemble_gather2_smem(const DevicePlan &d, int stages) {
     return (size_t)((d.asm_max_rows * 3 * COMPACT_TILE + 3) & ~3) * sizeof(float) + (size_t)ASM_WARPS * stages * AG_REC * sizeof(float) +
            (size_t)d.asm_max_walk * ASM_WARPS * sizeof(int4);
@@ -608,6 +732,23 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
         cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
+    } else if (d.asm_gather_gen >= 3 && frame_stride % 4 == 0 && reinterpret_cast<uintptr_t>(dgrad) % 16 == 0 && encode_tiled_fn() &&
+               assemble_gather3_smem(d, 2) <= (size_t)227 * 1024) {
+        // the dgrad tensor as a 2-D tensor map [frame][row floats], box = {12 floats, 64 frames}
+        CUtensorMap tmap;
+        const cuuint64_t dims[2] = {(cuuint64_t)frame_stride, (cuuint64_t)n_frames};
+        const cuuint64_t strides[1] = {(cuuint64_t)frame_stride * 4};
+        const cuuint32_t box[2] = {12, (cuuint32_t)COMPACT_TILE}, estr[2] = {1, 1};
+        if (encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(dgrad), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+        const bool three = assemble_gather3_smem(d, 3) <= (size_t)227 * 1024;
+        const size_t smem = assemble_gather3_smem(d, three ? 3 : 2);
+        auto kern = three ? k_assemble_gather3<3> : k_assemble_gather3<2>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, ASM_THREADS, smem, stream>>>(P, tmap);
     } else if (d.asm_gather_gen >= 2 && (long long)(COMPACT_TILE - 1) * frame_stride + 12 < 0x7fffffffLL && frame_stride % 4 == 0 &&
                reinterpret_cast<uintptr_t>(dgrad) % 16 == 0) {   // 16-byte copies of aligned spans
         // as many stages (equations in flight per warp) as fit beside the accumulator

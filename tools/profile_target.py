@@ -1,6 +1,6 @@
 """Target of the ncu captures (profiles/): the bench's batch (75 600 frames) through both batched entry points --
 three decode + reconstruction calls (k_split16 x2, k_decode_tc16, k_assemble, k_solve_tc, k_output), then three calls
-on the reference-layout dgrad (k_assemble_gather2, k_solve_tc, k_output).  L2 is flushed between calls like in bench.py."""
+on the reference-layout dgrad (k_assemble_gather3, k_solve_tc, k_output).  L2 is flushed between calls like in bench.py."""
 import os
 import sys
 
