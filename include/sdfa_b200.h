@@ -52,8 +52,8 @@ int sdfa_create(sdfa_handle **out, const float *verts, int n_verts, const uint32
  *   solver=auto|simt|tensor   which solve kernel (auto: the tcgen05 block solve when the template fits, else SIMT sweeps)
  *   pipe_chunk=N              frames per chunk of large batches (0 = never chunk); see sdfa_set_option
  *   frames_per_tile, asm_rows, ts_leaf   tuning knobs of the planners
- *   asm_gather=1|2|3         assembly kernel for reference-layout dgrad (3: TMA tensor-map boxes, default; 2: per-warp cp.async
- *                            rings; 1: first generation)
+ *   asm_gather=1|2|3         assembly kernel for reference-layout dgrad (3: TMA tensor-map boxes; 2: per-warp cp.async rings;
+ *                            1: first generation; default: 3 for rows up to 1 MB, else 2)
  *   decode=f16|tf32          decode kernel: FP16 hi/lo split (default when the basis widths fit) or the TF32 split
  *   output=1|2, output_frames=8|16|32   output kernel generation and frames per CTA (default 2, 8)
  * An unknown key is SDFA_ERR_ARG.  (The SDFA_* environment variables of the same names are read at creation as

@@ -366,7 +366,7 @@ int sdfa_create_with(sdfa_handle **out, const float *verts, int n_verts, const u
     }
     {
         const std::string g = setting("asm_gather", "SDFA_ASM_GATHER");
-        h->dev.asm_gather_gen = g.empty() ? 3 : std::atoi(g.c_str());
+        h->dev.asm_gather_gen = g.empty() ? 0 : std::atoi(g.c_str());   // 0: chosen per call by the row size
         const std::string og = setting("output", "SDFA_OUTPUT");
         h->dev.out_gen = og.empty() ? 2 : std::atoi(og.c_str());
         const std::string of = setting("output_frames", "SDFA_OUTPUT_FRAMES");

@@ -32,7 +32,9 @@ struct DevicePlan {
     int asm_max_walk = 0;
     int out_fc = 8;                         // frames per CTA of k_output2 (8, 16 or 32): 8 keeps the set of lines written at any one time compact (1.41 -> 1.23 ms)
     int out_gen = 2;                        // output kernel: 2 = k_output2 (direct 16-byte loads), 1 = k_output (staged)
-    int asm_gather_gen = 3;                 // assembly kernel for reference-layout dgrad: 3 = k_assemble_gather3 (TMA tensor-map boxes), 2 = k_assemble_gather2 (cp.async rings), 1 = k_assemble_gather
+    int asm_gather_gen = 0;                 // assembly kernel for reference-layout dgrad: 3 = k_assemble_gather3 (TMA tensor-map boxes), 2 = k_assemble_gather2
+                                            // (cp.async rings), 1 = k_assemble_gather, 0 = 3 for rows up to 1 MB (FLAME: 359 KB, 3.70 -> 2.82 ms), else 2 (the
+                                            // twice-subdivided template's 5.7 MB rows measure 11.0 ms with boxes against 9.7 ms with the rings)
     int32_t        *asm_eq_src_local = nullptr; // source triangle per block-local equation
     const int32_t  *asm_row_ptr = nullptr;      // CSR incidence of the block rows (gather variant)
     const uint16_t *asm_inc = nullptr;

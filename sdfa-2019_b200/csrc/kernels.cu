@@ -732,7 +732,8 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
         cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k_assemble<<<grid, ASM_THREADS, smem, stream>>>(P);
-    } else if (d.asm_gather_gen >= 3 && frame_stride % 4 == 0 && reinterpret_cast<uintptr_t>(dgrad) % 16 == 0 && encode_tiled_fn() &&
+    } else if ((d.asm_gather_gen >= 3 || (d.asm_gather_gen == 0 && frame_stride <= 262144)) && frame_stride % 4 == 0 &&
+               reinterpret_cast<uintptr_t>(dgrad) % 16 == 0 && encode_tiled_fn() &&
                assemble_gather3_smem(d, 2) <= (size_t)227 * 1024) {
         // the dgrad tensor as a 2-D tensor map [frame][row floats], box = {12 floats, 64 frames}
         CUtensorMap tmap;
@@ -749,7 +750,7 @@ cudaError_t launch_assembly(const DevicePlan &d, const float *dgrad, long long f
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kern<<<grid, ASM_THREADS, smem, stream>>>(P, tmap);
-    } else if (d.asm_gather_gen >= 2 && (long long)(COMPACT_TILE - 1) * frame_stride + 12 < 0x7fffffffLL && frame_stride % 4 == 0 &&
+    } else if ((d.asm_gather_gen >= 2 || d.asm_gather_gen == 0) && (long long)(COMPACT_TILE - 1) * frame_stride + 12 < 0x7fffffffLL && frame_stride % 4 == 0 &&
                reinterpret_cast<uintptr_t>(dgrad) % 16 == 0) {   // 16-byte copies of aligned spans
         // as many stages (equations in flight per warp) as fit beside the accumulator
         const bool three = assemble_gather2_smem(d, 3) <= (size_t)227 * 1024;

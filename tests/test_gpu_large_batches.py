@@ -353,8 +353,9 @@ def test_kernel_generations_agree(flame):
         assert np.array_equal(dec, base_dec) and np.array_equal(rec, base_rec), opts
     dec, rec = run({"asm_gather": 1})
     assert np.array_equal(dec, base_dec) and np.abs(rec - base_rec).max() <= 1e-7
-    dec, rec = run({"asm_gather": 2})                          # the same arithmetic fed by cp.async rings instead of tensor-map boxes: bit-equal
-    assert np.array_equal(dec, base_dec) and np.array_equal(rec, base_rec)
+    for gen in (2, 3):                                         # the same arithmetic fed by cp.async rings / by tensor-map boxes: bit-equal
+        dec, rec = run({"asm_gather": gen})
+        assert np.array_equal(dec, base_dec) and np.array_equal(rec, base_rec), gen
     dec, rec = run({"decode": "tf32"})
     assert np.array_equal(rec, base_rec) and np.abs(dec - base_dec).max() <= 1e-7
     chk = _checker(V, F, nfv)
