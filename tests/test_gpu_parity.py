@@ -331,6 +331,28 @@ def test_tensor_and_simt_solvers_agree(chk, flame):
     assert np.array_equal(rt.get_mesh_batch(dg[200:201])[0], a[200])
 
 
+def test_tensor_plan_variants_are_bit_equal(flame):
+    """The planner's alternatives of the K3T plan -- one epilogue stream instead of two, no separate read events -- move
+    the same values through the same products in the same order: bit-equal results, over many tiles per CTA."""
+    import os
+    import torch
+    V, F, nfv = flame["V"], flame["F"], flame["nfv"]
+    dg = torch.from_numpy(W.iid_dgrad(64, len(F), sigma=0.05, seed=31)).cuda().repeat(400, 1)      # 25 600 frames: 600 tiles
+    outs = []
+    for env in ({}, {"SDFA_TS_STREAMS": "1"}, {"SDFA_TS_EARLY": "0"}):
+        os.environ.update(env)
+        try:
+            r = D.Reconstructor(V, F, cnsts=nfv, device=0, solver="tensor")
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert int(r.debug("ts_stats")[14]) == (1 if env.get("SDFA_TS_STREAMS") == "1" else 2)
+        outs.append(r.get_mesh_batch(dg))
+        r.close()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(outs[0][:64], outs[0][-64:])            # every tile of every persistent CTA
+
+
 def test_config3_batch_sizes_give_identical_frames(rec, flame):
     """Config 3 (solve sweep over RHS batches 64..4096): the same frames reconstructed in batches of different size
     are bit-identical -- tiles are independent and the summation orders are fixed (no atomics anywhere)."""

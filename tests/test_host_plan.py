@@ -227,6 +227,32 @@ def test_tensor_emulated_flame_frames_match_oracle(flame_rec_tensor, flame, gold
         assert np.array_equal(out, first)     # the result does not depend on the interleaving
 
 
+def test_tensor_emulated_plan_variants(flame, golden_flame):
+    """One epilogue stream (SDFA_TS_STREAMS=1) and no separate read events (SDFA_TS_EARLY=0): the same results as the
+    default plan under the emulator's random interleavings."""
+    V, F, nfv = flame["V"], flame["F"], flame["nfv"]
+    free = np.setdiff1d(np.arange(len(V)), nfv)
+    dg = W.iid_dgrad(2, len(F), sigma=0.01, seed=0)
+    outs = []
+    for env in ({}, {"SDFA_TS_STREAMS": "1"}, {"SDFA_TS_EARLY": "0"}):
+        os.environ.update(env)
+        try:
+            r = D.Reconstructor(V, F, cnsts=nfv, device=-1, solver="tensor")
+        finally:
+            for k in env:
+                del os.environ[k]
+        epi = r.debug("ts_epi").view(T.EPI_DT)
+        if env.get("SDFA_TS_STREAMS") == "1":
+            assert (epi["stream"] == 0).all()
+        if env.get("SDFA_TS_EARLY") == "0":
+            assert (epi["signal_read"] < 0).all()
+        out = T.solve(r, E.assemble(r, dg), seed=5)
+        for i in range(2):
+            assert np.abs(out[i][free] - golden_flame["iid_free_verts"][i]).max() < 0.1 * flame["tol"]
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 def test_tensor_emulated_large_deformation(flame_rec_tensor, flame, golden_flame):
     V, F, nfv, nft = flame["V"], flame["F"], flame["nfv"], flame["nft"]
     free = np.setdiff1d(np.arange(len(V)), nfv)
