@@ -15,12 +15,14 @@
 //   warp 16   streamer  : matrix chunks -> ring (mbarrier full / empty)
 //   warp 17   issuer    : one thread walks the MmaOp stream
 //   warp 18   row loader: the scratch rows the EpiOp streams will add, TMA bulk copies into a second ring, ops ahead
+//   warp 19   row storer: bulk-stores the rows an op wrote into its ring stage, then frees the stage
 //   warps 0-7 EPI stream 0, warps 8-15 EPI stream 1: thread = column = tensor-memory lane (two warps per lane
-//             quarter split an op's chunks); each walks its own ops of the EpiOp list.  Rows leave as plain
-//             coalesced stores (one 128-byte line per warp and row).
-// The three instruction streams synchronise through single-use-per-tile mbarrier events chosen by the planner; a
-// named barrier over the EPI warps closes a tile.  Per-op latencies (a tensor-memory round trip, the hand-off to the
-// other stream) bound a tile, not bandwidth: two EPI streams let the round trips of independent tree nodes overlap.
+//             quarter split an op's chunks); each walks its own ops of the EpiOp list.
+// The three instruction streams synchronise through single-use-per-tile mbarrier events chosen by the planner (an op
+// that only reads columns another stream will overwrite signals a separate event right after its tcgen05.ld); a named
+// barrier over the EPI warps closes a tile.  The issuer works from MmaIssue records resolved once per CTA.  Per-op
+// latencies (a tensor-memory round trip, the hand-off to the other stream, the issuer's per-op work) bound a tile, not
+// bandwidth: two EPI streams let the round trips of independent tree nodes overlap.
 #include "device_plan.hpp"
 
 namespace sdfa {
