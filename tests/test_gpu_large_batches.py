@@ -363,3 +363,55 @@ def test_kernel_generations_agree(flame):
     for i in (0, 63, 64, n - 1):
         want = chk.get_mesh(dgh[i].astype(np.float64), vert_cnsts=V[nfv])
         assert np.abs(base_dec[i] - want).max() <= tol and np.abs(base_rec[i] - want).max() <= tol
+
+
+def test_no_write_outside_the_callers_buffers(flame):
+    """compute-sanitizer is closed on this pool, so the bounds of what the kernels write into CALLER-provided device buffers
+    are checked here: every output buffer sits between two guard regions of a recognisable bit pattern that must survive
+    the call -- vertices (full and free-rows layout, both entry points), the compact dgrad of sdfa_decode_compact_dev
+    (written by the decode kernel in 64-frame tiles, both kernel generations) -- at frame counts around every tile size."""
+    import torch
+    from deformation._native import check, lib, ptr
+    V, F, nfv, nft = flame["V"], flame["F"], flame["nfv"], flame["nft"]
+    pca = W.random_pca(len(F), seed=1, zero_tris=nft)
+    GUARD, PAT = 1 << 16, 0x7FC0BEEF                           # floats per guard region; a NaN payload no kernel produces
+
+    def guarded(n_floats):
+        buf = torch.full((GUARD + n_floats + GUARD,), PAT, dtype=torch.int32, device="cuda")
+        return buf, buf[GUARD:GUARD + n_floats].view(torch.float32)
+
+    def intact(buf, n_floats):
+        return bool((buf[:GUARD] == PAT).all()) and bool((buf[GUARD + n_floats:] == PAT).all())
+
+    for opts in ({}, {"decode": "tf32"}):
+        r = D.Reconstructor(V, F, cnsts=nfv, device=0, options=opts)
+        r.set_pca(*pca)
+        slots = lib.sdfa_compact_layout(r._h, None, 0)
+        T = int(r.debug("compact_tile")[0])
+        for n in (1, 31, 33, 63, 64, 65, 127, 128, 129, 255, 257, 300):
+            xs, xr = (torch.from_numpy(a).cuda() for a in W.random_coeffs(n, seed=n))
+            s = torch.cuda.current_stream().cuda_stream
+            # vertices, both layouts, decode path
+            for free_only, rows in ((False, len(V)), (True, r.n_free)):
+                buf, out = guarded(n * rows * 3)
+                r.decode_and_get_mesh(xs, xr, out=out.view(n, rows, 3), free_only=free_only)
+                torch.cuda.synchronize()
+                assert intact(buf, n * rows * 3), (opts, n, free_only)
+                assert not bool((out.view(torch.int32) == PAT).any()), (opts, n, free_only)      # and every element was written
+            # the compact dgrad: whole 64-frame tiles
+            nc = (n + T - 1) // T * slots * T
+            buf, cd = guarded(nc)
+            check(lib.sdfa_decode_compact_dev(r._h, ptr(xs.data_ptr()), ptr(xr.data_ptr()), n, ptr(cd.data_ptr()), ptr(s)))
+            torch.cuda.synchronize()
+            assert intact(buf, nc), (opts, n, "compact")
+            if opts:
+                continue
+            # vertices from a reference-layout dgrad
+            dg = r.decode_dgrad(xs, xr)
+            for free_only, rows in ((False, len(V)), (True, r.n_free)):
+                buf, out = guarded(n * rows * 3)
+                r.get_mesh_batch(dg, out=out.view(n, rows, 3), free_only=free_only)
+                torch.cuda.synchronize()
+                assert intact(buf, n * rows * 3), (n, free_only, "dgrad")
+                assert not bool((out.view(torch.int32) == PAT).any()), (n, free_only, "dgrad")
+        r.close()
