@@ -583,7 +583,13 @@ def main():
         barrier()
         return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / steps
 
+    t_start = time.time()
+
+    def trace(leg):                                 # progress on stderr (every rank): which leg a failed run was in
+        print(f"bench.py[rank {rank}] +{time.time() - t_start:6.1f}s {leg}", file=sys.stderr, flush=True)
+
     # ---- the timed step, then parity of what it just wrote
+    trace("headline: decode + reconstruction")
     launches0 = D.lib.sdfa_launch_count()
     with ClockSampler(local) as clocks:
         ms_step = timed(lambda: rec.decode_and_get_mesh(xs_d, xr_d, out=out), args.steps, args.warmup)
@@ -594,6 +600,7 @@ def main():
     out_samples = out[torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
 
     # ---- the literal metric: dgrad resident in HBM (gather assembly + solve + output)
+    trace("dgrad resident")
     dgrad = rec.decode_dgrad(xs_d, xr_d)            # [n, 89784] fp32
     ms_dgrad = timed(lambda: rec.get_mesh_batch(dgrad, out=out), args.steps, args.warmup)
     out_samples_dgrad = out[torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
@@ -606,6 +613,7 @@ def main():
     ms_sentence = timed(lambda: rec.decode_and_get_mesh(xs_d[:one], xr_d[:one], out=out_one), max(args.steps, 20), args.warmup)
 
     # ---- per-kernel device time (library's own CUDA events on the launch stream), separate pass
+    trace("per-kernel times")
     rec.set_timing(True)
     stage = {"decode_ms": 0.0, "assembly_ms": 0.0, "solve_ms": 0.0, "output_ms": 0.0}
     reps = max(3, min(args.steps, 10))
@@ -618,6 +626,7 @@ def main():
     rec.set_timing(False)
 
     # ---- end to end through the host-buffer calls: host coefficients in, host vertices out, wall clock
+    trace("end to end (host buffers)")
     def e2e(fn):
         for _ in range(args.warmup):
             fn()
@@ -663,6 +672,7 @@ def main():
         row_b = N_FREE * 12
         for key, mode, expand in (("all_gather_free_rows", "all", False), ("all_gather_expanded", "all", True),
                                   ("gather_to_rank0_free_rows", "root", False)):
+            trace("gather leg " + key)
             pipe = sharded.GatherPipeline(rec, chunk_frames=148 * 128, mode=mode, dst=0, expand=expand)
             rows = N_VERTS if expand else N_FREE
             g_out = (torch.empty((world * n, rows, 3), dtype=torch.float32, device=dev)
@@ -682,6 +692,7 @@ def main():
             torch.cuda.empty_cache()
         # the same gather with our own data path: symmetric memory + peer-to-peer pushes on a side stream (no NCCL kernel)
         for key, mode in (("p2p_all_gather_free_rows", "all"), ("p2p_gather_to_rank0_free_rows", "root")):
+            trace("gather leg " + key)
             try:
                 pg = sharded.PeerGather(rec, n, chunk_frames=148 * 128, mode=mode, dst=0)
             except Exception as ex:                      # no peer mapping on this box: the NCCL numbers above stand
@@ -704,6 +715,7 @@ def main():
                              "receiver; at N = 8 the all-gather needs 7 x 1.14 GB per GPU and step in each direction "
                              "(900 GB/s per direction => 8.9 ms against 5.3 ms of kernels); the kernels overlap on the main stream")
 
+    trace("multi-rank part done")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
