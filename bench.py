@@ -23,6 +23,7 @@ ranks with no data-path collective ("weak": per-GPU batch fixed).
 """
 import argparse
 import importlib.util
+import gc
 import json
 import os
 import sys
@@ -688,7 +689,7 @@ def main():
                 # the gathered + expanded frames of rank r are this rank's timed output when r == rank
                 mine = g_out[rank * n + torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
                 gather[key]["equals_local_output"] = bool(np.array_equal(mine, out_samples))
-            del g_out, pipe
+            del g_out, pipe, step                  # (the closure's defaults hold both buffers as well)
             torch.cuda.empty_cache()
         # the same gather with our own data path: symmetric memory + peer-to-peer pushes on a side stream (no NCCL kernel)
         for key, mode in (("p2p_all_gather_free_rows", "all"), ("p2p_gather_to_rank0_free_rows", "root")):
@@ -697,6 +698,7 @@ def main():
                 pg = sharded.PeerGather(rec, n, chunk_frames=148 * 128, mode=mode, dst=0)
             except Exception as ex:                      # no peer mapping on this box: the NCCL numbers above stand
                 gather[key] = {"unavailable": str(ex)[:200]}
+                barrier()                                # (the same barrier the other branch ends with)
                 continue
 
             def step(pg=pg):
@@ -709,8 +711,10 @@ def main():
             if mode == "all":
                 mine = pg.buf[rank * n + torch.from_numpy(sample_ids).to(dev)].cpu().numpy()
                 gather[key]["equals_local_output"] = bool(np.array_equal(mine, out_samples[:, rec.free_vertices]))
-            del pg
+            del pg, step                           # the closure's default holds the symmetric buffer and its peer mappings
+            gc.collect()
             torch.cuda.empty_cache()
+            barrier()                              # every rank has let go of the symmetric memory before anyone moves on (or exits)
         gather["limiter"] = ("NVLink: (N-1)/N of every frame's free rows (15 132 B) leave each sender N-1 times and arrive at each "
                              "receiver; at N = 8 the all-gather needs 7 x 1.14 GB per GPU and step in each direction "
                              "(900 GB/s per direction => 8.9 ms against 5.3 ms of kernels); the kernels overlap on the main stream")
