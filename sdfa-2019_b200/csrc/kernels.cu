@@ -609,7 +609,7 @@ __device__ __forceinline__ void ag_mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <int AG_STAGES>
 __global__ void __launch_bounds__(ASM_THREADS, 1) k_assemble_gather3(AsmParams P, const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(128) float acc[];                    // [row][3][64], frame pairing (l, l + 32)
+    extern __shared__ __align__(16) float acc[];                     // [row][3][64], frame pairing (l, l + 32)
     constexpr int CT = COMPACT_TILE;
     const int4 blk = P.blocks[blockIdx.x];
     const int n_rows = blk.w - blk.z;

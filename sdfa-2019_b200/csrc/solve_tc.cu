@@ -76,12 +76,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor (same encoding as decode_tc.cu)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
-    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
-    return ((uint64_t)hi << 32) | lo;
-}
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, K = 8 (A: lane = row, 8 consecutive 32-bit columns)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
